@@ -1,0 +1,590 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues.  D[M,N] = A[M,K] * B[N,K]^T.
+//
+// One persistent, warp-specialised kernel (256 threads, 1 CTA / SM):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages x (A 16 KB + B 32 KB))
+//   warp 1   : MMA issuer    (one lane issues tcgen05.mma kind::f16, 128x256x16, accumulators in TMEM)
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
+//   warps 4-7: epilogue      (tcgen05.ld -> registers -> fused math -> smem transpose -> coalesced global I/O)
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static persistent tile loop.
+// Operand majors: K-major (fwd), K-major x MN-major (dgrad: B = W[N_red][K_out]), MN x MN (wgrad: reduction over tokens).
+// Split precision (bf16x3): the k-loop is run over up to three (A part, B part) pairs hi*hi, lo*hi, hi*lo into the
+// same TMEM accumulator, giving fp32-class products from the bf16 tensor pipe.
+//
+// Replaces: every nn.Linear forward/backward GEMM on the reference hot path (see include/clipdlm.h).
+#include "common.cuh"
+#include "../../include/clipdlm.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace clipdlm {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16384
+constexpr int B_STAGE_BYTES = BN * BK * 2;          // 32768
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int STG_PITCH = 144;                      // bytes per staged row (128 B payload + 16 B pad: conflict-free 16 B accesses)
+constexpr int STG_WARP_BYTES = 32 * STG_PITCH;      // 4608
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;
+
+struct GemmArgs {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, k_splits, kb_per_split, kb_total;
+  int nparts;
+  int part_a[3], part_b[3];  // 0 = hi map, 1 = lo map
+  int gather_len;            // A gather (3-D tensor map) if > 0
+  uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides (bytes)
+  // epilogue
+  __nv_bfloat16 *out_hi, *out_lo, *out2_hi, *out2_lo;
+  float* out_f32;
+  long long ldo;
+  const float* bias;
+  const __nv_bfloat16 *res_hi, *res_lo;
+  long long ldr;
+  const __nv_bfloat16 *u_hi, *u_lo;
+  long long ldu;
+  int scatter_len, scatter_stride;
+  DropoutCfg drop;
+  float* part_max;
+  float* part_sum;
+  int* part_arg;
+  float* tgt_logit;
+  const int* targets;
+  int tgt_period;
+  const float* lse;
+  float grad_scale;
+};
+
+__device__ __forceinline__ long long map_row(const GemmArgs& g, int m) {
+  return g.scatter_len > 0 ? (long long)(m / g.scatter_len) * g.scatter_stride + (m % g.scatter_len) : (long long)m;
+}
+
+// ---- per-warp smem transposes: thread-owns-row <-> coalesced global access --------------------------------------
+// bf16 tile 32 rows x 32 cols. Coalesced side: lane l handles row (l>>2)+8j, 16-byte piece (l&3).
+__device__ __forceinline__ void tile_load_bf16(const GemmArgs& g, const __nv_bfloat16* base, long long ld, int row_base, int n0,
+                                               uint8_t* stg, float (&r)[32], bool accumulate) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rr = (lane >> 2) + 8 * j;
+    const int m = row_base + rr;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (m < g.M) val = __ldg(reinterpret_cast<const uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8));
+    *reinterpret_cast<uint4*>(stg + rr * STG_PITCH + (lane & 3) * 16) = val;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 x = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + i * 16);
+    float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
+    if (accumulate) {
+      r[i * 8 + 0] += a.x; r[i * 8 + 1] += a.y; r[i * 8 + 2] += b.x; r[i * 8 + 3] += b.y;
+      r[i * 8 + 4] += c.x; r[i * 8 + 5] += c.y; r[i * 8 + 6] += d.x; r[i * 8 + 7] += d.y;
+    } else {
+      r[i * 8 + 0] = a.x; r[i * 8 + 1] = a.y; r[i * 8 + 2] = b.x; r[i * 8 + 3] = b.y;
+      r[i * 8 + 4] = c.x; r[i * 8 + 5] = c.y; r[i * 8 + 6] = d.x; r[i * 8 + 7] = d.y;
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tile_load_pair(const GemmArgs& g, const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long ld,
+                                               int row_base, int n0, uint8_t* stg, float (&r)[32]) {
+  tile_load_bf16(g, hi, ld, row_base, n0, stg, r, false);
+  if (lo != nullptr) tile_load_bf16(g, lo, ld, row_base, n0, stg, r, true);
+}
+__device__ __forceinline__ void tile_store_bf16(const GemmArgs& g, __nv_bfloat16* base, long long ld, int row_base, int n0,
+                                                uint8_t* stg, const float (&v)[32]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 x;
+    x.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]); x.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    x.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); x.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + i * 16) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rr = (lane >> 2) + 8 * j;
+    const int m = row_base + rr;
+    if (m < g.M)
+      *reinterpret_cast<uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8) =
+          *reinterpret_cast<const uint4*>(stg + rr * STG_PITCH + (lane & 3) * 16);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tile_store_pair(const GemmArgs& g, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld, int row_base,
+                                                int n0, uint8_t* stg, const float (&v)[32]) {
+  tile_store_bf16(g, hi, ld, row_base, n0, stg, v);
+  if (lo != nullptr) {
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = v[i] - bf16_round(v[i]);
+    tile_store_bf16(g, lo, ld, row_base, n0, stg, r);
+  }
+}
+// fp32 tile 32 rows x 32 cols (128 B per row). Coalesced side: lane l handles row (l>>3)+4j, 16-byte piece (l&7).
+template <bool RED>
+__device__ __forceinline__ void tile_store_f32(const GemmArgs& g, float* base, long long ld, int row_base, int n0, uint8_t* stg,
+                                               const float (&v)[32]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(stg + lane * STG_PITCH + i * 16) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rr = (lane >> 3) + 4 * j;
+    const int m = row_base + rr;
+    if (m < g.M) {
+      const float4 x = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + (lane & 7) * 16);
+      float* dst = base + map_row(g, m) * ld + n0 + (lane & 7) * 4;
+      if (RED) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = x;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int AMAJ, int BMAJ, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+            const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(staging + 4 * STG_WARP_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + BN * 4);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = g.num_m_tiles * g.num_n_tiles * g.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB0);
+    if (g.nparts > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int split = w % g.k_splits;
+        const int tile = w / g.k_splits;
+        const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.kb_total);
+        for (int part = 0; part < g.nparts; ++part) {
+          const CUtensorMap* ta = g.part_a[part] ? &tmA1 : &tmA0;
+          const CUtensorMap* tb = g.part_b[part] ? &tmB1 : &tmB0;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stages + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (AMAJ == 0) {
+              if (g.gather_len > 0) tma_load_3d(sa, ta, &full_bar[stage], kb * BK, 0, m_blk * (BM / g.gather_len));
+              else tma_load_2d(sa, ta, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ta, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+            }
+            if (BMAJ == 0) {
+              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, tb, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, AMAJ, BMAJ);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int split = w % g.k_splits;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(kb0 + g.kb_per_split, g.kb_total);
+        const int iters = (kb1 - kb0) * g.nparts;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = AMAJ == 0 ? make_smem_desc_sw128(sa, 16, 1024) : make_smem_desc_sw128(sa, g.mn_lbo, g.mn_sbo);
+          const uint64_t bdesc = BMAJ == 0 ? make_smem_desc_sw128(sb, 16, 1024) : make_smem_desc_sw128(sb, g.mn_lbo, g.mn_sbo);
+          constexpr uint32_t a_step = (AMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;  // K advance per MMA, 16-byte units
+          constexpr uint32_t b_step = (BMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);       // accumulator ready for the epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    uint8_t* stg = staging + q * STG_WARP_BYTES;
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int tile = w / g.k_splits;
+      const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
+      const int row_base = m_blk * BM + q * 32;
+      const int m = row_base + lane;
+
+      if (EPI == CLIPDLM_EPI_STORE && g.bias != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers done
+        for (int i = threadIdx.x - 128; i < BN; i += 128) {
+          const int n = n_blk * BN + i;
+          sbias[i] = n < g.N ? g.bias[n] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+      if (EPI == CLIPDLM_EPI_LSE) {
+        float mx = -INFINITY, sum = 0.f; int arg = 0;
+        const int tgt = (m < g.M) ? g.targets[m % g.tgt_period] : -1;
+        float tl = 0.f; bool has_t = false;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= g.N) break;
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          const float prev_max = mx;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = (n0 + j) < g.N;
+            const float x = ok ? v[j] : -INFINITY;
+            v[j] = x;
+            if (x > mx) { mx = x; arg = n0 + j; }  // strict '>' keeps the first maximum (torch.argmax tie rule)
+            if (n0 + j == tgt) { tl = x; has_t = true; }
+          }
+          // online softmax: rescale the running sum from prev_max to the new max (chunk has >= 1 valid column)
+          float csum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) csum += __expf(v[j] - mx);
+          sum = sum * __expf(prev_max - mx) + csum;
+        }
+        if (m < g.M) {
+          g.part_max[(size_t)n_blk * g.M + m] = mx;
+          g.part_sum[(size_t)n_blk * g.M + m] = sum;
+          g.part_arg[(size_t)n_blk * g.M + m] = arg;
+          if (has_t) g.tgt_logit[m] = tl;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (EPI != CLIPDLM_EPI_SMGRAD && n0 >= g.N) break;
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if (EPI == CLIPDLM_EPI_WGRAD) {
+            tile_store_f32<true>(g, g.out_f32, g.ldo, row_base, n0, stg, v);
+          } else if (EPI == CLIPDLM_EPI_SMGRAD) {
+            const int tgt = (m < g.M) ? g.targets[m % g.tgt_period] : -1;
+            const float l = (m < g.M) ? g.lse[m] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              float p = (n < g.N) ? __expf(v[j] - l) : 0.f;
+              if (n == tgt) p -= 1.f;
+              v[j] = p * g.grad_scale;
+            }
+            tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
+          } else {  // STORE
+            if (g.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += sbias[c * 32 + j];
+            }
+            if (g.drop.thresh16 != 0) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const unsigned long long idx = (unsigned long long)m * (unsigned long long)g.N + (unsigned long long)(n0 + j8 * 8);
+                const uint32_t keep = dropout_keep8(g.drop, idx >> 3);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = ((keep >> i) & 1u) ? v[j8 * 8 + i] * g.drop.scale : 0.f;
+              }
+            }
+            if (g.u_hi != nullptr) {
+              float u[32];
+              tile_load_pair(g, g.u_hi, g.u_lo, g.ldu, row_base, n0, stg, u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= dgelu_f(u[j]);
+            }
+            if (g.res_hi != nullptr) {
+              float r[32];
+              tile_load_pair(g, g.res_hi, g.res_lo, g.ldr, row_base, n0, stg, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += r[j];
+            }
+            if (g.out_hi != nullptr) tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
+            if (g.out_f32 != nullptr) tile_store_f32<false>(g, g.out_f32, g.ldo, row_base, n0, stg, v);
+            if (g.out2_hi != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+              tile_store_pair(g, g.out2_hi, g.out2_lo, g.ldo, row_base, n0, stg, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// LSE partial combine: one thread per row, tiles scanned in order (lowest tile wins argmax ties).
+// ------------------------------------------------------------------------------------------------
+__global__ void lse_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const int* __restrict__ parg,
+                                   int n_tiles, int M, const float* __restrict__ tgt_logit, float* __restrict__ lse,
+                                   int* __restrict__ argmax, double* loss_acc, double scale) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f;
+  if (m < M) {
+    float mx = -INFINITY; int arg = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const float v = pmax[(size_t)t * M + m];
+      if (v > mx) { mx = v; arg = parg[(size_t)t * M + m]; }
+    }
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += psum[(size_t)t * M + m] * __expf(pmax[(size_t)t * M + m] - mx);
+    const float l = mx + logf(s);
+    if (lse != nullptr) lse[m] = l;
+    if (argmax != nullptr) argmax[m] = arg;
+    if (tgt_logit != nullptr) loss = l - tgt_logit[m];
+  }
+  if (loss_acc != nullptr) {
+    loss = warp_sum(loss);
+    __shared__ float wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += (double)wsum[i];
+      atomicAdd(loss_acc, t * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 2-D / 3-D bf16 tensor map with 128-byte swizzle. dims/strides innermost first; strides in bytes for dims 1..rank-1.
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  auto fn = get_encode_fn();
+  CLIPDLM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CLIPDLM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu box %u %u stride %llu base %p)",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1],
+                (unsigned long long)strides_bytes[0], base);
+  return 0;
+}
+
+// Operand map. major 0: stored [rows][K] pitch ld -> dims {K, rows}, box {64, tile_rows}.
+//              major 1: stored [K][rows] pitch ld -> dims {rows, K}, box {64, 64}.
+static int operand_map(CUtensorMap* tm, const void* base, int major, int rows, int K, long long ld, int tile_rows, int gather_len,
+                       int gather_stride) {
+  CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base %p not 16-byte aligned", base);
+  CLIPDLM_CHECK((ld * 2) % 16 == 0, "GEMM operand pitch %lld elements not a multiple of 8", ld);
+  if (major == 0) {
+    if (gather_len > 0) {
+      CLIPDLM_CHECK(tile_rows % gather_len == 0 && rows % gather_len == 0, "gather_len %d must divide %d and M %d", gather_len,
+                    tile_rows, rows);
+      uint64_t dims[3] = {(uint64_t)K, (uint64_t)gather_len, (uint64_t)(rows / gather_len)};
+      uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)gather_stride};
+      uint32_t box[3] = {64, (uint32_t)gather_len, (uint32_t)(tile_rows / gather_len)};
+      return encode_map(tm, base, 3, dims, str, box);
+    }
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {64, (uint32_t)tile_rows};
+    return encode_map(tm, base, 2, dims, str, box);
+  }
+  CLIPDLM_CHECK(gather_len == 0, "gather is only supported for K-major A");
+  uint64_t dims[2] = {(uint64_t)rows, (uint64_t)K};
+  uint64_t str[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {64, 64};
+  return encode_map(tm, base, 2, dims, str, box);
+}
+
+static uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0;
+static int g_num_sms = 0;
+
+template <int AMAJ, int BMAJ, int EPI>
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
+                       int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kfn = gemm_kernel<AMAJ, BMAJ, EPI>;
+  if (!attr_set) {
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  kfn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a0, a1, b0, b1, ga);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
+  CLIPDLM_CHECK(g != nullptr, "null gemm descriptor");
+  CLIPDLM_CHECK(g->M > 0 && g->N > 0 && g->K > 0, "bad GEMM shape %d %d %d", g->M, g->N, g->K);
+  CLIPDLM_CHECK(g->a_hi && g->b_hi, "null GEMM operand");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CLIPDLM_CUDA_OK(cudaGetDevice(&dev));
+    CLIPDLM_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap a0, a1, b0, b1;
+  int rc;
+  if ((rc = operand_map(&a0, g->a_hi, g->a_major, g->M, g->K, g->lda, BM, g->gather_len, g->gather_stride))) return rc;
+  if ((rc = operand_map(&b0, g->b_hi, g->b_major, g->N, g->K, g->ldb, BN, 0, 0))) return rc;
+  a1 = a0; b1 = b0;
+  if (g->a_lo && (rc = operand_map(&a1, g->a_lo, g->a_major, g->M, g->K, g->lda, BM, g->gather_len, g->gather_stride))) return rc;
+  if (g->b_lo && (rc = operand_map(&b1, g->b_lo, g->b_major, g->N, g->K, g->ldb, BN, 0, 0))) return rc;
+
+  GemmArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.M = g->M; ga.N = g->N; ga.K = g->K;
+  ga.num_m_tiles = (g->M + BM - 1) / BM;
+  ga.num_n_tiles = (g->N + BN - 1) / BN;
+  ga.kb_total = (g->K + BK - 1) / BK;
+  ga.k_splits = 1;
+  if (g->epilogue == CLIPDLM_EPI_WGRAD) {
+    int tiles = ga.num_m_tiles * ga.num_n_tiles;
+    int ks = g->k_splits;
+    if (ks <= 0) {
+      ks = (2 * g_num_sms + tiles - 1) / tiles;
+      int max_ks = ga.kb_total / 16;
+      if (ks > max_ks) ks = max_ks;
+      if (ks < 1) ks = 1;
+    }
+    if (ks > ga.kb_total) ks = ga.kb_total;
+    ga.kb_per_split = (ga.kb_total + ks - 1) / ks;
+    ga.k_splits = (ga.kb_total + ga.kb_per_split - 1) / ga.kb_per_split;
+  } else {
+    ga.kb_per_split = ga.kb_total;
+  }
+  ga.nparts = 1; ga.part_a[0] = 0; ga.part_b[0] = 0;
+  if (g->a_lo) { ga.part_a[ga.nparts] = 1; ga.part_b[ga.nparts] = 0; ga.nparts++; }
+  if (g->b_lo) { ga.part_a[ga.nparts] = 0; ga.part_b[ga.nparts] = 1; ga.nparts++; }
+  ga.gather_len = g->gather_len;
+  ga.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192;
+  ga.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
+  ga.out_hi = (__nv_bfloat16*)g->out_hi; ga.out_lo = (__nv_bfloat16*)g->out_lo;
+  ga.out2_hi = (__nv_bfloat16*)g->out2_hi; ga.out2_lo = (__nv_bfloat16*)g->out2_lo;
+  ga.out_f32 = g->epilogue == CLIPDLM_EPI_WGRAD ? g->acc_f32 : g->out_f32;
+  ga.ldo = g->ldo;
+  ga.bias = g->bias;
+  ga.res_hi = (const __nv_bfloat16*)g->res_hi; ga.res_lo = (const __nv_bfloat16*)g->res_lo; ga.ldr = g->ldr;
+  ga.u_hi = (const __nv_bfloat16*)g->u_hi; ga.u_lo = (const __nv_bfloat16*)g->u_lo; ga.ldu = g->ldu;
+  ga.scatter_len = g->scatter_len; ga.scatter_stride = g->scatter_stride;
+  ga.drop.seed = g->drop_seed; ga.drop.site = g->drop_site;
+  ga.drop.thresh16 = g->drop_p > 0.f ? (uint32_t)(g->drop_p * 65536.f + 0.5f) : 0u;
+  ga.drop.scale = g->drop_p > 0.f ? 1.f / (1.f - g->drop_p) : 1.f;
+  ga.part_max = g->part_max; ga.part_sum = g->part_sum; ga.part_arg = g->part_arg; ga.tgt_logit = g->tgt_logit;
+  ga.targets = g->targets; ga.tgt_period = g->tgt_period > 0 ? g->tgt_period : 1;
+  ga.lse = g->lse; ga.grad_scale = g->grad_scale;
+
+  const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+
+  switch (g->epilogue) {
+    case CLIPDLM_EPI_STORE:
+      CLIPDLM_CHECK(g->N % 32 == 0, "STORE epilogue needs N %% 32 == 0 (N = %d)", g->N);
+      CLIPDLM_CHECK(g->out_hi || g->out_f32, "STORE epilogue without output");
+      CLIPDLM_CHECK(g->a_major == 0, "STORE epilogue expects K-major A");
+      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
+    case CLIPDLM_EPI_WGRAD:
+      CLIPDLM_CHECK(g->a_major == 1 && g->b_major == 1, "WGRAD epilogue expects MN-major A and B");
+      CLIPDLM_CHECK(g->N % 32 == 0 && g->acc_f32, "WGRAD needs N %% 32 == 0 and an fp32 accumulator");
+      return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(a0, a1, b0, b1, ga, grid, st);
+    case CLIPDLM_EPI_LSE:
+      CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE epilogue expects K-major operands");
+      CLIPDLM_CHECK(g->part_max && g->part_sum && g->part_arg && g->targets && g->tgt_logit, "LSE epilogue buffers missing");
+      return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(a0, a1, b0, b1, ga, grid, st);
+    case CLIPDLM_EPI_SMGRAD:
+      CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
+      CLIPDLM_CHECK(g->out_hi && g->lse && g->targets, "SMGRAD epilogue buffers missing");
+      CLIPDLM_CHECK(g->ldo >= (long long)ga.num_n_tiles * BN, "SMGRAD output pitch %lld < %d", (long long)g->ldo, ga.num_n_tiles * BN);
+      return launch_gemm<0, 0, CLIPDLM_EPI_SMGRAD>(a0, a1, b0, b1, ga, grid, st);
+    default:
+      CLIPDLM_CHECK(false, "unknown epilogue %d", g->epilogue);
+  }
+  return 0;
+}
+
+int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
+                         int* argmax, double* loss_acc, double scale, cudaStream_t st) {
+  const int threads = 256;
+  lse_combine_kernel<<<(M + threads - 1) / threads, threads, 0, st>>>(pmax, psum, parg, n_tiles, M, tgt_logit, lse, argmax, loss_acc,
+                                                                     scale);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+void gemm_debug_mn_desc(uint32_t lbo, uint32_t sbo) { g_dbg_mn_lbo = lbo; g_dbg_mn_sbo = sbo; }
+
+}  // namespace clipdlm

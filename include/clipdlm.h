@@ -1,0 +1,236 @@
+/* clipdlm.h — C-ABI of libclipdlm.so: the B200 (sm_100a) implementation of the CLIP-Diffusion-LM hot path.
+ *
+ * The reference (xu-shitong/diffusion-image-captioning, CLIP-DDPM.py) has no FFI: its boundary is a set of
+ * Python functions over torch tensors.  Every entry point below therefore cites the reference function (or the
+ * third-party op that function dispatches to) that it replaces; the Python host in
+ * diffusion-image-captioning_b200/ keeps the reference's names/signatures and binds these symbols with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions: plain C types only; every pointer is a DEVICE pointer owned by the caller unless stated; the
+ * library allocates nothing on the hot path (workspace is caller-provided); all work is enqueued on the given
+ * cudaStream_t (passed as void*); return 0 = ok, <0 = error with text in clipdlm_last_error() (thread-local).
+ * "bf16 pair" (hi, lo): lo == NULL means plain bf16 storage; lo != NULL means split storage value = hi + lo
+ * ("bf16x3" precision mode: GEMMs run three tensor-core passes hi*hi + lo*hi + hi*lo, fp32-class accuracy).
+ */
+#ifndef CLIPDLM_H
+#define CLIPDLM_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* clipdlm_stream; /* cudaStream_t */
+
+const char* clipdlm_last_error(void);
+int clipdlm_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM present), else 0; <0 on CUDA error. */
+int clipdlm_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM   D[M,N] = A[M,K] * B[N,K]^T  (bf16 in, fp32 accumulate in TMEM), fused epilogues.
+ * Replaces: nn.Linear forward (HF modeling_distilbert.py:187-189,206,224-226,514; CLIP-DDPM.py:299,323) and the
+ * autograd dgrad / wgrad GEMMs of l.backward() (CLIP-DDPM.py:483).
+ * a_major/b_major: 0 = operand stored row-major [M|N][K] (K contiguous); 1 = stored [K][M|N] (MN contiguous).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum {
+  CLIPDLM_EPI_STORE = 0,  /* out = f(acc): +bias, dropout, +residual, gelu dual-store, *gelu'(u); bf16 pair / f32 */
+  CLIPDLM_EPI_WGRAD = 1,  /* acc_f32[M,N] += acc   (split-K, fp32 red.add) */
+  CLIPDLM_EPI_LSE = 2,    /* per (row, 256-col tile) max / sum-exp / argmax partials + target logit; no logits in HBM */
+  CLIPDLM_EPI_SMGRAD = 3  /* out = (exp(acc - lse[m]) - [n == tgt[m]]) * scale   (softmax-CE gradient, bf16 pair) */
+};
+
+typedef struct clipdlm_gemm {
+  const void* a_hi; const void* a_lo;
+  const void* b_hi; const void* b_lo;
+  int64_t lda, ldb;               /* row pitch in elements of the stored 2-D arrays */
+  int32_t M, N, K;
+  int32_t a_major, b_major;
+  int32_t gather_len, gather_stride; /* >0: logical A row m = stored row (m / len) * stride + m % len  (K-major A only) */
+  int32_t epilogue;
+  int32_t k_splits;               /* WGRAD only; 0 = auto */
+  /* STORE */
+  void* out_hi; void* out_lo; float* out_f32; int64_t ldo;
+  void* out2_hi; void* out2_lo;   /* if set: out = acc+bias (pre-activation), out2 = gelu(out) */
+  const float* bias;              /* [N] or NULL */
+  const void* res_hi; const void* res_lo; int64_t ldr; /* residual (same row mapping as out) or NULL */
+  const void* u_hi; const void* u_lo; int64_t ldu;     /* if set: out = acc * gelu'(u) */
+  int32_t scatter_len, scatter_stride; /* >0: output/residual row = (m / len) * stride + m % len */
+  uint64_t drop_seed; uint32_t drop_site; float drop_p; /* dropout on (acc + bias) before the residual; p = 0 off */
+  /* WGRAD */
+  float* acc_f32;                 /* [M, ldo] fp32, accumulated in place */
+  /* LSE / SMGRAD */
+  float* part_max; float* part_sum; int32_t* part_arg; /* [ceil(N/256)][M] */
+  float* tgt_logit;               /* [M] */
+  const int32_t* targets; int32_t tgt_period; /* target of row m = targets[m % tgt_period] */
+  const float* lse;               /* [M] (SMGRAD) */
+  float grad_scale;               /* SMGRAD */
+} clipdlm_gemm_t;
+
+int clipdlm_gemm(const clipdlm_gemm_t* g, clipdlm_stream stream);
+/* Debug hook for bring-up: override the MN-major smem descriptor strides (bytes); 0,0 restores defaults. */
+void clipdlm_gemm_debug_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes);
+
+/* Reduce LSE partials: lse[m], argmax[m] (may be NULL), and adds sum_m(lse[m] - tgt_logit[m]) * scale to *loss_acc (double).
+ * Replaces softmax -> gather -> log -> sum -> mean (CLIP-DDPM.py:436-437) and softmax/argmax (CLIP-DDPM.py:620). */
+int clipdlm_lse_combine(const float* part_max, const float* part_sum, const int32_t* part_arg, int32_t n_tiles, int32_t M,
+                        const float* tgt_logit, float* lse, int32_t* argmax, double* loss_acc, double scale,
+                        clipdlm_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound kernels
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct clipdlm_bf { void* hi; void* lo; } clipdlm_bf_t;
+
+/* K1-K4: embedding gather + q_sample + CLIP concat/add fusion + segment/position add + embedding LayerNorm (+dropout).
+ * Replaces model.embedding (CLIP-DDPM.py:459), diffuse_t (:347-362), forward's hstack/segment add (:296-307) and HF
+ * Embeddings.forward (modeling_distilbert.py:96-122).
+ * mode 0: x = x_in[r, p, :] (fp32 [R, Ltxt, D]);  mode 1: x = ca[r / B] * E[ids[b, p]] + cb[r / B] * noise[b, p] with b = r % B.
+ * Row r (0..R), position p (0..L): concat: p < Ltxt text, p == Ltxt image proj, p == Ltxt+1 text proj, + seg[p >= Ltxt] + pos[p];
+ * add-fusion (fusion == 1, L == Ltxt): x + img_proj[b] (+ txt_proj[b] if guided) + pos[p].
+ * Writes z (pre-LN) and h (post-LN, post-dropout). */
+typedef struct clipdlm_embed {
+  int32_t R, B, Ltxt, L, D, fusion, mode, guided;
+  const float* x_in;            /* mode 0 */
+  const float* emb_table; const int32_t* ids; const float* noise; const float* coef_a; const float* coef_b; /* mode 1 */
+  const float* img_proj; const float* txt_proj; /* [B, D] fp32 (image_linear / text_linear outputs) */
+  const float* seg; const float* pos;           /* [2, D], [max_pos, D] */
+  const float* ln_w; const float* ln_b; float ln_eps;
+  clipdlm_bf_t z; clipdlm_bf_t h;               /* [R*L, D] */
+  uint64_t drop_seed; uint32_t drop_site; float drop_p;
+} clipdlm_embed_t;
+int clipdlm_embed_fwd(const clipdlm_embed_t* e, clipdlm_stream stream);
+/* Backward of the fusion (after LN bwd produced dz): accumulates d pos [L rows], d seg [2], d img_proj / d txt_proj [B, D] (fp32, +=). */
+int clipdlm_embed_bwd(const clipdlm_bf_t* dz, int32_t R, int32_t B, int32_t Ltxt, int32_t L, int32_t D, int32_t fusion, int32_t guided,
+                      float* d_pos, float* d_seg, float* d_img_proj, float* d_txt_proj, clipdlm_stream stream);
+
+/* LayerNorm over the last dim (HF nn.LayerNorm eps=1e-12; modeling_distilbert.py:120,257,261,516). y = LN(z)*w + b (+dropout). */
+int clipdlm_layernorm_fwd(const clipdlm_bf_t* z, const float* w, const float* b, float eps, int64_t rows, int32_t D,
+                          const clipdlm_bf_t* y, uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream);
+/* dz = LN'(z) applied to dy (dy masked by the output dropout if drop_p_out > 0); dw, db += (fp32 atomics);
+ * optional dz_drop = dz * mask_in / (1 - p_in) (gradient entering a dropout that preceded the residual add). */
+int clipdlm_layernorm_bwd(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, int64_t rows, int32_t D,
+                          const clipdlm_bf_t* dz, float* dw, float* db,
+                          uint64_t drop_seed, uint32_t drop_site_out, float drop_p_out,
+                          const clipdlm_bf_t* dz_drop, uint32_t drop_site_in, float drop_p_in, clipdlm_stream stream);
+
+/* Multi-head self-attention over L <= 128 positions, one warp per (row, head); qkv [R*L, 3*D] (q | k | v).
+ * Replaces DistilBertSelfAttention / sdpa (modeling_distilbert.py:126-151,177-207). keymask[r] bit j = key j visible
+ * (CLIP-DDPM.py:296-297 hstack([mask, 1, 0])); for L > 32 keymask is [R][ceil(L/32)] words. */
+int clipdlm_attn_fwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, int32_t R, int32_t L, int32_t D, int32_t H,
+                     const clipdlm_bf_t* ctx, uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream);
+int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int32_t R, int32_t L, int32_t D,
+                     int32_t H, const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p,
+                     clipdlm_stream stream);
+
+/* Column sums (bias gradients): out[n] += sum_m x[m, n]. */
+int clipdlm_colsum(const clipdlm_bf_t* x, int64_t rows, int32_t N, float* out, clipdlm_stream stream);
+
+/* Embedding-space loss between x_out[:, :Ltxt] and x_0[b] = E[ids[b]] (LOSS_FUNC, CLIP-DDPM.py:77-89,418,428), forward
+ * value added to *loss_acc (double) and gradient written to dx [R*L, D] (rows p >= Ltxt zeroed).
+ * kind: 0 series_sum_sample_mean, 1 series_sum, 2 mse_series_mean, 3 mse_series_sum. batch_size = reference BATCH_SIZE
+ * (divisor of kinds 1 and 3); R_total = rows of the whole pass (divisor of the means) when called per chunk. */
+int clipdlm_embed_loss(const clipdlm_bf_t* x_out, const float* emb_table, const int32_t* ids, int32_t R, int32_t B, int32_t Ltxt,
+                       int32_t L, int32_t D, int32_t kind, int64_t R_total, int32_t batch_size, float weight,
+                       double* loss_acc, const clipdlm_bf_t* dx, clipdlm_stream stream);
+
+/* Small fp32 linear for the CLIP projections (image_linear / text_linear, CLIP-DDPM.py:252-253,299): y[B,N] = x[B,K] W[N,K]^T + b. */
+int clipdlm_small_linear_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t K, int32_t N, float* y,
+                             clipdlm_stream stream);
+/* dW[N,K] += dy^T x ; db[N] += colsum(dy). */
+int clipdlm_small_linear_bwd(const float* x, const float* dy, int32_t B, int32_t K, int32_t N, float* dw, float* db,
+                             clipdlm_stream stream);
+
+/* Flat multi-tensor AdamW (torch.optim.AdamW defaults, decoupled weight decay on every element; CLIP-DDPM.py:335,484),
+ * refreshing the bf16 (pair) shadow copy the GEMMs read. grad_scale multiplies g (1/world_size after a sum all-reduce). */
+int clipdlm_adamw(float* p, const float* g, float* m, float* v, void* shadow_hi, void* shadow_lo, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                  clipdlm_stream stream);
+/* fp32 -> bf16 (pair) conversion (weights shadow refresh, frozen embedding table). */
+int clipdlm_to_bf16(const float* x, void* hi, void* lo, int64_t n, clipdlm_stream stream);
+/* bf16 (pair) -> fp32. */
+int clipdlm_to_f32(const void* hi, const void* lo, float* y, int64_t n, clipdlm_stream stream);
+/* y[r, :] = x[(r / len) * stride + r % len, :] gather of the first `len` of every `stride` rows, to fp32. */
+int clipdlm_gather_rows_f32(const clipdlm_bf_t* x, int64_t rows_out, int32_t len, int32_t stride, int32_t D, float* y,
+                            clipdlm_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine: the composite hot path (model forward / loss+backward / denoise step) orchestrated natively.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct clipdlm_config {
+  int32_t n_layers, dim, n_heads, hidden_dim, vocab, max_len, clip_dim, max_pos;
+  int32_t fusion;     /* 0 = "concat", 1 = "add"  (CLIP_ADDING_METHOD, CLIP-DDPM.py:93-94) */
+  int32_t precision;  /* 0 = bf16 tensor-core passes, 1 = split bf16x3 (parity mode) */
+  float ln_eps;       /* 1e-12 */
+  float dropout, attn_dropout; /* DistilBertConfig defaults 0.1 / 0.1 */
+} clipdlm_config_t;
+
+typedef struct clipdlm_engine clipdlm_engine_t;
+
+/* Flat parameter layout (fp32 master / grads / Adam moments / bf16 shadows share it). Slot ids below;
+ * per-layer slots are CLIPDLM_P_LAYER0 + layer * CLIPDLM_P_PER_LAYER + k. */
+enum {
+  CLIPDLM_P_POS = 0, CLIPDLM_P_EMB_LN_W, CLIPDLM_P_EMB_LN_B, CLIPDLM_P_VT_W, CLIPDLM_P_VT_B, CLIPDLM_P_VLN_W, CLIPDLM_P_VLN_B,
+  CLIPDLM_P_IMG_W, CLIPDLM_P_IMG_B, CLIPDLM_P_TXT_W, CLIPDLM_P_TXT_B, CLIPDLM_P_SEG, CLIPDLM_P_LAYER0,
+  /* per layer: */
+  CLIPDLM_PL_QKV_W = 0, CLIPDLM_PL_QKV_B, CLIPDLM_PL_O_W, CLIPDLM_PL_O_B, CLIPDLM_PL_LN1_W, CLIPDLM_PL_LN1_B,
+  CLIPDLM_PL_FF1_W, CLIPDLM_PL_FF1_B, CLIPDLM_PL_FF2_W, CLIPDLM_PL_FF2_B, CLIPDLM_PL_LN2_W, CLIPDLM_PL_LN2_B, CLIPDLM_P_PER_LAYER
+};
+int64_t clipdlm_param_count(const clipdlm_config_t* cfg);                 /* total fp32 elements of the flat buffer */
+int64_t clipdlm_param_offset(const clipdlm_config_t* cfg, int32_t slot);  /* element offset of a slot, <0 if invalid */
+int64_t clipdlm_param_size(const clipdlm_config_t* cfg, int32_t slot);
+
+size_t clipdlm_workspace_bytes(const clipdlm_config_t* cfg, int32_t max_rows, int32_t batch, int32_t training);
+
+typedef struct clipdlm_buffers {
+  float* params;            /* flat fp32 master weights (trainable; reference model.parameters(), CLIP-DDPM.py:258-269) */
+  float* grads;             /* flat fp32 gradients (accumulated) */
+  void* shadow_hi; void* shadow_lo;   /* flat bf16 (pair) copy of params */
+  const float* emb_table;   /* frozen E [vocab, dim] fp32 (model.embedding, CLIP-DDPM.py:245) */
+  void* emb_hi; void* emb_lo;         /* bf16 (pair) copy of the frozen lm_head weight [vocab, dim] (CLIP-DDPM.py:246) */
+  void* workspace; size_t workspace_bytes;
+} clipdlm_buffers_t;
+
+clipdlm_engine_t* clipdlm_engine_create(const clipdlm_config_t* cfg, const clipdlm_buffers_t* bufs, int32_t max_rows, int32_t batch,
+                                        int32_t training);
+void clipdlm_engine_destroy(clipdlm_engine_t* e);
+
+/* One encoder pass over R rows (R <= max_rows), = DistilBertModel.forward without the lm_head (CLIP-DDPM.py:271-322).
+ * Inputs as clipdlm_embed_t mode 0/1 (x_in XOR ids+noise+coef); image_clip/text_clip are [B, clip_dim] fp32 with row r using
+ * caption r % B; attn_mask [B, max_len] int32 (0/1); guided = concat_mask[:,1] (uniform over rows).
+ * train = 1 enables dropout and keeps activations for clipdlm_engine_backward. x_out (fp32 [R, L, D]) may be NULL. */
+typedef struct clipdlm_pass {
+  int32_t R, B, mode, guided, train;
+  const float* x_in;
+  const int32_t* ids; const float* noise; const float* coef_a; const float* coef_b;
+  const float* image_clip; const float* text_clip; const int32_t* attn_mask;
+  uint64_t drop_seed;
+  float* x_out;
+} clipdlm_pass_t;
+int clipdlm_engine_forward(clipdlm_engine_t* e, const clipdlm_pass_t* p, clipdlm_stream stream);
+
+/* lm_head over x_out[:, :max_len] of the last forward: logits fp32 [R*max_len, vocab] (may be NULL) and/or argmax ids
+ * int32 [R*max_len] (may be NULL). Replaces self.lm_head(x_out[:, :MAX_LENGTH]) and argmax (CLIP-DDPM.py:323,620). */
+int clipdlm_engine_lm_head(clipdlm_engine_t* e, float* logits, int32_t* argmax, clipdlm_stream stream);
+
+/* Loss of the last forward + full backward into bufs.grads (+=). Adds to losses[0] (embedding loss) and losses[1]
+ * (cross-entropy, unweighted) as doubles. Row means use R_total (rows of the whole pass when chunked).
+ * Replaces loss() terms (CLIP-DDPM.py:415-437) and l.backward() (:483) for the rows of this pass. */
+typedef struct clipdlm_loss_cfg {
+  int32_t loss_kind;      /* LOSS_FUNC id, see clipdlm_embed_loss */
+  int32_t use_embed_loss; /* USE_X_T_LOSS / USE_X_1_LOSS */
+  int32_t use_prob_loss;  /* USE_PROB_LOSS */
+  int32_t batch_size;     /* BATCH_SIZE */
+  int64_t R_total;
+  float rounding_weight;  /* ROUNDING_WEIGHT */
+  int32_t backward;       /* 0 = losses only (validate, CLIP-DDPM.py:488-501) */
+} clipdlm_loss_cfg_t;
+int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* lc, double* losses, clipdlm_stream stream);
+
+/* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */
+int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPDLM_H */
