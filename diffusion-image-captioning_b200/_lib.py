@@ -45,7 +45,7 @@ class Gemm(C.Structure):
 class Embed(C.Structure):
     _fields_ = [
         ("R", i32), ("B", i32), ("Ltxt", i32), ("L", i32), ("D", i32), ("fusion", i32), ("mode", i32), ("guided", i32),
-        ("x_in", c_p),
+        ("x_in", c_p), ("x_in_stride", i64),
         ("emb_table", c_p), ("ids", c_p), ("noise", c_p), ("coef_a", c_p), ("coef_b", c_p),
         ("img_proj", c_p), ("txt_proj", c_p),
         ("seg", c_p), ("pos", c_p),
@@ -75,7 +75,7 @@ class Buffers(C.Structure):
 class Pass(C.Structure):
     _fields_ = [
         ("R", i32), ("B", i32), ("mode", i32), ("guided", i32), ("train", i32),
-        ("x_in", c_p),
+        ("x_in", c_p), ("x_in_stride", i64),
         ("ids", c_p), ("noise", c_p), ("coef_a", c_p), ("coef_b", c_p),
         ("image_clip", c_p), ("text_clip", c_p), ("attn_mask", c_p),
         ("drop_seed", u64),
@@ -88,6 +88,7 @@ class LossCfg(C.Structure):
         ("loss_kind", i32), ("use_embed_loss", i32), ("use_prob_loss", i32), ("batch_size", i32),
         ("R_total", i64),
         ("rounding_weight", f32), ("backward", i32),
+        ("target", c_p), ("target_rows", i32),
     ]
 
 
@@ -108,20 +109,22 @@ _SIGS = {
     "clipdlm_lse_combine": (C.c_int, [c_p, c_p, c_p, i32, i32, c_p, c_p, c_p, c_p, f64, c_p]),
     "clipdlm_embed_fwd": (C.c_int, [C.POINTER(Embed), c_p]),
     "clipdlm_embed_bwd": (C.c_int, [C.POINTER(Bf), i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p, c_p, c_p]),
-    "clipdlm_layernorm_fwd": (C.c_int, [C.POINTER(Bf), c_p, c_p, f32, i64, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
+    "clipdlm_layernorm_fwd": (C.c_int, [C.POINTER(Bf), c_p, c_p, f32, i64, i32, C.POINTER(Bf), c_p, u64, u32, f32, c_p]),
     "clipdlm_layernorm_bwd": (C.c_int, [C.POINTER(Bf), C.POINTER(Bf), c_p, f32, i64, i32, C.POINTER(Bf), c_p, c_p,
-                                        u64, u32, f32, C.POINTER(Bf), u32, f32, c_p]),
+                                        u64, u32, f32, C.POINTER(Bf), u32, f32, C.POINTER(Bf), c_p, c_p]),
     "clipdlm_attn_fwd": (C.c_int, [C.POINTER(Bf), c_p, i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
     "clipdlm_attn_bwd": (C.c_int, [C.POINTER(Bf), c_p, C.POINTER(Bf), i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
     "clipdlm_colsum": (C.c_int, [C.POINTER(Bf), i64, i32, c_p, c_p]),
-    "clipdlm_embed_loss": (C.c_int, [C.POINTER(Bf), c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p,
+    "clipdlm_embed_loss": (C.c_int, [C.POINTER(Bf), c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p,
                                      C.POINTER(Bf), c_p]),
     "clipdlm_small_linear_fwd": (C.c_int, [c_p, c_p, c_p, i32, i32, i32, c_p, c_p]),
     "clipdlm_small_linear_bwd": (C.c_int, [c_p, c_p, i32, i32, i32, c_p, c_p, c_p]),
-    "clipdlm_adamw": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, f32, c_p]),
+    "clipdlm_adamw": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, f32, i32, c_p]),
     "clipdlm_to_bf16": (C.c_int, [c_p, c_p, c_p, i64, c_p]),
     "clipdlm_to_f32": (C.c_int, [c_p, c_p, c_p, i64, c_p]),
     "clipdlm_gather_rows_f32": (C.c_int, [C.POINTER(Bf), i64, i32, i32, i32, c_p, c_p]),
+    "clipdlm_q_sample": (C.c_int, [c_p, c_p, c_p, c_p, i64, i32, c_p, c_p]),
+    "clipdlm_keymask": (C.c_int, [c_p, i32, i32, i32, i32, i32, i32, c_p, c_p]),
     "clipdlm_param_count": (i64, [C.POINTER(Config)]),
     "clipdlm_param_offset": (i64, [C.POINTER(Config), i32]),
     "clipdlm_param_size": (i64, [C.POINTER(Config), i32]),
@@ -129,7 +132,7 @@ _SIGS = {
     "clipdlm_engine_create": (c_p, [C.POINTER(Config), C.POINTER(Buffers), i32, i32, i32]),
     "clipdlm_engine_destroy": (None, [c_p]),
     "clipdlm_engine_forward": (C.c_int, [c_p, C.POINTER(Pass), c_p]),
-    "clipdlm_engine_lm_head": (C.c_int, [c_p, c_p, c_p, c_p]),
+    "clipdlm_engine_lm_head": (C.c_int, [c_p, c_p, i64, c_p, c_p]),
     "clipdlm_engine_loss_backward": (C.c_int, [c_p, C.POINTER(LossCfg), c_p, c_p]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
 }

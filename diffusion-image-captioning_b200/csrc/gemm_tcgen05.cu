@@ -280,7 +280,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
       if (EPI == CLIPDLM_EPI_LSE) {
         float mx = -INFINITY, sum = 0.f; int arg = 0;
-        const int tgt = (m < g.M) ? g.targets[m % g.tgt_period] : -1;
+        const int tgt = (m < g.M && g.targets != nullptr) ? g.targets[m % g.tgt_period] : -1;
         float tl = 0.f; bool has_t = false;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -307,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           g.part_max[(size_t)n_blk * g.M + m] = mx;
           g.part_sum[(size_t)n_blk * g.M + m] = sum;
           g.part_arg[(size_t)n_blk * g.M + m] = arg;
-          if (has_t) g.tgt_logit[m] = tl;
+          if (has_t && g.tgt_logit != nullptr) g.tgt_logit[m] = tl;
         }
       } else {
 #pragma unroll 1
@@ -553,7 +553,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   switch (g->epilogue) {
     case CLIPDLM_EPI_STORE:
       CLIPDLM_CHECK(g->N % 32 == 0, "STORE epilogue needs N %% 32 == 0 (N = %d)", g->N);
-      CLIPDLM_CHECK(g->out_hi || g->out_f32, "STORE epilogue without output");
+      CLIPDLM_CHECK(g->out_hi || g->out_f32 || g->out2_hi, "STORE epilogue without output");
       CLIPDLM_CHECK(g->a_major == 0, "STORE epilogue expects K-major A");
       if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
       return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
@@ -563,7 +563,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
       return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_LSE:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE epilogue expects K-major operands");
-      CLIPDLM_CHECK(g->part_max && g->part_sum && g->part_arg && g->targets && g->tgt_logit, "LSE epilogue buffers missing");
+      CLIPDLM_CHECK(g->part_max && g->part_sum && g->part_arg && (!g->targets || g->tgt_logit), "LSE epilogue buffers missing");
       return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");

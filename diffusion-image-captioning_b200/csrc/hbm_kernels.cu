@@ -1,0 +1,769 @@
+// HBM-bound kernels of the clipdlm hot path (sm_100a): everything that is not a GEMM or attention.
+//
+//   embed_fwd / embed_bwd      K1-K4: embedding gather + q_sample + CLIP concat/add fusion + segment/position add + LayerNorm
+//   layernorm_fwd / _bwd       post-LN blocks, MLM-transform LN; bwd fuses dropout masks, gelu', and the bias column sums
+//   colsum                     bias gradients of the wide Linears
+//   embed_loss                 LOSS_FUNC (L1 / L2-norm variants) forward value + gradient in one pass
+//   small_linear fwd/bwd       image_linear / text_linear (512 -> D), evaluated once per caption instead of once per row
+//   adamw                      flat multi-tensor AdamW, refreshes the bf16 (pair) shadow and zeroes the gradient
+//   to_bf16 / to_f32 / gather_rows_f32 / keymask
+//
+// Design rule for all of them: one warp owns one row of D (= NV * 256) elements, every lane moves 16-byte vectors
+// (8 bf16) that are contiguous across the warp (512 B per request), reductions are warp shuffles, cross-row
+// reductions (dw/db/bias grads) are register partials -> shared memory -> one fp32 atomic per column per block.
+#include "common.cuh"
+#include "../../include/clipdlm.h"
+
+namespace clipdlm {
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+DropoutCfg make_drop(unsigned long long seed, uint32_t site, float p) {
+  DropoutCfg d;
+  d.seed = seed; d.site = site;
+  d.thresh16 = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
+  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+
+__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void apply_drop8(const DropoutCfg& d, unsigned long long elem_idx, float (&v)[8]) {
+  const uint32_t keep = dropout_keep8(d, elem_idx >> 3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * d.scale : 0.f;
+}
+
+// mean / rstd of a row held as x[NV][8] per lane (two-pass, fp32)
+template <int NV>
+__device__ __forceinline__ void row_stats(const float (&x)[NV][8], int D, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[v][i];
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = x[v][i] - mean; q += d * d; }
+  rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embed_fwd
+// ------------------------------------------------------------------------------------------------------------------
+struct EmbedArgs {
+  int R, B, Ltxt, L, D, fusion, mode, guided;
+  const float* x_in; long long x_in_stride;
+  const float* emb_table; const int* ids; const float* noise; const float* coef_a; const float* coef_b;
+  const float* img_proj; const float* txt_proj; const float* seg; const float* pos;
+  const float* ln_w; const float* ln_b; float ln_eps;
+  BfPtr z, h;
+  DropoutCfg drop;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const EmbedArgs e) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)e.R * e.L) return;
+  const int r = (int)(row / e.L), p = (int)(row % e.L);
+  const int s = r / e.B, b = r % e.B;
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * 8;
+    float t[8];
+    if (p < e.Ltxt) {
+      if (e.mode == 0) {
+        load8_f32(e.x_in + (long long)r * e.x_in_stride + (long long)p * e.D + c, t);
+      } else {
+        const int id = e.ids[b * e.Ltxt + p];
+        float ev[8], nv[8];
+        load8_f32(e.emb_table + (long long)id * e.D + c, ev);
+        load8_f32(e.noise + ((long long)b * e.Ltxt + p) * e.D + c, nv);
+        const float ca = e.coef_a[s], cb = e.coef_b[s];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = ca * ev[i] + cb * nv[i];
+      }
+      if (e.fusion == 1) {
+        float q[8];
+        load8_f32(e.img_proj + (long long)b * e.D + c, q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += q[i];
+        if (e.guided) {
+          load8_f32(e.txt_proj + (long long)b * e.D + c, q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] += q[i];
+        }
+      }
+    } else {
+      load8_f32((p == e.Ltxt ? e.img_proj : e.txt_proj) + (long long)b * e.D + c, t);
+    }
+    float a[8];
+    if (e.fusion == 0) {
+      load8_f32(e.seg + (p >= e.Ltxt ? e.D : 0) + c, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] += a[i];
+    }
+    load8_f32(e.pos + (long long)p * e.D + c, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[v][i] = t[i] + a[i];
+  }
+  if (e.z.hi != nullptr) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) store8(e.z, (size_t)row * e.D + (v * 32 + lane) * 8, x[v]);
+  }
+  float mean, rstd;
+  row_stats<NV>(x, e.D, e.ln_eps, mean, rstd);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * 8;
+    float w[8], bb[8], y[8];
+    load8_f32(e.ln_w + c, w);
+    load8_f32(e.ln_b + c, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (x[v][i] - mean) * rstd * w[i] + bb[i];
+    if (e.drop.thresh16 != 0) apply_drop8(e.drop, (unsigned long long)row * e.D + c, y);
+    store8(e.h, (size_t)row * e.D + c, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embed_bwd: (1) position / segment gradients, (2) CLIP projection gradients
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_bwd_posseg_kernel(CBfPtr dz, int R, int L, int Ltxt, int D, int fusion, int rows_per_slab,
+                                                               float* d_pos, float* d_seg) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int p = blockIdx.y;
+  const int r0 = blockIdx.z * rows_per_slab;
+  const int r1 = min(R, r0 + rows_per_slab);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0 + warp; r < r1; r += 8) {
+    float v[8];
+    load8(dz, ((size_t)r * L + p) * D + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][t];
+  const int col = blockIdx.x * 256 + t;
+  atomicAdd(d_pos + (size_t)p * D + col, s);
+  if (fusion == 0) atomicAdd(d_seg + (p >= Ltxt ? D : 0) + col, s);
+}
+
+// thread per (b, 8-column vector): sums over the samples s (rows r = s*B + b)
+__global__ void embed_bwd_proj_kernel(CBfPtr dz, int R, int B, int L, int Ltxt, int D, int fusion, int guided, float* d_img, float* d_txt) {
+  const int nvec = D / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * nvec) return;
+  const int b = (int)(idx / nvec), c = (int)(idx % nvec) * 8;
+  const int S = R / B;
+  float ai[8] = {0, 0, 0, 0, 0, 0, 0, 0}, at[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < S; ++s) {
+    const size_t r = (size_t)s * B + b;
+    float v[8];
+    if (fusion == 0) {
+      load8(dz, (r * L + Ltxt) * D + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ai[i] += v[i];
+      load8(dz, (r * L + Ltxt + 1) * D + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) at[i] += v[i];
+    } else {
+      for (int p = 0; p < L; ++p) {
+        load8(dz, (r * L + p) * D + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ai[i] += v[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    d_img[(size_t)b * D + c + i] += ai[i];
+    if (fusion == 0) d_txt[(size_t)b * D + c + i] += at[i];
+    else if (guided) d_txt[(size_t)b * D + c + i] += ai[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm forward
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(CBfPtr z, const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                                            long long rows, int D, BfPtr y, float* y_f32, DropoutCfg drop) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) load8(z, (size_t)row * D + (v * 32 + lane) * 8, x[v]);
+  float mean, rstd;
+  row_stats<NV>(x, D, eps, mean, rstd);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * 8;
+    float ww[8], bb[8], o[8];
+    load8_f32(w + c, ww);
+    load8_f32(b + c, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (x[v][i] - mean) * rstd * ww[i] + bb[i];
+    if (drop.thresh16 != 0) apply_drop8(drop, (unsigned long long)row * D + c, o);
+    if (y.hi != nullptr) store8(y, (size_t)row * D + c, o);
+    if (y_f32 != nullptr) store8_f32(y_f32 + (size_t)row * D + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm backward (+ fused dropout masks, gelu', bias column sums)
+// ------------------------------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  CBfPtr z, dy;
+  const float* w; float eps; long long rows; int D;
+  BfPtr dz;
+  float* dw; float* db;
+  DropoutCfg drop_out;   // dropout that followed this LN's output (mask applied to dy)
+  BfPtr dz_drop;         // optional second output dz * mask_in / (1 - p_in)
+  DropoutCfg drop_in;
+  CBfPtr gelu_u;         // optional: dz *= gelu'(u)   (MLM transform head: z = gelu(u))
+  float* dbias;          // optional: += column sums of (dz_drop if set else dz)   -> bias grad of the producing Linear
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdArgs a) {
+  extern __shared__ float red[];  // [8 warps][D] reused for dw, db, dbias
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  float pdw[NV][8], pdb[NV][8], pbias[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pdw[v][i] = 0.f; pdb[v][i] = 0.f; pbias[v][i] = 0.f; }
+  float wv[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) load8_f32(a.w + (v * 32 + lane) * 8, wv[v]);
+
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < a.rows; row += (long long)gridDim.x * nwarps) {
+    float x[NV][8], g[NV][8];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = (size_t)row * a.D + (v * 32 + lane) * 8;
+      load8(a.z, off, x[v]);
+      load8(a.dy, off, g[v]);
+      if (a.drop_out.thresh16 != 0) apply_drop8(a.drop_out, (unsigned long long)off, g[v]);
+    }
+    float mean, rstd;
+    row_stats<NV>(x, a.D, a.eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (x[v][i] - mean) * rstd;
+        const float gw = g[v][i] * wv[v][i];
+        pdw[v][i] += g[v][i] * xh;
+        pdb[v][i] += g[v][i];
+        s1 += gw; s2 += gw * xh;
+        x[v][i] = xh; g[v][i] = gw;
+      }
+    s1 = warp_sum(s1) / (float)a.D;
+    s2 = warp_sum(s2) / (float)a.D;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = (size_t)row * a.D + (v * 32 + lane) * 8;
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = (g[v][i] - s1 - x[v][i] * s2) * rstd;
+      if (a.gelu_u.hi != nullptr) {
+        float u[8];
+        load8(a.gelu_u, off, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] *= dgelu_f(u[i]);
+      }
+      store8(a.dz, off, d);
+      if (a.dz_drop.hi != nullptr) {
+        apply_drop8(a.drop_in, (unsigned long long)off, d);
+        store8(a.dz_drop, off, d);
+      }
+      if (a.dbias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pbias[v][i] += d[i];
+      }
+    }
+  }
+  // block reduction: three passes through the same [nwarps][D] shared buffer
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? a.dw : (which == 1 ? a.db : a.dbias);
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        red[warp * a.D + (v * 32 + lane) * 8 + i] = which == 0 ? pdw[v][i] : (which == 1 ? pdb[v][i] : pbias[v][i]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.D; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += red[w * a.D + c];
+      atomicAdd(dst + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// colsum
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(CBfPtr x, long long rows, int N, long long rows_per_slab, float* out) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  const long long r1 = min(rows, r0 + rows_per_slab);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    float v[8];
+    load8(x, (size_t)r * N + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+  atomicAdd(out + blockIdx.x * 256 + threadIdx.x, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embed_loss: one block per sequence row r
+// ------------------------------------------------------------------------------------------------------------------
+// target row of (r, p): tgt != NULL ? tgt[(r % tgt_rows), p, :] : emb[ids[r % B, p], :]
+__device__ __forceinline__ const float* loss_target_row(const float* emb, const int* ids, const float* tgt, int tgt_rows, int r, int b, int p,
+                                                        int Ltxt, int D) {
+  if (tgt != nullptr) return tgt + ((size_t)(r % tgt_rows) * Ltxt + p) * D;
+  return emb + (size_t)ids[b * Ltxt + p] * D;
+}
+__global__ void __launch_bounds__(256) embed_loss_kernel(CBfPtr x_out, const float* __restrict__ emb, const int* __restrict__ ids,
+                                                         const float* __restrict__ tgt, int tgt_rows, int R,
+                                                         int B, int Ltxt, int L, int D, int kind, double inv_div, float gscale,
+                                                         double* loss_acc, BfPtr dx) {
+  __shared__ float wred[8];
+  __shared__ float total_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x;
+  const int b = r % B;
+  const int nvec = D / 8;
+  float acc = 0.f;
+  for (int p = warp; p < Ltxt; p += 8) {
+    const size_t row = (size_t)r * L + p;
+    const float* e = loss_target_row(emb, ids, tgt, tgt_rows, r, b, p, Ltxt, D);
+    for (int v = lane; v < nvec; v += 32) {
+      float x[8], t[8];
+      load8(x_out, row * D + v * 8, x);
+      load8_f32(e + v * 8, t);
+      if (kind <= 1) {
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = x[i] - t[i];
+          acc += fabsf(d);
+          g[i] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+        }
+        if (dx.hi != nullptr) store8(dx, row * D + v * 8, g);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = x[i] - t[i]; acc += d * d; }
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wred[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += wred[i];
+    total_s = t;
+  }
+  __syncthreads();
+  const float total = total_s;
+  if (kind >= 2) {
+    const float norm = sqrtf(total);
+    const float gs = norm > 0.f ? gscale / norm : 0.f;
+    if (dx.hi != nullptr) {
+      for (int p = warp; p < Ltxt; p += 8) {
+        const size_t row = (size_t)r * L + p;
+        const float* e = loss_target_row(emb, ids, tgt, tgt_rows, r, b, p, Ltxt, D);
+        for (int v = lane; v < nvec; v += 32) {
+          float x[8], t[8], g[8];
+          load8(x_out, row * D + v * 8, x);
+          load8_f32(e + v * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = (x[i] - t[i]) * gs;
+          store8(dx, row * D + v * 8, g);
+        }
+      }
+    }
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(loss_acc, (double)norm * inv_div);
+  } else {
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(loss_acc, (double)total * inv_div);
+  }
+  if (dx.hi != nullptr) {  // rows that do not enter the loss (CLIP positions) get a zero gradient
+    const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = Ltxt + warp; p < L; p += 8)
+      for (int v = lane; v < nvec; v += 32) store8(dx, ((size_t)r * L + p) * D + v * 8, zero);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small linear (CLIP projections), fp32
+// ------------------------------------------------------------------------------------------------------------------
+// one warp per output feature n, 8 captions per block.y slab: W row read once per 8 captions
+__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, int B, int K, int N, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b0 = blockIdx.y * 8;
+  if (n >= N) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = lane; k < K; k += 32) {
+    const float wk = __ldg(w + (size_t)n * K + k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b0 + j < B) acc[j] += wk * __ldg(x + (size_t)(b0 + j) * K + k);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = warp_sum(acc[j]);
+    if (lane == 0 && b0 + j < B) y[(size_t)(b0 + j) * N + n] = s + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+// dW[n, k] += sum_b dy[b, n] x[b, k]; db[n] += sum_b dy[b, n].  grid (ceil(K/256), N)
+__global__ void __launch_bounds__(256) small_linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int K, int N,
+                                                               float* dw, float* db) {
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  float acc = 0.f, accb = 0.f;
+  if (k < K) {
+    for (int b = 0; b < B; ++b) {
+      const float g = __ldg(dy + (size_t)b * N + n);
+      acc += g * __ldg(x + (size_t)b * K + k);
+      accb += g;
+    }
+    dw[(size_t)n * K + k] += acc;
+    if (k == 0 && db != nullptr) db[n] += accb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW single-tensor semantics applied to the flat buffer)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                    __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo, long long n4,
+                                                    float decay, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2,
+                                                    float grad_scale, int zero_grad) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = reinterpret_cast<float*>(&pp); float* G = reinterpret_cast<float*>(&gg);
+    float* M = reinterpret_cast<float*>(&mm); float* V = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * grad_scale;
+      P[j] *= decay;
+      M[j] = beta1 * M[j] + (1.f - beta1) * gr;
+      V[j] = beta2 * V[j] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(V[j]) * inv_sqrt_bc2 + eps;
+      P[j] -= step_size * (M[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sh_hi != nullptr) {
+      uint2 h;
+      h.x = pack_bf16x2(P[0], P[1]); h.y = pack_bf16x2(P[2], P[3]);
+      reinterpret_cast<uint2*>(sh_hi)[i] = h;
+      if (sh_lo != nullptr) {
+        uint2 l;
+        l.x = pack_bf16x2(P[0] - bf16_round(P[0]), P[1] - bf16_round(P[1]));
+        l.y = pack_bf16x2(P[2] - bf16_round(P[2]), P[3] - bf16_round(P[3]));
+        reinterpret_cast<uint2*>(sh_lo)[i] = l;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conversions
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo != nullptr) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+__global__ void to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = __bfloat162float(hi[i]);
+    if (lo != nullptr) v += __bfloat162float(lo[i]);
+    y[i] = v;
+  }
+}
+__global__ void gather_rows_f32_kernel(CBfPtr x, long long rows_out, int len, int stride, int D, float* __restrict__ y) {
+  const int nvec = D / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows_out * nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 8;
+    const long long src = (r / len) * stride + (r % len);
+    float v[8];
+    load8(x, (size_t)src * D + c, v);
+    store8_f32(y + (size_t)r * D + c, v);
+  }
+}
+// q_sample (diffuse_t, CLIP-DDPM.py:347-362): out[s, b, :] = ca[s] * x0[b, :] + cb[s] * noise[b, :]; n = elements per sample
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ ca,
+                                const float* __restrict__ cb, long long n4, int S, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 * S; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i / n4);
+    const long long j = i % n4;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(x0) + j);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(noise) + j);
+    const float a = ca[s], b = cb[s];
+    reinterpret_cast<float4*>(out)[i] = make_float4(a * x.x + b * e.x, a * x.y + b * e.y, a * x.z + b * e.z, a * x.w + b * e.w);
+  }
+}
+// keymask[r] (one word per 32 keys): text keys from attn_mask[b], image key visible, text-CLIP key visible iff guided
+__global__ void keymask_kernel(const int* __restrict__ attn_mask, int R, int B, int Ltxt, int L, int fusion, int guided, int kw,
+                               uint32_t* __restrict__ km) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * kw) return;
+  const int r = idx / kw, w = idx % kw;
+  const int b = r % B;
+  uint32_t bits = 0;
+  for (int j = w * 32; j < min(L, w * 32 + 32); ++j) {
+    bool vis;
+    if (j < Ltxt) vis = attn_mask == nullptr ? true : attn_mask[b * Ltxt + j] != 0;
+    else if (fusion == 0) vis = (j == Ltxt) ? true : (guided != 0);
+    else vis = true;
+    if (vis) bits |= 1u << (j & 31);
+  }
+  km[idx] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------------------------
+static inline CBfPtr cbf(const clipdlm_bf_t* p) {
+  CBfPtr r; r.hi = p ? (const __nv_bfloat16*)p->hi : nullptr; r.lo = p ? (const __nv_bfloat16*)p->lo : nullptr; return r;
+}
+static inline BfPtr mbf(const clipdlm_bf_t* p) {
+  BfPtr r; r.hi = p ? (__nv_bfloat16*)p->hi : nullptr; r.lo = p ? (__nv_bfloat16*)p->lo : nullptr; return r;
+}
+static inline int grid_1d(long long n, int threads, int max_blocks) {
+  long long b = (n + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define DISPATCH_NV(D, ...)                                                                       \
+  switch ((D) / 256) {                                                                            \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; break; }                                         \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; break; }                                         \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; break; }                                         \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; break; }                                         \
+    default: CLIPDLM_CHECK(false, "unsupported model dim %d (need a multiple of 256, <= 1024)", (D)); \
+  }
+
+int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st) {
+  CLIPDLM_CHECK(e != nullptr && e->D % 256 == 0, "embed_fwd: bad descriptor / dim");
+  CLIPDLM_CHECK(e->R > 0 && e->B > 0 && e->R % e->B == 0, "embed_fwd: R %d must be a positive multiple of B %d", e->R, e->B);
+  CLIPDLM_CHECK(e->fusion == 0 ? e->L == e->Ltxt + 2 : e->L == e->Ltxt, "embed_fwd: L %d inconsistent with Ltxt %d for fusion %d", e->L,
+                e->Ltxt, e->fusion);
+  CLIPDLM_CHECK(e->mode == 0 ? e->x_in != nullptr : (e->emb_table && e->ids && e->noise && e->coef_a && e->coef_b),
+                "embed_fwd: missing inputs for mode %d", e->mode);
+  CLIPDLM_CHECK(e->img_proj && e->txt_proj && e->pos && e->ln_w && e->ln_b && e->h.hi, "embed_fwd: null pointer");
+  EmbedArgs a;
+  a.R = e->R; a.B = e->B; a.Ltxt = e->Ltxt; a.L = e->L; a.D = e->D; a.fusion = e->fusion; a.mode = e->mode; a.guided = e->guided;
+  a.x_in = e->x_in; a.x_in_stride = e->x_in_stride > 0 ? e->x_in_stride : (long long)e->Ltxt * e->D;
+  a.emb_table = e->emb_table; a.ids = e->ids; a.noise = e->noise; a.coef_a = e->coef_a; a.coef_b = e->coef_b;
+  a.img_proj = e->img_proj; a.txt_proj = e->txt_proj; a.seg = e->seg; a.pos = e->pos;
+  a.ln_w = e->ln_w; a.ln_b = e->ln_b; a.ln_eps = e->ln_eps;
+  a.z = mbf(&e->z); a.h = mbf(&e->h);
+  a.drop = make_drop(e->drop_seed, e->drop_site, e->drop_p);
+  const long long rows = (long long)e->R * e->L;
+  const int grid = (int)((rows + 7) / 8);
+  DISPATCH_NV(e->D, embed_fwd_kernel<NV><<<grid, 256, 0, st>>>(a));
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int embed_bwd_dispatch(const clipdlm_bf_t* dz, int R, int B, int Ltxt, int L, int D, int fusion, int guided, float* d_pos, float* d_seg,
+                       float* d_img, float* d_txt, cudaStream_t st) {
+  CLIPDLM_CHECK(dz && dz->hi && D % 256 == 0 && R % B == 0, "embed_bwd: bad arguments");
+  CLIPDLM_CHECK(d_pos && d_img && d_txt && (fusion != 0 || d_seg), "embed_bwd: null gradient buffer");
+  int slabs = (4 * num_sms()) / ((D / 256) * L);
+  if (slabs < 1) slabs = 1;
+  if (slabs > (R + 7) / 8) slabs = (R + 7) / 8;
+  const int rps = (R + slabs - 1) / slabs;
+  dim3 grid(D / 256, L, (R + rps - 1) / rps);
+  embed_bwd_posseg_kernel<<<grid, 256, 0, st>>>(cbf(dz), R, L, Ltxt, D, fusion, rps, d_pos, d_seg);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  const long long n = (long long)B * (D / 8);
+  embed_bwd_proj_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(cbf(dz), R, B, L, Ltxt, D, fusion, guided, d_img, d_txt);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b, float eps, long long rows, int D, const clipdlm_bf_t* y,
+                           float* y_f32, unsigned long long seed, uint32_t site, float p, cudaStream_t st) {
+  CLIPDLM_CHECK(z && z->hi && w && b && rows > 0 && ((y && y->hi) || y_f32), "layernorm_fwd: bad arguments");
+  const int grid = (int)((rows + 7) / 8);
+  const DropoutCfg d = make_drop(seed, site, p);
+  DISPATCH_NV(D, layernorm_fwd_kernel<NV><<<grid, 256, 0, st>>>(cbf(z), w, b, eps, rows, D, mbf(y), y_f32, d));
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, long long rows, int D,
+                           const clipdlm_bf_t* dz, float* dw, float* db, unsigned long long seed, uint32_t site_out, float p_out,
+                           const clipdlm_bf_t* dz_drop, uint32_t site_in, float p_in, const clipdlm_bf_t* gelu_u, float* dbias,
+                           cudaStream_t st) {
+  CLIPDLM_CHECK(z && z->hi && dy && dy->hi && w && dz && dz->hi && rows > 0, "layernorm_bwd: bad arguments");
+  LnBwdArgs a;
+  a.z = cbf(z); a.dy = cbf(dy); a.w = w; a.eps = eps; a.rows = rows; a.D = D;
+  a.dz = mbf(dz); a.dw = dw; a.db = db;
+  a.drop_out = make_drop(seed, site_out, p_out);
+  a.dz_drop = (dz_drop && p_in > 0.f) ? mbf(dz_drop) : mbf(nullptr);
+  a.drop_in = make_drop(seed, site_in, p_in);
+  a.gelu_u = cbf(gelu_u);
+  a.dbias = dbias;
+  long long want = (rows + 7) / 8;
+  int grid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
+  const size_t smem = (size_t)8 * D * sizeof(float);
+  DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 256, smem, st>>>(a));
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int colsum_dispatch(const clipdlm_bf_t* x, long long rows, int N, float* out, cudaStream_t st) {
+  CLIPDLM_CHECK(x && x->hi && out && N % 256 == 0 && rows > 0, "colsum: bad arguments (N must be a multiple of 256)");
+  long long slabs = (4LL * num_sms()) / (N / 256);
+  if (slabs < 1) slabs = 1;
+  if (slabs > (rows + 31) / 32) slabs = (rows + 31) / 32;
+  const long long rps = (rows + slabs - 1) / slabs;
+  dim3 grid(N / 256, (unsigned)((rows + rps - 1) / rps));
+  colsum_kernel<<<grid, 256, 0, st>>>(cbf(x), rows, N, rps, out);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* ids, const float* tgt, int tgt_rows, int R, int B, int Ltxt,
+                        int L, int D, int kind, long long R_total, int batch_size, float weight, double* loss_acc, const clipdlm_bf_t* dx,
+                        cudaStream_t st) {
+  CLIPDLM_CHECK(x_out && x_out->hi && ((emb && ids) || (tgt && tgt_rows > 0)) && R > 0 && D % 8 == 0 && kind >= 0 && kind <= 3,
+                "embed_loss: bad arguments");
+  double inv_div;
+  switch (kind) {
+    case 0: inv_div = 1.0 / ((double)R_total * D); break;            // (..).abs().sum(dim=1).mean()           CLIP-DDPM.py:77-78
+    case 1: inv_div = 1.0 / ((double)batch_size * 768.0 * 100.0); break;  // .abs().sum()/BATCH_SIZE/768/100  :80-81 (literals)
+    case 2: inv_div = 1.0 / (double)R_total; break;                   // L2 norm per row, mean                  :83-84
+    default: inv_div = 1.0 / (double)batch_size; break;               // L2 norm per row, sum / BATCH_SIZE      :86-87
+  }
+  embed_loss_kernel<<<R, 256, 0, st>>>(cbf(x_out), emb, ids, tgt, tgt_rows, R, B, Ltxt, L, D, kind, inv_div, (float)(inv_div * weight), loss_acc, mbf(dx));
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int small_linear_fwd_dispatch(const float* x, const float* w, const float* b, int B, int K, int N, float* y, cudaStream_t st) {
+  CLIPDLM_CHECK(x && w && y && B > 0, "small_linear_fwd: bad arguments");
+  dim3 grid((N + 7) / 8, (B + 7) / 8);
+  small_linear_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, B, K, N, y);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int small_linear_bwd_dispatch(const float* x, const float* dy, int B, int K, int N, float* dw, float* db, cudaStream_t st) {
+  CLIPDLM_CHECK(x && dy && dw && B > 0, "small_linear_bwd: bad arguments");
+  dim3 grid((K + 255) / 256, N);
+  small_linear_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, B, K, N, dw, db);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int adamw_dispatch(float* p, float* g, float* m, float* v, void* sh_hi, void* sh_lo, long long n, float lr, float beta1, float beta2,
+                   float eps, float wd, int step, float grad_scale, int zero_grad, cudaStream_t st) {
+  CLIPDLM_CHECK(p && g && m && v && n > 0 && n % 4 == 0 && step >= 1, "adamw: bad arguments (n must be a multiple of 4, step >= 1)");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float decay = (float)(1.0 - (double)lr * (double)wd);
+  const int grid = grid_1d(n / 4, 256, 8 * num_sms());
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)sh_hi, (__nv_bfloat16*)sh_lo, n / 4, decay, beta1, beta2, eps, step_size,
+                                     inv_sqrt_bc2, grad_scale, zero_grad);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int to_bf16_dispatch(const float* x, void* hi, void* lo, long long n, cudaStream_t st) {
+  CLIPDLM_CHECK(x && hi && n > 0, "to_bf16: bad arguments");
+  to_bf16_kernel<<<grid_1d(n, 256, 16 * num_sms()), 256, 0, st>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int to_f32_dispatch(const void* hi, const void* lo, float* y, long long n, cudaStream_t st) {
+  CLIPDLM_CHECK(hi && y && n > 0, "to_f32: bad arguments");
+  to_f32_kernel<<<grid_1d(n, 256, 16 * num_sms()), 256, 0, st>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, y, n);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int gather_rows_f32_dispatch(const clipdlm_bf_t* x, long long rows_out, int len, int stride, int D, float* y, cudaStream_t st) {
+  CLIPDLM_CHECK(x && x->hi && y && rows_out > 0 && D % 8 == 0 && len > 0 && stride >= len, "gather_rows_f32: bad arguments");
+  gather_rows_f32_kernel<<<grid_1d(rows_out * (D / 8), 256, 16 * num_sms()), 256, 0, st>>>(cbf(x), rows_out, len, stride, D, y);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int q_sample_dispatch(const float* x0, const float* noise, const float* ca, const float* cb, long long n, int S, float* out, cudaStream_t st) {
+  CLIPDLM_CHECK(x0 && noise && ca && cb && out && n > 0 && n % 4 == 0 && S > 0, "q_sample: bad arguments");
+  q_sample_kernel<<<grid_1d(n / 4 * S, 256, 16 * num_sms()), 256, 0, st>>>(x0, noise, ca, cb, n / 4, S, out);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int keymask_dispatch(const int* attn_mask, int R, int B, int Ltxt, int L, int fusion, int guided, uint32_t* km, cudaStream_t st) {
+  CLIPDLM_CHECK(km && R > 0 && B > 0, "keymask: bad arguments");
+  const int kw = (L + 31) / 32;
+  keymask_kernel<<<(R * kw + 255) / 256, 256, 0, st>>>(attn_mask, R, B, Ltxt, L, fusion, guided, kw, km);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace clipdlm

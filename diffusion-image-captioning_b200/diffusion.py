@@ -1,0 +1,294 @@
+"""The reference's step functions over the native engine: `diffuse_t`, `generate_diffuse_pair`, `loss`, `train_func`,
+`validate` (CLIP-DDPM.py:347-501) with the same names / argument meaning / return values, plus the thin `train()` (epoch loop,
+:515-557) and `sample()` (denoise loop, :611-621) wrappers BASELINE.json's north star names.
+
+Differences a maintainer should know (all documented in INTEGRATION.md):
+  * the hyperparameters are a dict (`model.hp`) instead of module globals;
+  * `loss()` is eager: the reference builds an autograd graph and `train_func` calls `l.backward()`; here the hand-written
+    backward of each row chunk runs inside `loss()` (when `backward=True`) because activations are kept per chunk, and
+    `train_func` only adds the optimizer step;
+  * keyword-only `t=`, `noise_t=`, `noise_1=`, `dropout_seed=` pin the random draws for parity tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional
+
+import torch
+
+from . import _lib as L
+from .hparams import LOSS_KIND, alpha_cumprod, learning_rates
+from .model import AdamW, DistilBertModel
+
+_ACP_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def _acp(hp: dict, device) -> torch.Tensor:
+    key = (str(device), hp["COSIN_SCHEDULE"], hp["STEP_TOT"], hp["BETA_MIN"], hp["BETA_MAX"])
+    if key not in _ACP_CACHE:
+        _ACP_CACHE[key] = alpha_cumprod(hp, device).float().contiguous()
+    return _ACP_CACHE[key]
+
+
+def _coefs(hp: dict, t: torch.Tensor):
+    a = _acp(hp, t.device)[t.reshape(-1)]
+    return torch.sqrt(a).contiguous(), torch.sqrt(1 - a).contiguous()
+
+
+def _need_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.ClipdlmError("clipdlm operates on CUDA tensors only (no CPU fallback)")
+
+
+def diffuse_t(x: torch.Tensor, t: torch.Tensor, hp: dict, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q_sample, CLIP-DDPM.py:347-362. x [B, seq, C]; t [n] int64 -> [n*B, seq, C], row = s*B + b; ONE noise draw of
+    x.shape shared by the n samples (reference semantics)."""
+    _need_cuda(x)
+    B, seq, ch = x.shape
+    S = t.numel()
+    if noise is None:
+        noise = torch.randn(x.shape, device=x.device)
+    ca, cb = _coefs(hp, t.to(x.device))
+    x32, n32 = x.float().contiguous(), noise.float().contiguous()
+    out = torch.empty(S * B, seq, ch, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().clipdlm_q_sample(L.ptr(x32), L.ptr(n32), L.ptr(ca), L.ptr(cb), x32.numel(), S, L.ptr(out),
+                                          torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def generate_diffuse_pair(x_0, t, hp: dict, t_next=None):
+    """CLIP-DDPM.py:364-380."""
+    if hp["X_0_PREDICTION"]:
+        return diffuse_t(x_0, t, hp), x_0
+    return diffuse_t(x_0, t, hp), diffuse_t(x_0, t_next, hp)
+
+
+def _next_seed() -> int:
+    return int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: no device sync
+
+
+def _loss_pass(model: DistilBertModel, eng, losses: torch.Tensor, slot: int, *, R: int, B: int, R_total: int, mode: int, ids32, mask32,
+               image_clip, text_clip, backward: bool, seed: int, use_embed: bool, x_in=None, noise=None, coef_a=None, coef_b=None,
+               target=None, target_rows: int = 0, guided: bool = False):
+    hp = model.hp
+    model._run_forward(eng, R=R, B=B, mode=mode, guided=guided, train=model.training, image_clip=image_clip, text_clip=text_clip,
+                       attn_mask=mask32, x_in=x_in, ids=ids32, noise=noise, coef_a=coef_a, coef_b=coef_b, drop_seed=seed)
+    lc = L.LossCfg(LOSS_KIND[hp["LOSS_FUNC"]], 1 if use_embed else 0, 1 if hp["USE_PROB_LOSS"] else 0, hp["BATCH_SIZE"], R_total,
+                   float(hp["ROUNDING_WEIGHT"]), 1 if backward else 0, L.ptr(target), target_rows)
+    with torch.cuda.device(model.device):
+        L.check(L.load().clipdlm_engine_loss_backward(eng, C.byref(lc), losses.data_ptr() + 8 * slot, model._stream()))
+    if backward:
+        model._grads_dirty = True
+
+
+def _finish(model, losses):
+    hp = model.hp
+    lf = losses.float()
+    x_t_loss, x_1_loss = lf[0], lf[2]
+    prob_loss = float(hp["ROUNDING_WEIGHT"]) * (lf[1] + lf[3])  # CLIP-DDPM.py:445
+    return x_t_loss, x_1_loss, prob_loss
+
+
+def _prep_batch(model, image_clip, text_clip, mask, idx):
+    dev = model.device
+    return (image_clip.to(dev, torch.float32).contiguous(), text_clip.to(dev, torch.float32).contiguous(),
+            (mask != 0).to(dev, torch.int32).contiguous(), idx.to(dev, torch.int32).contiguous())
+
+
+def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, loss_func=None, *, backward: Optional[bool] = None,
+         dropout_seed: Optional[int] = None):
+    """CLIP-DDPM.py:382-445. Same inputs / outputs: returns (x_t_loss, x_1_loss, ROUNDING_WEIGHT * (x_t_prob_loss + x_1_prob_loss))
+    as 0-dim device tensors. `loss_func` is accepted for signature compatibility; the objective is `model.hp['LOSS_FUNC']`
+    (a name) because the kernels implement the reference's four LOSS_FUNCs natively. backward=None => model.training and grad
+    enabled: the gradients of `x_t_loss + x_1_loss + prob_loss` are accumulated into the model's flat grad buffer."""
+    hp = model.hp
+    S, B, ML, D = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    assert tuple(x_t.shape) == (S * B, ML, D)  # :396-400
+    assert tuple(x_1.shape) == tuple(x_0.shape) == (B, ML, D)
+    assert tuple(image_clip.shape) == tuple(text_clip.shape) == (B, hp["CLIP_DIM"])
+    assert tuple(mask.shape) == (B, ML) and tuple(idx.shape) == (B, ML)
+    if loss_func is not None and getattr(loss_func, "__name__", loss_func) != hp["LOSS_FUNC"]:
+        raise ValueError(f"loss_func {getattr(loss_func, '__name__', loss_func)} differs from hp['LOSS_FUNC'] = {hp['LOSS_FUNC']}")
+    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:
+        raise NotImplementedError("classifier-free guidance training (CLIP-DDPM.py:406-410) is not built yet (SURVEY 8f N1)")
+    _need_cuda(x_t)
+    if backward is None:
+        backward = model.training and torch.is_grad_enabled()
+    img, txt, mask32, ids32 = _prep_batch(model, image_clip, text_clip, mask, idx)
+    x_t32, x_132, x_032 = x_t.float().contiguous(), x_1.float().contiguous(), x_0.float().contiguous()
+    tgt_t = x_032 if hp["X_0_PREDICTION"] else x_tgt.float().contiguous()
+    if not hp["X_0_PREDICTION"]:
+        assert tuple(x_tgt.shape) == tuple(x_t.shape)  # :420
+    spc = max(1, model.chunk_rows // B)
+    eng = model._engine(min(S, spc) * B, B, backward or model.training)
+    losses = torch.zeros(4, dtype=torch.float64, device=model.device)
+    seed = _next_seed() if dropout_seed is None else int(dropout_seed)
+    row_elems = ML * D
+    for ci, s0 in enumerate(range(0, S, spc)):
+        s1 = min(S, s0 + spc)
+        R = (s1 - s0) * B
+        xin = x_t32[s0 * B:s1 * B]
+        if hp["X_0_PREDICTION"]:
+            target, trows = tgt_t, B
+        else:
+            target, trows = tgt_t[s0 * B:s1 * B], R
+        _loss_pass(model, eng, losses, 0, R=R, B=B, R_total=S * B, mode=0, ids32=ids32, mask32=mask32, image_clip=img, text_clip=txt,
+                   backward=backward, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], x_in=xin, target=target, target_rows=trows)
+    _loss_pass(model, eng, losses, 2, R=B, B=B, R_total=B, mode=0, ids32=ids32, mask32=mask32, image_clip=img, text_clip=txt,
+               backward=backward, seed=seed + 7919, use_embed=hp["USE_X_1_LOSS"], x_in=x_132, target=x_032, target_rows=B)
+    return _finish(model, losses)
+
+
+def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train: bool = True, *, t: Optional[torch.Tensor] = None,
+               noise_t: Optional[torch.Tensor] = None, noise_1: Optional[torch.Tensor] = None, dropout_seed: Optional[int] = None):
+    """CLIP-DDPM.py:458-486: embed -> draw t -> q_sample x2 -> zero_grad -> loss -> backward -> AdamW step.
+    Returns (l, x_t_loss, x_1_loss, prob_loss) as 0-dim device tensors (no host sync, like the reference's loop :530-533).
+
+    With X_0_PREDICTION (the default) nothing of shape [S*B, 16, 768] is materialised: the fused prologue kernel gathers
+    E[ids], applies sqrt(abar_t) / sqrt(1 - abar_t) per sample and the CLIP fusion in one pass, chunk by chunk."""
+    hp = model.hp
+    dev = model.device
+    S, B, ML, D = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    ids = x["input_ids"].to(dev)
+    assert tuple(ids.shape) == (B, ML), f"batch must be exactly BATCH_SIZE={B} x MAX_LENGTH={ML} (reference asserts :396-400)"
+    if t is None:
+        t = torch.randint(0, hp["STEP_TOT"], (S, 1, 1), device=dev)  # :461
+        if model.dp_group is not None:  # the reference shares t across the whole batch; keep that across ranks
+            torch.distributed.broadcast(t, src=0, group=model.dp_group)
+    t = t.to(dev)
+    assert t.numel() == S
+    backward = bool(train)
+    if train:
+        trainer.zero_grad()  # :471
+    if not hp["X_0_PREDICTION"] or hp["CLASSIFIER_FREE_WEIGHT"] > 0:
+        # x_{t-1}-prediction objective (:466-467): explicit tensors through loss()
+        x_0 = model.embedding(ids)
+        t_next = torch.max(t - hp["X_T_STEP_INTERVAL"], torch.zeros_like(t))
+        x_t = diffuse_t(x_0, t, hp, noise_t)
+        x_tgt = diffuse_t(x_0, t_next, hp)
+        x_1 = diffuse_t(x_0, torch.ones(1, dtype=torch.int64, device=dev), hp, noise_1)
+        x_t_loss, x_1_loss, prob_loss = loss(model, x_t, x_1, x_tgt, x_0, x["image_clip"], x["text_clip"], x["attention_mask"], ids,
+                                             backward=backward, dropout_seed=dropout_seed)
+    else:
+        img, txt, mask32, ids32 = _prep_batch(model, x["image_clip"], x["text_clip"], x["attention_mask"], ids)
+        if noise_t is None:
+            noise_t = torch.randn(B, ML, D, device=dev)  # one draw shared by the S samples (:359)
+        if noise_1 is None:
+            noise_1 = torch.randn(B, ML, D, device=dev)
+        noise_t, noise_1 = noise_t.to(dev, torch.float32).contiguous(), noise_1.to(dev, torch.float32).contiguous()
+        ca, cb = _coefs(hp, t)
+        ca1, cb1 = _coefs(hp, torch.ones(1, dtype=torch.int64, device=dev))  # x_1 = diffuse_t(x_0, ones(1)) :468
+        spc = max(1, model.chunk_rows // B)
+        eng = model._engine(min(S, spc) * B, B, backward or model.training)
+        losses = torch.zeros(4, dtype=torch.float64, device=dev)
+        seed = _next_seed() if dropout_seed is None else int(dropout_seed)
+        for ci, s0 in enumerate(range(0, S, spc)):
+            s1 = min(S, s0 + spc)
+            _loss_pass(model, eng, losses, 0, R=(s1 - s0) * B, B=B, R_total=S * B, mode=1, ids32=ids32, mask32=mask32, image_clip=img,
+                       text_clip=txt, backward=backward, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], noise=noise_t, coef_a=ca[s0:s1],
+                       coef_b=cb[s0:s1])
+        _loss_pass(model, eng, losses, 2, R=B, B=B, R_total=B, mode=1, ids32=ids32, mask32=mask32, image_clip=img, text_clip=txt,
+                   backward=backward, seed=seed + 7919, use_embed=hp["USE_X_1_LOSS"], noise=noise_1, coef_a=ca1, coef_b=cb1)
+        x_t_loss, x_1_loss, prob_loss = _finish(model, losses)
+    l = x_t_loss + x_1_loss + prob_loss  # :481
+    if train:
+        if model.dp_group is not None:
+            torch.distributed.all_reduce(model.grad, group=model.dp_group)  # sum; AdamW applies 1/world
+        trainer.step()  # :484
+    return l, x_t_loss, x_1_loss, prob_loss
+
+
+def validate(model: DistilBertModel, val_loader: Iterable[dict]):
+    """CLIP-DDPM.py:488-501: eval mode, no grad, mean of the three loss terms over the validation loader."""
+    was_training = model.training
+    model.eval()
+    x_t_loss = x_1_loss = prob_loss = 0
+    n = 0
+    with torch.no_grad():
+        for x in val_loader:
+            _, a, b, c = train_func(model, None, x, train=False)
+            x_t_loss, x_1_loss, prob_loss = x_t_loss + a, x_1_loss + b, prob_loss + c
+            n += 1
+    model.train(was_training)
+    n = max(n, 1)
+    return x_t_loss / n, x_1_loss / n, prob_loss / n
+
+
+def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dict] = None, val_loader=None, summary=None, on_early_stop=None):
+    """The epoch loop of CLIP-DDPM.py:515-557 as a function: per-epoch learning rate from `lrs` (:451-456,520-522), the
+    dynamic rounding weight (:535-536), validation + the early-stop hook (:546-553), one summary line per epoch (:554).
+    Returns a list of per-epoch dicts. Loss accumulators stay on the device (no per-step sync)."""
+    hp = model.hp if hp is None else hp
+    lrs = learning_rates(hp)
+    early_stopped = False
+    model.train()
+    history = []
+    for epoch in range(hp["EPOCH_NUM"]):
+        acc_x_t = acc_x_1 = acc_prob = acc_l = 0
+        if not hp["END_LEARNING_RATE"] == hp["LEARNING_RATE"]:
+            for g in trainer.param_groups:
+                g["lr"] = lrs[epoch]
+        n_batches = 0
+        for x in train_loader:
+            l, x_t_loss, x_1_loss, prob_loss = train_func(model, trainer, x)
+            acc_x_t, acc_x_1, acc_prob, acc_l = acc_x_t + x_t_loss, acc_x_1 + x_1_loss, acc_prob + prob_loss, acc_l + l
+            n_batches += 1
+            if hp["DYNAMIC_ROUNDING_WEIGHT"] > 0:
+                model.hp["ROUNDING_WEIGHT"] = float(((acc_x_t + acc_x_1) / acc_prob).item() * hp["DYNAMIC_ROUNDING_WEIGHT"])
+            if hp["DEBUG"]:
+                break
+        n_batches = max(n_batches, 1)
+        rec = dict(epoch=epoch, x_t_loss=acc_x_t / n_batches, x_1_loss=acc_x_1 / n_batches, prob_loss=acc_prob / n_batches, lr=trainer.param_groups[0]["lr"])
+        if val_loader is not None:
+            val_x_t, val_x_1, val_prob = validate(model, val_loader)
+            rec.update(val_x_t=val_x_t, val_x_1=val_x_1, val_prob=val_prob)
+            if val_x_t + val_x_1 + val_prob > hp["EARLY_STOP_RATIO"] * acc_l / n_batches:
+                if not early_stopped and on_early_stop is not None:
+                    on_early_stop(model, epoch)
+                early_stopped = True
+        rec["early_stopped"] = early_stopped
+        if summary is not None:
+            summary.write(f"epoch {epoch} average x_t_loss, x_1_loss, prob_loss, val losses: {float(rec['x_t_loss'])}, {float(rec['x_1_loss'])}, "
+                          f"{float(rec['prob_loss'])}, {float(rec.get('val_x_t', float('nan')))}, {float(rec.get('val_x_1', float('nan')))}, "
+                          f"{float(rec.get('val_prob', float('nan')))}\n")
+        history.append(rec)
+        if hp["DEBUG"]:
+            break
+    return history
+
+
+@torch.no_grad()
+def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, return_all: bool = False,
+           restored: Optional[torch.Tensor] = None, unique_consecutive: bool = False):
+    """The reference's reverse "denoise" loop (CLIP-DDPM.py:611-621, COCO_BLEU.py:249-257): restored ~ N(0, I) [B, L, C];
+    n_steps x { out, restored = model(restored[:, :MAX_LENGTH], image_clip, 0, ones, [1, 0]) }; ids = argmax over the vocabulary.
+
+    Returns ids int64 [B, MAX_LENGTH] (and the final `restored`, and per-step ids if return_all). The lm_head GEMM runs only
+    where ids are needed (last step; every step if return_all) with a fused running-argmax epilogue: logits never reach HBM.
+    unique_consecutive=True applies the reference's `indexes.unique_consecutive(dim=-1)` post-processing (:621)."""
+    hp = model.hp
+    dev = model.device
+    _need_cuda(image_clip)
+    B = image_clip.shape[0]
+    ML, D = hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    Lfull = ML + (2 if hp["CLIP_ADDING_METHOD"] == "concat" else 0)
+    if restored is None:
+        restored = torch.randn(B, Lfull, D, device=dev)  # :613
+    cur = restored.to(dev, torch.float32).contiguous().clone()
+    nxt = torch.empty_like(cur)
+    img = image_clip.to(dev, torch.float32).contiguous()
+    txt = torch.zeros_like(img)  # text_clip = zeros (:617)
+    eng = model._engine(B, B, False)
+    model._last_eng = eng
+    outs = []
+    for _ in range(n_steps):
+        model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=cur,
+                           x_in_stride=Lfull * D, x_out=nxt)
+        cur, nxt = nxt, cur
+        if return_all:
+            outs.append(model.argmax_last(B))
+    indexes = outs[-1] if return_all and outs else model.argmax_last(B)  # softmax is monotone: argmax(softmax(x)) == argmax(x) (:620)
+    if unique_consecutive:
+        indexes = indexes.unique_consecutive(dim=-1)
+    return (indexes, cur, outs) if return_all else (indexes, cur)

@@ -1,0 +1,424 @@
+"""Host-side mirror of the reference's model / optimizer objects (CLIP-DDPM.py:227-335) over the native engine.
+
+`DistilBertModel` keeps the reference's constructor, `forward(x, image_clip, text_clip, mask, concat_mask)` signature,
+`.embedding`, `.lm_head`, `.parameters()`, `.train()/.eval()`; underneath it owns ONE flat fp32 parameter buffer (+ flat grad
+buffer + bf16 shadow) laid out by libclipdlm (include/clipdlm.h, clipdlm_param_offset) and calls the C-ABI engine.
+`AdamW` mirrors `torch.optim.AdamW(model.parameters(), lr)` (param_groups[0]['lr'], zero_grad(), step()) over the flat buffer.
+
+PyTorch is used for device memory, streams and torch.distributed only. There is no CPU / eager fallback: every entry point
+raises if libclipdlm.so or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .hparams import default_hparams
+
+
+class _Cfg:
+    """Duck-typed stand-in for transformers.DistilBertConfig (only the fields the path reads)."""
+
+    def __init__(self, n_layers=6, dim=768, n_heads=12, hidden_dim=3072, dropout=0.1, attention_dropout=0.1,
+                 max_position_embeddings=512, vocab_size=30522):
+        self.n_layers, self.dim, self.n_heads, self.hidden_dim = n_layers, dim, n_heads, hidden_dim
+        self.dropout, self.attention_dropout = dropout, attention_dropout
+        self.max_position_embeddings, self.vocab_size = max_position_embeddings, vocab_size
+
+
+DistilBertConfig = _Cfg
+
+
+class ParamList(list):
+    """`model.parameters()` result: the reference returns a plain list (CLIP-DDPM.py:258-269); this one remembers its owner
+    so that `AdamW(model.parameters(), lr)` can find the flat buffers."""
+    owner: "DistilBertModel" = None
+
+
+class _Embedding:
+    """`model.embedding(ids)` (CLIP-DDPM.py:459,584): frozen lookup into the fp32 table."""
+
+    def __init__(self, weight: torch.Tensor):
+        self.weight = weight
+
+    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        return self.weight[ids]
+
+
+class _LmHead:
+    """`model.lm_head` (CLIP-DDPM.py:246-247): frozen projection, bias zeroed. Calling it runs the tcgen05 GEMM."""
+
+    def __init__(self, owner: "DistilBertModel"):
+        self._owner = owner
+        self.weight = owner.lm_head_weight
+        self.bias = torch.zeros(owner.hp["VOCAB_SIZE"], device=owner.device)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        return self._owner._lm_head_dense(x)
+
+
+def _slot_names(hp: dict) -> List[Tuple[str, int, Tuple[int, ...], int]]:
+    """(reference parameter name, slot, shape, row offset inside the slot) in the reference's parameters() order."""
+    d, f, c = hp["DIM"], hp["HIDDEN_DIM"], hp["CLIP_DIM"]
+    out = [("model.distilbert.embeddings.position_embeddings.weight", L.P_POS, (hp["MAX_POSITION"], d), 0),
+           ("model.distilbert.embeddings.LayerNorm.weight", L.P_EMB_LN_W, (d,), 0),
+           ("model.distilbert.embeddings.LayerNorm.bias", L.P_EMB_LN_B, (d,), 0)]
+    for i in range(hp["N_LAYERS"]):
+        base = L.P_LAYER0 + i * L.P_PER_LAYER
+        p = f"model.distilbert.transformer.layer.{i}."
+        for k, lin in enumerate(("q_lin", "k_lin", "v_lin")):
+            out += [(p + f"attention.{lin}.weight", base + L.PL_QKV_W, (d, d), k * d * d),
+                    (p + f"attention.{lin}.bias", base + L.PL_QKV_B, (d,), k * d)]
+        out += [(p + "attention.out_lin.weight", base + L.PL_O_W, (d, d), 0), (p + "attention.out_lin.bias", base + L.PL_O_B, (d,), 0),
+                (p + "sa_layer_norm.weight", base + L.PL_LN1_W, (d,), 0), (p + "sa_layer_norm.bias", base + L.PL_LN1_B, (d,), 0),
+                (p + "ffn.lin1.weight", base + L.PL_FF1_W, (f, d), 0), (p + "ffn.lin1.bias", base + L.PL_FF1_B, (f,), 0),
+                (p + "ffn.lin2.weight", base + L.PL_FF2_W, (d, f), 0), (p + "ffn.lin2.bias", base + L.PL_FF2_B, (d,), 0),
+                (p + "output_layer_norm.weight", base + L.PL_LN2_W, (d,), 0), (p + "output_layer_norm.bias", base + L.PL_LN2_B, (d,), 0)]
+    out += [("model.vocab_transform.weight", L.P_VT_W, (d, d), 0), ("model.vocab_transform.bias", L.P_VT_B, (d,), 0),
+            ("model.vocab_layer_norm.weight", L.P_VLN_W, (d,), 0), ("model.vocab_layer_norm.bias", L.P_VLN_B, (d,), 0),
+            ("image_linear.weight", L.P_IMG_W, (d, c), 0), ("image_linear.bias", L.P_IMG_B, (d,), 0),
+            ("text_linear.weight", L.P_TXT_W, (d, c), 0), ("text_linear.bias", L.P_TXT_B, (d,), 0)]
+    if hp["CLIP_ADDING_METHOD"] == "concat":
+        out += [("segment_embedding.weight", L.P_SEG, (2, d), 0)]
+    return out
+
+
+class DistilBertModel:
+    """Drop-in for the reference's `class DistilBertModel(nn.Module)` (CLIP-DDPM.py:227-323).
+
+    embedding / projection: the pretrained word-embedding and vocab-projector (modules with `.weight`, or tensors
+    [VOCAB_SIZE, DIM]); frozen copies are taken (:245-247). None => random N(0, 0.02) tied table (what
+    `DistilBertForMaskedLM(DistilBertConfig())` gives, the stand-in used where the checkpoint is unavailable).
+    config: DistilBertConfig-like object (n_layers, dim, n_heads, hidden_dim, dropout, attention_dropout, ...).
+    hp: hyperparameter dict (hparams.default_hparams). precision: "bf16" (speed mode: bf16 tensor-core passes) or "bf16x3"
+    (parity mode: split-bf16 storage, three tensor-core passes per GEMM, fp32-class results).
+    """
+
+    def __init__(self, embedding=None, projection=None, config=None, hp: Optional[dict] = None, precision: str = "bf16",
+                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 4096):
+        lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.ClipdlmError("clipdlm needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        with torch.cuda.device(self.device):
+            if lib.clipdlm_device_ok() != 1:
+                raise L.ClipdlmError("clipdlm needs a compute-capability 10.x device (B200, tcgen05/TMEM)")
+        hp = dict(hp) if hp is not None else default_hparams()
+        if config is not None:
+            hp.update(N_LAYERS=config.n_layers, DIM=config.dim, N_HEADS=config.n_heads, HIDDEN_DIM=config.hidden_dim,
+                      DROPOUT=float(config.dropout), ATTENTION_DROPOUT=float(config.attention_dropout),
+                      MAX_POSITION=config.max_position_embeddings)
+            if not hp["TRAIN_EMBEDDING"]:
+                hp["IN_CHANNEL"] = config.dim
+        if hp["TRAIN_EMBEDDING"]:
+            raise NotImplementedError("TRAIN_EMBEDDING=True (IN_CHANNEL=16 learned embedding, CLIP-DDPM.py:238-243) is outside the built path")
+        if hp["CLIP_ADDING_METHOD"] not in ("concat", "add"):
+            raise NotImplementedError(hp["CLIP_ADDING_METHOD"])  # CLIP-DDPM.py:269
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self.hp = hp
+        self.precision = precision
+        self.training = True
+        self.chunk_rows = int(chunk_rows)
+        self.dp_group = None  # set by parallel.enable_data_parallel
+        self.dp_world = 1
+        self._cfg = L.Config(hp["N_LAYERS"], hp["DIM"], hp["N_HEADS"], hp["HIDDEN_DIM"], hp["VOCAB_SIZE"], hp["MAX_LENGTH"], hp["CLIP_DIM"],
+                             hp["MAX_POSITION"], 0 if hp["CLIP_ADDING_METHOD"] == "concat" else 1, 1 if precision == "bf16x3" else 0,
+                             1e-12, hp["DROPOUT"], hp["ATTENTION_DROPOUT"])
+        n = lib.clipdlm_param_count(C.byref(self._cfg))
+        if n <= 0:
+            raise L.ClipdlmError("bad model configuration: " + lib.clipdlm_last_error().decode())
+        self.n_params = int(n)
+        dev = self.device
+        self.flat = torch.zeros(self.n_params, device=dev)
+        self.grad = torch.zeros(self.n_params, device=dev)
+        self.shadow_hi = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
+        self.shadow_lo = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16) if precision == "bf16x3" else None
+        self._views: Dict[str, torch.Tensor] = {}
+        self._gviews: Dict[str, torch.Tensor] = {}
+        for name, slot, shape, rel in _slot_names(hp):
+            off = int(lib.clipdlm_param_offset(C.byref(self._cfg), slot)) + rel
+            cnt = int(math.prod(shape))
+            self._views[name] = self.flat[off:off + cnt].view(shape)
+            self._gviews[name] = self.grad[off:off + cnt].view(shape)
+        if sum(v.numel() for v in self._views.values()) != self.n_params:
+            raise L.ClipdlmError("parameter name map does not cover the flat buffer")
+        self._init_parameters(seed)
+        V, D = hp["VOCAB_SIZE"], hp["DIM"]
+        if embedding is None:
+            g = torch.Generator(device="cpu")
+            g.manual_seed(0 if seed is None else seed + 1)
+            emb = torch.randn(V, D, generator=g) * 0.02
+        else:
+            emb = getattr(embedding, "weight", embedding).detach().float()
+        if tuple(emb.shape) != (V, D):
+            raise ValueError(f"embedding must be [{V}, {D}], got {tuple(emb.shape)}")
+        self.embedding_weight = emb.to(dev).contiguous().clone()
+        proj = emb if projection is None else getattr(projection, "weight", projection).detach().float()
+        if tuple(proj.shape) != (V, D):
+            raise ValueError(f"projection must be [{V}, {D}], got {tuple(proj.shape)}")
+        self.lm_head_weight = proj.to(dev).contiguous().clone()
+        self._vpad = (V + 255) // 256 * 256  # zero rows so that TMA boxes of the vocab tiles never leave the allocation
+        self.emb_hi = torch.zeros(self._vpad, D, device=dev, dtype=torch.bfloat16)
+        self.emb_lo = torch.zeros(self._vpad, D, device=dev, dtype=torch.bfloat16) if precision == "bf16x3" else None
+        self.embedding = _Embedding(self.embedding_weight)
+        self.lm_head = _LmHead(self)
+        self._engines: Dict[tuple, tuple] = {}
+        self._launches_retired = 0
+        self._grads_dirty = False
+        self.sync_shadow()
+
+    # ---------------------------------------------------------------------------------------------------------- params
+    def _init_parameters(self, seed: Optional[int]):
+        """HF DistilBERT init (N(0, 0.02) Linear / position weights, LayerNorm (1, 0), zero biases), nn.Linear default for the
+        CLIP projections, N(0, 1) segment embedding (CLIP-DDPM.py:236,252-256)."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(torch.initial_seed() if seed is None else seed)
+        c = self.hp["CLIP_DIM"]
+        for name, v in self._views.items():
+            if "LayerNorm.weight" in name or "layer_norm.weight" in name:
+                v.fill_(1.0)
+            elif name.startswith(("image_linear", "text_linear")):
+                bound = 1.0 / math.sqrt(c)
+                v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) * bound)
+            elif name.endswith(".bias"):
+                v.zero_()
+            elif name == "segment_embedding.weight":
+                v.copy_(torch.randn(v.shape, generator=g))
+            else:
+                v.copy_(torch.randn(v.shape, generator=g) * 0.02)
+
+    def parameters(self) -> ParamList:
+        out = ParamList(self._views.values())
+        out.owner = self
+        return out
+
+    def named_parameters(self):
+        return list(self._views.items())
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return dict(self._gviews)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-compatible names: trainable tensors + embedding.weight + lm_head.{weight,bias}."""
+        sd = {k: v.detach().clone() for k, v in self._views.items()}
+        sd["embedding.weight"] = self.embedding_weight.clone()
+        sd["lm_head.weight"] = self.lm_head_weight.clone()
+        sd["lm_head.bias"] = torch.zeros(self.hp["VOCAB_SIZE"], device=self.device)
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        missing = [k for k in self._views if k not in sd]
+        if strict and missing:
+            raise KeyError(f"missing keys: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+        for k, v in self._views.items():
+            if k in sd:
+                v.copy_(sd[k].to(self.device, torch.float32))
+        if "embedding.weight" in sd:
+            self.embedding_weight.copy_(sd["embedding.weight"].to(self.device, torch.float32))
+        if "lm_head.weight" in sd:
+            self.lm_head_weight.copy_(sd["lm_head.weight"].to(self.device, torch.float32))
+        elif "embedding.weight" in sd:
+            self.lm_head_weight.copy_(self.embedding_weight)
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        """Refresh the bf16 (pair) copies the GEMMs read, after any out-of-band change of the fp32 master weights."""
+        lib, st = L.load(), self._stream()
+        with torch.cuda.device(self.device):
+            L.check(lib.clipdlm_to_bf16(L.ptr(self.flat), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), self.n_params, st))
+            n = self.hp["VOCAB_SIZE"] * self.hp["DIM"]
+            L.check(lib.clipdlm_to_bf16(L.ptr(self.lm_head_weight), L.ptr(self.emb_hi), L.ptr(self.emb_lo), n, st))
+
+    # ---------------------------------------------------------------------------------------------------------- nn.Module-ish
+    def train(self, mode: bool = True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise L.ClipdlmError("clipdlm models live on the GPU; use state_dict() to move weights to the host")
+        return self
+
+    def cpu(self):
+        """The reference pickles `model.cpu()` (CLIP-DDPM.py:551,560); here the portable form is the state dict on the host."""
+        return {k: v.cpu() for k, v in self.state_dict().items()}
+
+    def __call__(self, *a, **kw):
+        return self.forward(*a, **kw)
+
+    # ---------------------------------------------------------------------------------------------------------- engine plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _engine(self, rows: int, batch: int, training: bool):
+        """Engine (+ its workspace) able to run passes of up to `rows` rows over `batch` captions. One engine is kept per
+        (training) flavour and regrown on demand."""
+        key = bool(training)
+        cur = self._engines.get(key)
+        if cur is not None and cur[1] >= rows and cur[2] >= batch:
+            return cur[0]
+        lib = L.load()
+        if cur is not None:
+            rows, batch = max(rows, cur[1]), max(batch, cur[2])
+            self._launches_retired += int(lib.clipdlm_engine_launch_count(cur[0]))
+            lib.clipdlm_engine_destroy(cur[0])
+            del self._engines[key]
+            cur = None
+        need = int(lib.clipdlm_workspace_bytes(C.byref(self._cfg), rows, batch, 1 if training else 0))
+        if need == 0:
+            raise L.ClipdlmError("workspace query failed: " + lib.clipdlm_last_error().decode())
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        bufs = L.Buffers(L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), L.ptr(self.embedding_weight),
+                         L.ptr(self.emb_hi), L.ptr(self.emb_lo), L.ptr(ws), need)
+        h = lib.clipdlm_engine_create(C.byref(self._cfg), C.byref(bufs), rows, batch, 1 if training else 0)
+        if not h:
+            raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
+        self._engines[key] = (h, rows, batch, ws)
+        return h
+
+    def launch_count(self) -> int:
+        """Kernel launches issued by this model's engines so far (bench `gpu_launches`)."""
+        lib = L.load()
+        return self._launches_retired + sum(int(lib.clipdlm_engine_launch_count(e[0])) for e in self._engines.values())
+
+    def __del__(self):
+        try:
+            lib = L.load()
+            for e in self._engines.values():
+                lib.clipdlm_engine_destroy(e[0])
+        except Exception:
+            pass
+
+    def _run_forward(self, eng, *, R, B, mode, guided, train, image_clip, text_clip, attn_mask, x_in=None, x_in_stride=0, ids=None,
+                     noise=None, coef_a=None, coef_b=None, drop_seed=0, x_out=None):
+        p = L.Pass(R, B, mode, 1 if guided else 0, 1 if train else 0, L.ptr(x_in), x_in_stride, L.ptr(ids), L.ptr(noise), L.ptr(coef_a),
+                   L.ptr(coef_b), L.ptr(image_clip), L.ptr(text_clip), L.ptr(attn_mask), drop_seed, L.ptr(x_out))
+        with torch.cuda.device(self.device):
+            L.check(L.load().clipdlm_engine_forward(eng, C.byref(p), self._stream()))
+
+    # ---------------------------------------------------------------------------------------------------------- forward
+    @staticmethod
+    def _f32(t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(torch.float32).contiguous()
+
+    def forward(self, x, image_clip, text_clip, mask, concat_mask):
+        """CLIP-DDPM.py:271-323. x [R, MAX_LENGTH, IN_CHANNEL]; image_clip / text_clip [R, 1, 512]; mask [R, MAX_LENGTH];
+        concat_mask [R, 2]. Returns (vocab_out [R, MAX_LENGTH, VOCAB_SIZE], feature_out [R, L, IN_CHANNEL]) in fp32.
+        Forward only (inference / parity checks): training goes through loss() / train_func(), which run the hand-written
+        backward chunk by chunk."""
+        hp = self.hp
+        R = x.shape[0]
+        ML, D = hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+        assert tuple(x.shape) == (R, ML, D)  # :284-287
+        assert tuple(image_clip.shape) == tuple(text_clip.shape) == (R, 1, hp["CLIP_DIM"])
+        assert tuple(mask.shape) == (R, ML)
+        assert tuple(concat_mask.shape) == (R, 2)
+        guidance = concat_mask[:, 1] == 1  # :290
+        n_guided = int(guidance.sum().item())
+        w = hp["CLASSIFIER_FREE_WEIGHT"]
+        x_out = self._encode(x, image_clip[:, 0], text_clip[:, 0], mask, guided=False)
+        if w > 0 and n_guided > 0:  # :313-317
+            idx = guidance.nonzero().flatten()
+            guided_out = self._encode(x[idx], image_clip[idx, 0], text_clip[idx, 0], mask[idx], guided=True)
+            x_out[idx] = (1 + w) * guided_out - w * x_out[idx]
+            return self.lm_head(x_out[:, :ML, :]), x_out
+        return self._lm_head_last(R), x_out
+
+    def _encode(self, x, image_clip, text_clip, mask, guided: bool, x_stride: int = 0):
+        hp = self.hp
+        R = x.shape[0]
+        Lfull = hp["MAX_LENGTH"] + (2 if hp["CLIP_ADDING_METHOD"] == "concat" else 0)
+        eng = self._engine(R, R, False)
+        x_out = torch.empty(R, Lfull, hp["DIM"], device=self.device)
+        xin = x if x_stride else self._f32(x)
+        self._run_forward(eng, R=R, B=R, mode=0, guided=guided, train=False, image_clip=self._f32(image_clip),
+                          text_clip=self._f32(text_clip), attn_mask=(mask != 0).to(torch.int32).contiguous(), x_in=xin,
+                          x_in_stride=x_stride, x_out=x_out)
+        self._last_eng = eng
+        return x_out
+
+    def _lm_head_last(self, R: int) -> torch.Tensor:
+        """Dense logits of the rows of the last forward (fp32; padding columns sliced away)."""
+        hp = self.hp
+        V, ML = hp["VOCAB_SIZE"], hp["MAX_LENGTH"]
+        n32 = (V + 31) // 32 * 32
+        logits = torch.empty(R * ML, n32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.load().clipdlm_engine_lm_head(self._last_eng, L.ptr(logits), n32, None, self._stream()))
+        return logits.view(R, ML, n32)[:, :, :V]
+
+    def _lm_head_dense(self, x: torch.Tensor) -> torch.Tensor:
+        """lm_head on an arbitrary [..., DIM] tensor through the tcgen05 GEMM (used by forward()'s CFG branch and demos)."""
+        hp = self.hp
+        V, D = hp["VOCAB_SIZE"], hp["DIM"]
+        lead = x.shape[:-1]
+        xf = self._f32(x).view(-1, D)
+        M = xf.shape[0]
+        hi = torch.empty(M, D, device=self.device, dtype=torch.bfloat16)
+        lo = torch.empty(M, D, device=self.device, dtype=torch.bfloat16) if self.precision == "bf16x3" else None
+        n32 = (V + 31) // 32 * 32
+        out = torch.empty(M, n32, device=self.device)
+        lib, st = L.load(), self._stream()
+        with torch.cuda.device(self.device):
+            L.check(lib.clipdlm_to_bf16(L.ptr(xf), L.ptr(hi), L.ptr(lo), M * D, st))
+            g = L.Gemm()
+            g.a_hi, g.a_lo, g.b_hi, g.b_lo = L.ptr(hi), L.ptr(lo), L.ptr(self.emb_hi), L.ptr(self.emb_lo)
+            g.lda, g.ldb, g.M, g.N, g.K = D, D, M, n32, D
+            g.epilogue, g.out_f32, g.ldo = L.EPI_STORE, L.ptr(out), n32
+            L.check(lib.clipdlm_gemm(C.byref(g), st))
+        return out.view(*lead, n32)[..., :V]
+
+    def argmax_last(self, R: int) -> torch.Tensor:
+        """argmax over the vocabulary of lm_head(x_out[:, :MAX_LENGTH]) of the last forward, via the fused GEMM + running
+        argmax epilogue (softmax(...).argmax(-1), CLIP-DDPM.py:620). int64 [R, MAX_LENGTH]."""
+        ML = self.hp["MAX_LENGTH"]
+        out = torch.empty(R * ML, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            L.check(L.load().clipdlm_engine_lm_head(self._last_eng, None, 0, L.ptr(out), self._stream()))
+        return out.view(R, ML).to(torch.int64)
+
+
+class AdamW:
+    """`torch.optim.AdamW(model.parameters(), lr=...)` (CLIP-DDPM.py:335) over the model's flat buffers: one fused kernel per
+    step (decoupled weight decay on every element — the reference has a single param group, so biases / LayerNorm decay too),
+    which also refreshes the bf16 shadow weights and clears the gradient buffer for the next step."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        owner = getattr(params, "owner", None)
+        if owner is None:
+            raise TypeError("AdamW expects model.parameters() of a clipdlm DistilBertModel")
+        self.model = owner
+        self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
+        self.m = torch.zeros_like(owner.flat)
+        self.v = torch.zeros_like(owner.flat)
+        self.t = 0
+
+    def zero_grad(self, set_to_none: bool = True):
+        if self.model._grads_dirty:  # step() already cleared them inside the AdamW kernel
+            self.model.grad.zero_()
+            self.model._grads_dirty = False
+
+    def step(self):
+        g = self.param_groups[0]
+        m = self.model
+        self.t += 1
+        with torch.cuda.device(m.device):
+            L.check(L.load().clipdlm_adamw(L.ptr(m.flat), L.ptr(m.grad), L.ptr(self.m), L.ptr(self.v), L.ptr(m.shadow_hi), L.ptr(m.shadow_lo),
+                                           m.n_params, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.t,
+                                           1.0 / m.dp_world, 1, m._stream()))
+        m._grads_dirty = False  # the kernel zeroed them
+
+    def state_dict(self):
+        return {"m": self.m.clone(), "v": self.v.clone(), "t": self.t, "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+        self.param_groups = [dict(g) for g in sd["param_groups"]]

@@ -91,7 +91,8 @@ typedef struct clipdlm_bf { void* hi; void* lo; } clipdlm_bf_t;
  * Writes z (pre-LN) and h (post-LN, post-dropout). */
 typedef struct clipdlm_embed {
   int32_t R, B, Ltxt, L, D, fusion, mode, guided;
-  const float* x_in;            /* mode 0 */
+  const float* x_in;            /* mode 0: fp32, row r at x_in + r * x_in_stride, position p at + p * D */
+  int64_t x_in_stride;          /* elements between consecutive rows; 0 = Ltxt * D (dense) */
   const float* emb_table; const int32_t* ids; const float* noise; const float* coef_a; const float* coef_b; /* mode 1 */
   const float* img_proj; const float* txt_proj; /* [B, D] fp32 (image_linear / text_linear outputs) */
   const float* seg; const float* pos;           /* [2, D], [max_pos, D] */
@@ -106,13 +107,17 @@ int clipdlm_embed_bwd(const clipdlm_bf_t* dz, int32_t R, int32_t B, int32_t Ltxt
 
 /* LayerNorm over the last dim (HF nn.LayerNorm eps=1e-12; modeling_distilbert.py:120,257,261,516). y = LN(z)*w + b (+dropout). */
 int clipdlm_layernorm_fwd(const clipdlm_bf_t* z, const float* w, const float* b, float eps, int64_t rows, int32_t D,
-                          const clipdlm_bf_t* y, uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream);
+                          const clipdlm_bf_t* y, float* y_f32 /* optional fp32 copy of y, may be NULL */,
+                          uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream);
 /* dz = LN'(z) applied to dy (dy masked by the output dropout if drop_p_out > 0); dw, db += (fp32 atomics);
- * optional dz_drop = dz * mask_in / (1 - p_in) (gradient entering a dropout that preceded the residual add). */
+ * optional dz_drop = dz * mask_in / (1 - p_in) (gradient entering a dropout that preceded the residual add);
+ * optional gelu_u: dz *= gelu'(u) (MLM transform head, z = gelu(u)); optional dbias[D] += column sums of
+ * (dz_drop if given else dz) = the bias gradient of the Linear that produced z's non-residual branch. */
 int clipdlm_layernorm_bwd(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, int64_t rows, int32_t D,
                           const clipdlm_bf_t* dz, float* dw, float* db,
                           uint64_t drop_seed, uint32_t drop_site_out, float drop_p_out,
-                          const clipdlm_bf_t* dz_drop, uint32_t drop_site_in, float drop_p_in, clipdlm_stream stream);
+                          const clipdlm_bf_t* dz_drop, uint32_t drop_site_in, float drop_p_in,
+                          const clipdlm_bf_t* gelu_u, float* dbias, clipdlm_stream stream);
 
 /* Multi-head self-attention over L <= 128 positions, one warp per (row, head); qkv [R*L, 3*D] (q | k | v).
  * Replaces DistilBertSelfAttention / sdpa (modeling_distilbert.py:126-151,177-207). keymask[r] bit j = key j visible
@@ -130,7 +135,10 @@ int clipdlm_colsum(const clipdlm_bf_t* x, int64_t rows, int32_t N, float* out, c
  * value added to *loss_acc (double) and gradient written to dx [R*L, D] (rows p >= Ltxt zeroed).
  * kind: 0 series_sum_sample_mean, 1 series_sum, 2 mse_series_mean, 3 mse_series_sum. batch_size = reference BATCH_SIZE
  * (divisor of kinds 1 and 3); R_total = rows of the whole pass (divisor of the means) when called per chunk. */
-int clipdlm_embed_loss(const clipdlm_bf_t* x_out, const float* emb_table, const int32_t* ids, int32_t R, int32_t B, int32_t Ltxt,
+int clipdlm_embed_loss(const clipdlm_bf_t* x_out, const float* emb_table, const int32_t* ids,
+                       const float* target /* optional explicit target [target_rows, Ltxt, D] fp32 (x_tgt of the x_{t-1} objective,
+                                              CLIP-DDPM.py:421): row r uses target[r % target_rows]; NULL = E[ids[r % B]] */,
+                       int32_t target_rows, int32_t R, int32_t B, int32_t Ltxt,
                        int32_t L, int32_t D, int32_t kind, int64_t R_total, int32_t batch_size, float weight,
                        double* loss_acc, const clipdlm_bf_t* dx, clipdlm_stream stream);
 
@@ -143,8 +151,9 @@ int clipdlm_small_linear_bwd(const float* x, const float* dy, int32_t B, int32_t
 
 /* Flat multi-tensor AdamW (torch.optim.AdamW defaults, decoupled weight decay on every element; CLIP-DDPM.py:335,484),
  * refreshing the bf16 (pair) shadow copy the GEMMs read. grad_scale multiplies g (1/world_size after a sum all-reduce). */
-int clipdlm_adamw(float* p, const float* g, float* m, float* v, void* shadow_hi, void* shadow_lo, int64_t n, float lr,
+int clipdlm_adamw(float* p, float* g, float* m, float* v, void* shadow_hi, void* shadow_lo, int64_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                  int32_t zero_grad /* 1: g is cleared in the same pass (trainer.zero_grad(), CLIP-DDPM.py:471) */,
                   clipdlm_stream stream);
 /* fp32 -> bf16 (pair) conversion (weights shadow refresh, frozen embedding table). */
 int clipdlm_to_bf16(const float* x, void* hi, void* lo, int64_t n, clipdlm_stream stream);
@@ -153,6 +162,15 @@ int clipdlm_to_f32(const void* hi, const void* lo, float* y, int64_t n, clipdlm_
 /* y[r, :] = x[(r / len) * stride + r % len, :] gather of the first `len` of every `stride` rows, to fp32. */
 int clipdlm_gather_rows_f32(const clipdlm_bf_t* x, int64_t rows_out, int32_t len, int32_t stride, int32_t D, float* y,
                             clipdlm_stream stream);
+/* q_sample / diffuse_t (CLIP-DDPM.py:347-362) as a standalone op: out[s, :] = coef_a[s] * x0 + coef_b[s] * noise over n elements
+ * (n = B * Ltxt * D, one noise draw shared by the S samples; coef_a = sqrt(alpha_bar[t]), coef_b = sqrt(1 - alpha_bar[t])).
+ * The training path never materialises this tensor (clipdlm_embed_fwd mode 1 fuses it); this entry point serves diffuse_t(). */
+int clipdlm_q_sample(const float* x0, const float* noise, const float* coef_a, const float* coef_b, int64_t n, int32_t S, float* out,
+                     clipdlm_stream stream);
+/* Key-visibility words for the attention kernels, keymask[r][ceil(L/32)]: text keys from attn_mask[r % B] (NULL = all
+ * visible), image-CLIP key always visible, text-CLIP key visible iff guided (CLIP-DDPM.py:296-297). */
+int clipdlm_keymask(const int32_t* attn_mask, int32_t R, int32_t B, int32_t Ltxt, int32_t L, int32_t fusion, int32_t guided,
+                    uint32_t* keymask, clipdlm_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Engine: the composite hot path (model forward / loss+backward / denoise step) orchestrated natively.
@@ -201,7 +219,7 @@ void clipdlm_engine_destroy(clipdlm_engine_t* e);
  * train = 1 enables dropout and keeps activations for clipdlm_engine_backward. x_out (fp32 [R, L, D]) may be NULL. */
 typedef struct clipdlm_pass {
   int32_t R, B, mode, guided, train;
-  const float* x_in;
+  const float* x_in; int64_t x_in_stride; /* mode 0 input and its row pitch in elements (0 = dense max_len * dim) */
   const int32_t* ids; const float* noise; const float* coef_a; const float* coef_b;
   const float* image_clip; const float* text_clip; const int32_t* attn_mask;
   uint64_t drop_seed;
@@ -209,9 +227,11 @@ typedef struct clipdlm_pass {
 } clipdlm_pass_t;
 int clipdlm_engine_forward(clipdlm_engine_t* e, const clipdlm_pass_t* p, clipdlm_stream stream);
 
-/* lm_head over x_out[:, :max_len] of the last forward: logits fp32 [R*max_len, vocab] (may be NULL) and/or argmax ids
- * int32 [R*max_len] (may be NULL). Replaces self.lm_head(x_out[:, :MAX_LENGTH]) and argmax (CLIP-DDPM.py:323,620). */
-int clipdlm_engine_lm_head(clipdlm_engine_t* e, float* logits, int32_t* argmax, clipdlm_stream stream);
+/* lm_head over x_out[:, :max_len] of the last forward: logits fp32 [R*max_len, ld_logits] with ld_logits >= vocab rounded
+ * up to 32 (may be NULL; the padding columns receive zeros) and/or argmax ids int32 [R*max_len] (may be NULL; computed by
+ * the fused GEMM + running-argmax epilogue, logits never reach HBM). The bf16 copy of the lm_head weight (emb_hi/lo) must be
+ * zero-padded to a multiple of 256 rows. Replaces self.lm_head(x_out[:, :MAX_LENGTH]) and argmax (CLIP-DDPM.py:323,620). */
+int clipdlm_engine_lm_head(clipdlm_engine_t* e, float* logits, int64_t ld_logits, int32_t* argmax, clipdlm_stream stream);
 
 /* Loss of the last forward + full backward into bufs.grads (+=). Adds to losses[0] (embedding loss) and losses[1]
  * (cross-entropy, unweighted) as doubles. Row means use R_total (rows of the whole pass when chunked).
@@ -224,6 +244,8 @@ typedef struct clipdlm_loss_cfg {
   int64_t R_total;
   float rounding_weight;  /* ROUNDING_WEIGHT */
   int32_t backward;       /* 0 = losses only (validate, CLIP-DDPM.py:488-501) */
+  const float* target;    /* optional explicit embedding-loss target, see clipdlm_embed_loss */
+  int32_t target_rows;
 } clipdlm_loss_cfg_t;
 int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* lc, double* losses, clipdlm_stream stream);
 

@@ -123,7 +123,7 @@ def init_params(hp: dict, seed: int = 0, closed_form: bool = False) -> Dict[str,
     """Trainable parameters + the frozen `embedding.weight` (== lm_head.weight values, lm_head.bias = 0; CLIP-DDPM.py:245-247).
 
     closed_form=False: HF-style random init (N(0, 0.02) weights, LN = (1, 0), zero biases; CLIP linears Kaiming-uniform-like;
-    segment N(0,1)) from a torch generator.  closed_form=True: a generator-free cosine formula, reproducible on any platform,
+    segment N(0,1)) from a torch generator.  closed_form=True: a generator-free integer-hash formula, reproducible on any platform,
     used by the committed golden fixtures.
     """
     g = torch.Generator().manual_seed(seed)
@@ -132,8 +132,7 @@ def init_params(hp: dict, seed: int = 0, closed_form: bool = False) -> Dict[str,
     for k, (name, shape) in enumerate(names):
         n = int(math.prod(shape))
         if closed_form:
-            idx = torch.arange(n, dtype=torch.float64)
-            base = torch.cos(idx * 0.6180339887498949 * (k + 1) + 0.1 * k + seed).reshape(shape)
+            base = hash_uniform(n, 1000 * seed + k).reshape(shape)  # unit variance, platform independent
             if "LayerNorm.weight" in name or "layer_norm.weight" in name:
                 v = 1.0 + 0.05 * base
             elif name.endswith(".bias"):
@@ -378,6 +377,43 @@ def sample(P: Dict[str, Tensor], image_clip: Tensor, hp: dict, n_steps: int = 5,
             outs.append(out.argmax(dim=-1))
     indexes = torch.softmax(out, dim=-1).argmax(dim=-1)  # :620
     return (indexes, restored, outs) if return_all else (indexes, restored)
+
+
+def _s64(c: int) -> int:
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _lsr(x: Tensor, s: int) -> Tensor:
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def hash_uniform(n: int, k: int) -> Tensor:
+    """n pseudo-random float64 values, uniform with zero mean and unit variance, from the splitmix64 integer hash of
+    (index, stream k). Pure int64 arithmetic (wrapping multiply): bit-identical on every platform and torch version."""
+    x = torch.arange(n, dtype=torch.int64) + _s64(((k + 1) * 0x9E3779B97F4A7C15) & ((1 << 64) - 1))
+    x = (x ^ _lsr(x, 30)) * _s64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _s64(0x94D049BB133111EB)
+    x = x ^ _lsr(x, 31)
+    u = _lsr(x, 11).double() / float(1 << 53)
+    return (u - 0.5) * math.sqrt(12.0)
+
+
+def closed_form_tensor(shape, k: int, scale: float = 1.0) -> Tensor:
+    """Generator-free pseudo-random tensor (integer hash): identical on every platform / torch version.
+    Used by the golden fixtures for noise, CLIP features and `restored`."""
+    return (scale * hash_uniform(int(math.prod(shape)), 7777 + k)).reshape(shape).float()
+
+
+def closed_form_batch(hp: dict, k: int = 0, ragged: bool = True) -> dict:
+    B, ML, V = hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["VOCAB_SIZE"]
+    ids = ((torch.arange(B * ML, dtype=torch.int64) * 7919 + 104729 * (k + 1)) % V).reshape(B, ML)
+    mask = torch.ones(B, ML, dtype=torch.int64)
+    if ragged:
+        lens = 6 + (torch.arange(B) * 5 + k) % (ML - 5)
+        mask = (torch.arange(ML)[None, :] < lens[:, None]).to(torch.int64)
+    img = F.normalize(closed_form_tensor((B, hp["CLIP_DIM"]), 11 + k), dim=-1)
+    txt = F.normalize(closed_form_tensor((B, hp["CLIP_DIM"]), 23 + k), dim=-1)
+    return {"input_ids": ids, "attention_mask": mask, "image_clip": img, "text_clip": txt}
 
 
 def synthetic_batch(hp: dict, seed: int = 0, ragged: bool = False, device="cpu") -> dict:

@@ -1,0 +1,58 @@
+"""Shared helpers for the test-suite (tests/ may import oracle/; the product package never does)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import clipdlm_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_T = [0, 17, 400, 999]
+
+
+def golden_hp(**kw):
+    hp = O.default_hparams()
+    hp.update(BATCH_SIZE=3, SAMPLE_SIZE=4, N_LAYERS=2, VOCAB_SIZE=997, DROPOUT=0.0, ATTENTION_DROPOUT=0.0)
+    hp.update(kw)
+    return hp
+
+
+GOLDEN_CASES = {
+    "concat_l1": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean"),
+    "add_l1": dict(CLIP_ADDING_METHOD="add", LOSS_FUNC="series_sum_sample_mean"),
+    "concat_mse_mean": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_mean"),
+    "concat_series_sum": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum"),
+    "concat_mse_sum": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_sum"),
+}
+FULL_CASES = ("concat_l1", "add_l1")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_inputs(hp):
+    """The closed-form inputs tests/golden/make_golden.py fed to the reference."""
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["DIM"]
+    R = 2
+    mask = torch.ones(R, ML, dtype=torch.int64)
+    mask[1, 9:] = 0
+    Lfull = ML + (2 if hp["CLIP_ADDING_METHOD"] == "concat" else 0)
+    return dict(
+        batch=O.closed_form_batch(hp, k=1, ragged=True),
+        fwd_x=O.closed_form_tensor((R, ML, D), 3, 0.5), fwd_img=O.closed_form_tensor((R, 1, hp["CLIP_DIM"]), 4, 0.05),
+        fwd_txt=O.closed_form_tensor((R, 1, hp["CLIP_DIM"]), 5, 0.05), fwd_mask=mask,
+        restored=O.closed_form_tensor((B, Lfull, D), 6, 1.0),
+        t=torch.tensor(GOLDEN_T).reshape(S, 1, 1), noise_t=O.closed_form_tensor((B, ML, D), 7, 1.0),
+        noise_1=O.closed_form_tensor((B, ML, D), 8, 1.0),
+    )
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

@@ -1,0 +1,119 @@
+"""Generates tests/golden/*.npz by running the REAL reference (CLIP-DDPM.py slices exec'd from /root/reference, driving HF
+DistilBertForMaskedLM) on closed-form (generator-free) weights and inputs. Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The fixtures travel with the repo; /root/reference does not. tests/test_oracle_golden.py replays them against the oracle
+(CPU) and tests/test_parity_gpu.py against the CUDA path (B200).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import clipdlm_oracle as O  # noqa: E402
+from oracle import reference_harness as H  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden_hp(**kw):
+    hp = O.default_hparams()
+    hp.update(BATCH_SIZE=3, SAMPLE_SIZE=4, N_LAYERS=2, VOCAB_SIZE=997, DROPOUT=0.0, ATTENTION_DROPOUT=0.0)
+    hp.update(kw)
+    return hp
+
+
+GOLDEN_T = [0, 17, 400, 999]
+
+
+class _TorchProxy:
+    """`torch` as seen by the exec'd reference code, with the two random draws of train_func pinned."""
+
+    def __init__(self, t, noises):
+        self._t, self._noises = t, list(noises)
+
+    def __getattr__(self, k):
+        return getattr(torch, k)
+
+    def randint(self, *a, **k):
+        return self._t.clone()
+
+    def normal(self, *a, **k):
+        return self._noises.pop(0).clone()
+
+
+def make_case(name: str, full: bool = True, **kw):
+    hp = golden_hp(**kw)
+    ns = H.build_namespace(hp)
+    model = H.build_model(ns, hp, seed=0)
+    P = O.init_params(hp, seed=0, closed_form=True)
+    H.load_params(model, P)
+    batch = O.closed_form_batch(hp, k=1, ragged=True)
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["DIM"]
+    out = {}
+    # forward (eval) on explicit rows
+    model.eval()
+    R = 2
+    xin = O.closed_form_tensor((R, ML, D), 3, 0.5)
+    img = O.closed_form_tensor((R, 1, hp["CLIP_DIM"]), 4, 0.05)
+    txt = O.closed_form_tensor((R, 1, hp["CLIP_DIM"]), 5, 0.05)
+    mask = torch.ones(R, ML, dtype=torch.int64); mask[1, 9:] = 0
+    with torch.no_grad():
+        logits, x_out = model(xin, img, txt, mask, torch.tensor([1, 0]).repeat(R, 1))
+    out["fwd_x_out"] = x_out.numpy() if full else x_out[:, :, :8].numpy()
+    out["fwd_argmax"] = logits.argmax(-1).numpy()
+    out["fwd_logits_head"] = logits[:, :, :64].numpy()
+    top2 = logits.topk(2, dim=-1).values
+    out["fwd_top2_gap"] = (top2[..., 0] - top2[..., 1]).numpy()
+    # denoise loop, 5 steps
+    Lfull = x_out.shape[1]
+    restored = O.closed_form_tensor((B, Lfull, D), 6, 1.0)
+    r = restored.clone()
+    with torch.no_grad():
+        for _ in range(5):
+            o, r = model(r[:, :ML, :], batch["image_clip"].unsqueeze(1), torch.zeros_like(batch["image_clip"]).unsqueeze(1),
+                         torch.ones(B, ML), torch.tensor([1, 0]).repeat(B, 1))
+    out["sample_ids"] = torch.softmax(o, -1).argmax(-1).numpy()
+    t2 = o.topk(2, dim=-1).values
+    out["sample_top2_gap"] = (t2[..., 0] - t2[..., 1]).numpy()
+    out["sample_restored"] = r.numpy() if full else r[:, :, :8].numpy()
+    # one train step (train mode; dropout p = 0), pinned t / noise
+    model.train()
+    t = torch.tensor(GOLDEN_T).reshape(S, 1, 1)
+    n_t = O.closed_form_tensor((B, ML, D), 7, 1.0)
+    n_1 = O.closed_form_tensor((B, ML, D), 8, 1.0)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    ns["torch"] = _TorchProxy(t, [n_t, n_1])
+    l, a, b, c = ns["train_func"](model, opt, batch)
+    ns["torch"] = torch
+    out["train_losses"] = np.array([l.item(), a.item(), b.item(), c.item()], dtype=np.float64)
+    grads = {n: p.grad.detach() for n, p in model.named_parameters() if p.grad is not None}
+    names = [n for n in O.trainable_names(hp) if n in grads]
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array([float(grads[n].double().norm()) for n in names])
+    for n in names:  # full gradients of the small tensors + first rows of the matrices
+        g = grads[n]
+        out["grad::" + n] = (g if g.numel() <= 4096 else g.reshape(-1)[:(4096 if full else 256)]).numpy()
+    after = H.export_params(model)
+    out["after_norms"] = np.array([float(after[n].double().norm()) for n in names])
+    for n in ("model.vocab_layer_norm.weight", "model.distilbert.transformer.layer.0.ffn.lin1.bias", "image_linear.bias"):
+        out["after::" + n] = after[n].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "losses", out["train_losses"], "min top-2 gaps", out["fwd_top2_gap"].min(), out["sample_top2_gap"].min())
+
+
+if __name__ == "__main__":
+    if not H.available():
+        sys.exit("reference unavailable")
+    torch.set_num_threads(8)
+    make_case("concat_l1", CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean")
+    make_case("add_l1", CLIP_ADDING_METHOD="add", LOSS_FUNC="series_sum_sample_mean")
+    make_case("concat_mse_mean", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_mean")
+    make_case("concat_series_sum", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum")
+    make_case("concat_mse_sum", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_sum")

@@ -1,0 +1,106 @@
+"""CPU (-m "not gpu"): host logic, the C-ABI library surface, and the no-fallback rule. No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from _util import O, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    import clipdlm
+    from clipdlm import _lib as L
+    header = open(os.path.join(ROOT, "include", "clipdlm.h")).read()
+    declared = set(re.findall(r"\b(clipdlm_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = L.load()  # resolves every symbol, raises AttributeError otherwise
+    nm = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (clipdlm_[a-z0-9_]+)", nm))
+    assert declared <= exported
+    assert lib.clipdlm_version() >= 100
+
+
+def test_sass_is_blackwell_native():
+    """The GEMM must carry tcgen05 / TMA instructions (UTC*MMA, UTMALDG), not a legacy mma.sync path."""
+    from clipdlm import _lib as L
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "UTMALDG" in sass
+    assert "LDTM" in sass
+    assert "sm_100a" in sass
+
+
+def test_param_layout_matches_reference_counts():
+    from clipdlm import _lib as L
+    from clipdlm import default_hparams
+    lib = L.load()
+    for layers, dim, heads, hid, expect in ((6, 768, 12, 3072, 44_303_616), (12, 768, 12, 3072, 86_830_848), (24, 1024, 16, 4096, None)):
+        cfg = L.Config(layers, dim, heads, hid, 30522, 16, 512, 512, 0, 0, 1e-12, 0.1, 0.1)
+        n = lib.clipdlm_param_count(C.byref(cfg))
+        hp = O.default_hparams(); hp.update(N_LAYERS=layers, DIM=dim, N_HEADS=heads, HIDDEN_DIM=hid)
+        want = sum(int(torch.tensor(s).prod()) for _, s in O.param_names(hp))
+        assert n == want
+        if expect is not None:
+            assert n == expect  # SURVEY App. B / BASELINE.md section 3
+        offs = [lib.clipdlm_param_offset(C.byref(cfg), s) for s in range(L.P_LAYER0 + layers * L.P_PER_LAYER)]
+        assert offs == sorted(offs) and all(o % 8 == 0 for o in offs)  # 16-byte aligned bf16 shadows for TMA
+        assert lib.clipdlm_param_offset(C.byref(cfg), 10_000) == -1
+    cfg = L.Config(6, 768, 12, 3072, 30522, 16, 512, 512, 0, 0, 1e-12, 0.1, 0.1)
+    train = lib.clipdlm_workspace_bytes(C.byref(cfg), 4096, 512, 1)
+    infer = lib.clipdlm_workspace_bytes(C.byref(cfg), 4096, 512, 0)
+    assert 0 < infer < train < 40 * 2 ** 30
+    bad = L.Config(6, 700, 12, 3072, 30522, 16, 512, 512, 0, 0, 1e-12, 0.1, 0.1)
+    assert lib.clipdlm_workspace_bytes(C.byref(bad), 16, 8, 1) == 0 and b"dim" in lib.clipdlm_last_error()
+
+
+def test_hparams_follow_reference_defaults():
+    import clipdlm
+    hp = clipdlm.default_hparams()
+    ref = O.default_hparams()
+    for k, v in ref.items():
+        assert hp[k] == v, k
+    assert clipdlm.model_name(hp).startswith("epoch5_lossseries_sum_sample_mean_lr1E-04-5E-05_schedulerlinspace_round5E-01_dynamic-1_clipconcat")
+    lrs = clipdlm.learning_rates(hp)
+    assert len(lrs) == 5 and abs(lrs[0] - 1e-4) < 1e-10 and abs(lrs[-1] - 5e-5) < 1e-10
+    assert len(clipdlm.learning_rates(clipdlm.default_hparams(SCHEDULER="cosine"))) == 15  # cosine_annealing(): 5 epochs x 3
+    lg = clipdlm.learning_rates(clipdlm.default_hparams(SCHEDULER="logspace"))
+    assert abs(lg[2] - (1e-4 * 5e-5) ** 0.5) < 1e-9
+    with pytest.raises(KeyError):
+        clipdlm.default_hparams(NOT_A_KEY=1)
+    assert torch.equal(clipdlm.alpha_cumprod(hp), O.alpha_cumprod(ref))
+    assert torch.equal(clipdlm.alpha_cumprod(clipdlm.default_hparams(COSIN_SCHEDULE=False)), O.alpha_cumprod(dict(ref, COSIN_SCHEDULE=False)))
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a GPU (no oracle / eager fallback)."""
+    import clipdlm
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(clipdlm.ClipdlmError):
+        clipdlm.DistilBertModel(None, None, None)
+    with pytest.raises(clipdlm.ClipdlmError):
+        clipdlm.diffuse_t(torch.zeros(1, 16, 768), torch.zeros(1, dtype=torch.int64), clipdlm.default_hparams())
+    src = ""
+    pkg_dir = os.path.join(ROOT, "diffusion-image-captioning_b200")
+    for f in os.listdir(pkg_dir):
+        if f.endswith(".py"):
+            src += open(os.path.join(pkg_dir, f)).read()
+    assert "oracle" not in src.replace("no oracle", "")  # the product never imports the checker
+
+
+def test_shard_range_covers_everything():
+    from clipdlm import shard_range
+    for n in (0, 1, 7, 512, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1

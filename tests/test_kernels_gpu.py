@@ -1,0 +1,402 @@
+"""-m gpu: every hand-written kernel against a plain PyTorch fp32 reference of the same op, through the C-ABI.
+pair=True is the parity ("bf16x3") storage mode, pair=False plain bf16."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import O, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import _gpu
+    assert torch.cuda.is_available(), "GPU tests selected on a box without CUDA"
+    torch.manual_seed(0)
+    return _gpu
+
+
+# ------------------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("shape", [(16, 768, 768), (144, 2304, 768), (1000, 768, 3072), (4096 + 48, 3072, 768)])
+def test_gemm_fwd_epilogues(G, shape, pair):
+    M, N, K = shape
+    a = torch.randn(M, K, device=G.DEV); w = torch.randn(N, K, device=G.DEV) * 0.05
+    bias = torch.randn(N, device=G.DEV); res = torch.randn(M, N, device=G.DEV)
+    ah, al = G.split(a, pair); wh, wl = G.split(w, pair); rh, rl = G.split(res, pair)
+    ref_in_a, ref_in_w, ref_res = G.join(ah, al), G.join(wh, wl), G.join(rh, rl)
+    ref = ref_in_a.double() @ ref_in_w.double().t() + bias.double()
+    oh, ol = G.empty_pair((M, N), pair)
+    G.gemm(a_hi=ah, a_lo=al, b_hi=wh, b_lo=wl, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out_hi=oh, out_lo=ol, ldo=N, bias=bias,
+           res_hi=rh, res_lo=rl, ldr=N)
+    assert rel(G.join(oh, ol), ref + ref_res.double()) < (1e-5 if pair else 4e-3)
+    # dual store: pre-activation + gelu
+    o2h, o2l = G.empty_pair((M, N), pair)
+    G.gemm(a_hi=ah, a_lo=al, b_hi=wh, b_lo=wl, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out_hi=oh, out_lo=ol, out2_hi=o2h, out2_lo=o2l,
+           ldo=N, bias=bias)
+    assert rel(G.join(oh, ol), ref) < (1e-5 if pair else 4e-3)
+    assert rel(G.join(o2h, o2l), F.gelu(ref.float()).double()) < (2e-5 if pair else 6e-3)
+    # gelu-only output (inference path: out NULL, out2 set) and fp32 output
+    o3h, o3l = G.empty_pair((M, N), pair)
+    of = torch.zeros(M, N, device=G.DEV)
+    G.gemm(a_hi=ah, a_lo=al, b_hi=wh, b_lo=wl, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out2_hi=o3h, out2_lo=o3l, out_f32=of, ldo=N, bias=bias)
+    assert torch.equal(o3h, o2h)
+    assert rel(of, ref) < (1e-5 if pair else 4e-3)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_gemm_dgrad_wgrad(G, pair):
+    T, N, K = 1000, 3072, 768  # y[T,N] = x[T,K] W[N,K]^T
+    dy = torch.randn(T, N, device=G.DEV); w = torch.randn(N, K, device=G.DEV) * 0.05; x = torch.randn(T, K, device=G.DEV)
+    u = torch.randn(T, K, device=G.DEV); res = torch.randn(T, K, device=G.DEV)
+    dh, dl = G.split(dy, pair); wh, wl = G.split(w, pair); xh, xl = G.split(x, pair); uh, ul = G.split(u, pair); rh, rl = G.split(res, pair)
+    dyr, wr, xr, ur, rr = G.join(dh, dl).double(), G.join(wh, wl).double(), G.join(xh, xl).double(), G.join(uh, ul), G.join(rh, rl).double()
+    oh, ol = G.empty_pair((T, K), pair)
+    G.gemm(a_hi=dh, a_lo=dl, b_hi=wh, b_lo=wl, lda=N, ldb=K, M=T, N=K, K=N, a_major=0, b_major=1, epilogue=0, out_hi=oh, out_lo=ol, ldo=K,
+           res_hi=rh, res_lo=rl, ldr=K)
+    assert rel(G.join(oh, ol), dyr @ wr + rr) < (1e-5 if pair else 4e-3)
+    G.gemm(a_hi=dh, a_lo=dl, b_hi=wh, b_lo=wl, lda=N, ldb=K, M=T, N=K, K=N, a_major=0, b_major=1, epilogue=0, out_hi=oh, out_lo=ol, ldo=K,
+           u_hi=uh, u_lo=ul, ldu=K)
+    ur_ = ur.clone().requires_grad_(True)
+    F.gelu(ur_).sum().backward()
+    assert rel(G.join(oh, ol), (dyr @ wr) * ur_.grad.double()) < (2e-5 if pair else 6e-3)
+    acc = torch.full((N, K), 0.5, device=G.DEV)
+    G.gemm(a_hi=dh, a_lo=dl, b_hi=xh, b_lo=xl, lda=N, ldb=K, M=N, N=K, K=T, a_major=1, b_major=1, epilogue=1, acc_f32=acc, ldo=K)
+    assert rel(acc, dyr.t() @ xr + 0.5) < (1e-5 if pair else 4e-3)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("R", [1, 9, 300])
+def test_gemm_lse_smgrad_gather_scatter(G, R, pair):
+    Ltxt, Lf, D, V = 16, 18, 768, 30522
+    M = R * Ltxt
+    xo = torch.randn(R * Lf, D, device=G.DEV)
+    E = torch.randn(V, D, device=G.DEV) * 0.02
+    Epad = torch.zeros((V + 255) // 256 * 256, D, device=G.DEV); Epad[:V] = E
+    xh, xl = G.split(xo, pair); eh, el = G.split(Epad, pair)
+    B = max(1, R // 3) if R % 3 == 0 else R
+    tgt = torch.randint(0, V, (B * Ltxt,), device=G.DEV, dtype=torch.int32)
+    nt = (V + 255) // 256
+    pm = torch.zeros(nt, M, device=G.DEV); ps = torch.zeros(nt, M, device=G.DEV); pa = torch.zeros(nt, M, device=G.DEV, dtype=torch.int32)
+    tl = torch.zeros(M, device=G.DEV)
+    G.gemm(a_hi=xh, a_lo=xl, b_hi=eh, b_lo=el, lda=D, ldb=D, M=M, N=V, K=D, gather_len=Ltxt, gather_stride=Lf, epilogue=2,
+           part_max=pm, part_sum=ps, part_arg=pa, tgt_logit=tl, targets=tgt, tgt_period=B * Ltxt)
+    lse = torch.zeros(M, device=G.DEV); am = torch.zeros(M, device=G.DEV, dtype=torch.int32)
+    acc = torch.zeros(1, device=G.DEV, dtype=torch.float64)
+    G.L.check(G.lib().clipdlm_lse_combine(pm.data_ptr(), ps.data_ptr(), pa.data_ptr(), nt, M, tl.data_ptr(), lse.data_ptr(), am.data_ptr(),
+                                          acc.data_ptr(), 1.0 / R, G.st()))
+    xg = G.join(xh, xl).view(R, Lf, D)[:, :Ltxt].reshape(M, D).double()
+    logits = xg @ G.join(eh, el)[:V].double().t()
+    ref_lse = torch.logsumexp(logits, -1)
+    tfull = tgt.long().repeat(M // (B * Ltxt))
+    ref_loss = (ref_lse - logits.gather(1, tfull[:, None])[:, 0]).sum() / R
+    assert rel(lse, ref_lse) < (1e-6 if pair else 1e-4)
+    assert abs(acc.item() - ref_loss.item()) < (1e-5 if pair else 2e-3) * abs(ref_loss.item())
+    top2 = logits.topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > (1e-4 if pair else 2e-2)
+    assert torch.equal(am.long()[safe], logits.argmax(-1)[safe]) and safe.float().mean() > 0.5
+    # softmax-CE gradient + dgrad with scatter/residual into [R*Lf, D]
+    ldl = nt * 256
+    dlh, dll = G.empty_pair((M, ldl), pair)
+    G.gemm(a_hi=xh, a_lo=xl, b_hi=eh, b_lo=el, lda=D, ldb=D, M=M, N=V, K=D, gather_len=Ltxt, gather_stride=Lf, epilogue=3, out_hi=dlh,
+           out_lo=dll, ldo=ldl, lse=lse, targets=tgt, tgt_period=B * Ltxt, grad_scale=0.37)
+    ref_dl = (torch.softmax(logits, -1) - F.one_hot(tfull, V).double()) * 0.37
+    assert rel(G.join(dlh, dll)[:, :V], ref_dl) < (2e-5 if pair else 6e-3)
+    assert float(G.join(dlh, dll)[:, V:].abs().max()) == 0.0
+    g0 = torch.randn(R * Lf, D, device=G.DEV)
+    gh, gl = G.split(g0, pair)
+    before = G.join(gh, gl).clone()
+    G.gemm(a_hi=dlh, a_lo=dll, b_hi=eh, b_lo=el, lda=ldl, ldb=D, M=M, N=D, K=V, a_major=0, b_major=1, epilogue=0, out_hi=gh, out_lo=gl, ldo=D,
+           res_hi=gh, res_lo=gl, ldr=D, scatter_len=Ltxt, scatter_stride=Lf)
+    ref_g = before.view(R, Lf, D).double().clone()
+    ref_g[:, :Ltxt] += (G.join(dlh, dll)[:, :V].double() @ G.join(eh, el)[:V].double()).view(R, Ltxt, D)
+    assert rel(G.join(gh, gl), ref_g.view(R * Lf, D)) < (1e-5 if pair else 5e-3)
+    assert torch.equal(G.join(gh, gl).view(R, Lf, D)[:, Ltxt:], before.view(R, Lf, D)[:, Ltxt:])  # CLIP rows untouched
+
+
+def test_gemm_dropout_epilogue(G):
+    M, N, K = 512, 768, 256
+    a = torch.randn(M, K, device=G.DEV).bfloat16(); w = (torch.randn(N, K, device=G.DEV) * 0.05).bfloat16()
+    o1 = torch.zeros(M, N, device=G.DEV); o2 = torch.zeros(M, N, device=G.DEV); o0 = torch.zeros(M, N, device=G.DEV)
+    G.gemm(a_hi=a, b_hi=w, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out_f32=o0, ldo=N)
+    G.gemm(a_hi=a, b_hi=w, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out_f32=o1, ldo=N, drop_seed=1234, drop_site=5, drop_p=0.1)
+    G.gemm(a_hi=a, b_hi=w, lda=K, ldb=K, M=M, N=N, K=K, epilogue=0, out_f32=o2, ldo=N, drop_seed=1234, drop_site=5, drop_p=0.1)
+    assert torch.equal(o1, o2)
+    keep = o1 != 0
+    assert abs(keep.float().mean().item() - 0.9) < 0.01
+    assert rel(o1[keep], o0[keep] / 0.9) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("D", [768, 1024])
+def test_layernorm_fwd_bwd(G, D, pair):
+    rows = 1003
+    z = torch.randn(rows, D, device=G.DEV) * 2 + 0.3
+    w = torch.randn(D, device=G.DEV) * 0.2 + 1; b = torch.randn(D, device=G.DEV) * 0.1
+    dy = torch.randn(rows, D, device=G.DEV)
+    u = torch.randn(rows, D, device=G.DEV)
+    zh, zl = G.split(z, pair); dh, dl = G.split(dy, pair); uh, ul = G.split(u, pair)
+    zr = G.join(zh, zl).clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    y_ref = F.layer_norm(zr, (D,), wr, br, 1e-12)
+    yh, yl = G.empty_pair((rows, D), pair)
+    yf = torch.zeros(rows, D, device=G.DEV)
+    lib, L = G.lib(), G.L
+    L.check(lib.clipdlm_layernorm_fwd(C.byref(G.bfp(zh, zl)), w.data_ptr(), b.data_ptr(), 1e-12, rows, D, C.byref(G.bfp(yh, yl)), yf.data_ptr(),
+                                      0, 0, 0.0, G.st()))
+    assert rel(yf, y_ref) < 1e-5
+    assert rel(G.join(yh, yl), y_ref) < (1e-5 if pair else 4e-3)
+    y_ref.backward(G.join(dh, dl))
+    gh, gl = G.empty_pair((rows, D), pair)
+    dw = torch.full((D,), 0.25, device=G.DEV); db = torch.zeros(D, device=G.DEV); dbias = torch.zeros(D, device=G.DEV)
+    L.check(lib.clipdlm_layernorm_bwd(C.byref(G.bfp(zh, zl)), C.byref(G.bfp(dh, dl)), w.data_ptr(), 1e-12, rows, D, C.byref(G.bfp(gh, gl)),
+                                      dw.data_ptr(), db.data_ptr(), 0, 0, 0.0, None, 0, 0.0, None, dbias.data_ptr(), G.st()))
+    assert rel(G.join(gh, gl), zr.grad) < (2e-5 if pair else 5e-3)
+    assert rel(dw - 0.25, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    assert rel(dbias, G.join(gh, gl).sum(0)) < 1e-4
+    # gelu' fusion (MLM transform head): dz *= gelu'(u)
+    ur = G.join(uh, ul).clone().requires_grad_(True)
+    F.gelu(ur).sum().backward()
+    g2h, g2l = G.empty_pair((rows, D), pair)
+    L.check(lib.clipdlm_layernorm_bwd(C.byref(G.bfp(zh, zl)), C.byref(G.bfp(dh, dl)), w.data_ptr(), 1e-12, rows, D, C.byref(G.bfp(g2h, g2l)),
+                                      None, None, 0, 0, 0.0, None, 0, 0.0, C.byref(G.bfp(uh, ul)), None, G.st()))
+    assert rel(G.join(g2h, g2l), zr.grad * ur.grad) < (3e-5 if pair else 8e-3)
+
+
+def test_layernorm_dropout_masks_consistent(G):
+    rows, D, p = 512, 768, 0.1
+    z = torch.randn(rows, D, device=G.DEV)
+    w = torch.ones(D, device=G.DEV); b = torch.full((D,), 3.0, device=G.DEV)  # b = 3 keeps outputs away from 0
+    zh, zl = G.split(z, True)
+    yf = torch.zeros(rows, D, device=G.DEV)
+    lib, L = G.lib(), G.L
+    L.check(lib.clipdlm_layernorm_fwd(C.byref(G.bfp(zh, zl)), w.data_ptr(), b.data_ptr(), 1e-12, rows, D, None, yf.data_ptr(), 77, 3, p, G.st()))
+    mask = (yf != 0).float()
+    assert abs(mask.mean().item() - (1 - p)) < 0.01
+    ref = F.layer_norm(G.join(zh, zl), (D,), w, b, 1e-12) * mask / (1 - p)
+    assert rel(yf, ref) < 1e-5
+    # the backward regenerates the same mask for dy (drop_out) and applies a second site's mask to dz (dz_drop)
+    dy = torch.randn(rows, D, device=G.DEV)
+    dh, dl = G.split(dy, True)
+    gh, gl = G.empty_pair((rows, D), True); g2h, g2l = G.empty_pair((rows, D), True)
+    dbias = torch.zeros(D, device=G.DEV)
+    L.check(lib.clipdlm_layernorm_bwd(C.byref(G.bfp(zh, zl)), C.byref(G.bfp(dh, dl)), w.data_ptr(), 1e-12, rows, D, C.byref(G.bfp(gh, gl)),
+                                      None, None, 77, 3, p, C.byref(G.bfp(g2h, g2l)), 3, p, None, dbias.data_ptr(), G.st()))
+    zr = G.join(zh, zl).clone().requires_grad_(True)
+    (F.layer_norm(zr, (D,), w, b, 1e-12) * mask / (1 - p)).backward(G.join(dh, dl))
+    assert rel(G.join(gh, gl), zr.grad) < 3e-5
+    assert rel(G.join(g2h, g2l), zr.grad * mask / (1 - p)) < 3e-5  # same (seed, site) => same mask
+    assert rel(dbias, G.join(g2h, g2l).sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, km_bool, R, L, D, H, mask_mult=None):
+    q, k, v = qkv.view(R, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    s = s.masked_fill(~km_bool[:, None, None, :], float("-inf"))
+    a = torch.softmax(s, -1)
+    if mask_mult is not None:
+        a = a * mask_mult
+    return (a @ v).permute(0, 2, 1, 3).reshape(R * L, D)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("L,R,D", [(18, 37, 768), (16, 5, 768), (66, 7, 1024), (1, 3, 768)])
+def test_attention_fwd_bwd(G, L, R, D, pair):
+    H = D // 64
+    qkv = torch.randn(R * L, 3 * D, device=G.DEV)
+    dctx = torch.randn(R * L, D, device=G.DEV)
+    km = torch.rand(R, L, device=G.DEV) > 0.3
+    km[:, min(L - 1, 2)] = True
+    kw = (L + 31) // 32
+    words = torch.zeros(R, kw, device=G.DEV, dtype=torch.int64)
+    for j in range(L):
+        words[:, j // 32] |= km[:, j].long() << (j % 32)
+    words32 = (words & 0xFFFFFFFF).to(torch.int64)
+    words32 = torch.where(words32 >= 2 ** 31, words32 - 2 ** 32, words32).to(torch.int32).contiguous()
+    qh, ql = G.split(qkv, pair); dh, dl = G.split(dctx, pair)
+    ch, cl = G.empty_pair((R * L, D), pair)
+    lib, Lb = G.lib(), G.L
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qh, ql)), words32.data_ptr(), R, L, D, H, C.byref(G.bfp(ch, cl)), 0, 0, 0.0, G.st()))
+    qr = G.join(qh, ql).double().requires_grad_(True)
+    ref = _attn_ref(qr, km, R, L, D, H)
+    assert rel(G.join(ch, cl), ref) < (1e-5 if pair else 5e-3)
+    ref.backward(G.join(dh, dl).double())
+    gh, gl = G.empty_pair((R * L, 3 * D), pair)
+    Lb.check(lib.clipdlm_attn_bwd(C.byref(G.bfp(qh, ql)), words32.data_ptr(), C.byref(G.bfp(dh, dl)), R, L, D, H, C.byref(G.bfp(gh, gl)),
+                                  0, 0, 0.0, G.st()))
+    assert rel(G.join(gh, gl), qr.grad) < (2e-5 if pair else 6e-3)
+
+
+def test_attention_dropout_fwd_bwd_consistent(G):
+    R, L, D, H, p = 11, 18, 768, 12, 0.1
+    qkv = torch.randn(R * L, 3 * D, device=G.DEV)
+    v = torch.zeros(R, L, H, 64, device=G.DEV)
+    for j in range(L):
+        v[:, j, :, j] = 1.0  # v_j = e_j: the context then equals the (dropped) probabilities
+    probe = qkv.clone(); probe.view(R, L, 3, H, 64)[:, :, 2] = v
+    words = torch.full((R, 1), (1 << L) - 1, device=G.DEV, dtype=torch.int32)
+    km = torch.ones(R, L, device=G.DEV, dtype=torch.bool)
+    ph, pl = G.split(probe, True)
+    ch, cl = G.empty_pair((R * L, D), True)
+    lib, Lb = G.lib(), G.L
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(ph, pl)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ch, cl)), 99, 7, p, G.st()))
+    a = G.join(ch, cl).view(R, L, H, 64)[..., :L].permute(0, 2, 1, 3)  # [R, H, i, j]
+    mask = (a != 0).double()
+    assert abs(mask.mean().item() - (1 - p)) < 0.02
+    # same seed / site on the real v: forward and backward must use exactly that mask
+    qh, ql = G.split(qkv, True)
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qh, ql)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ch, cl)), 99, 7, p, G.st()))
+    qr = G.join(qh, ql).double().requires_grad_(True)
+    ref = _attn_ref(qr, km, R, L, D, H, mask / (1 - p))
+    assert rel(G.join(ch, cl), ref) < 1e-5
+    dctx = torch.randn(R * L, D, device=G.DEV)
+    dh, dl = G.split(dctx, True)
+    ref.backward(G.join(dh, dl).double())
+    gh, gl = G.empty_pair((R * L, 3 * D), True)
+    Lb.check(lib.clipdlm_attn_bwd(C.byref(G.bfp(qh, ql)), words.data_ptr(), C.byref(G.bfp(dh, dl)), R, L, D, H, C.byref(G.bfp(gh, gl)), 99, 7, p,
+                                  G.st()))
+    assert rel(G.join(gh, gl), qr.grad) < 3e-5
+
+
+# ------------------------------------------------------------------------------------------------------------ embed / loss / misc
+@pytest.mark.parametrize("fusion,guided", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_embed_fwd_bwd(G, fusion, guided, mode):
+    B, S, Ltxt, D, V = 5, 3, 16, 768, 1000
+    Lf = Ltxt + 2 if fusion == 0 else Ltxt
+    R = S * B
+    E = torch.randn(V, D, device=G.DEV) * 0.02
+    ids = torch.randint(0, V, (B, Ltxt), device=G.DEV, dtype=torch.int32)
+    noise = torch.randn(B, Ltxt, D, device=G.DEV)
+    ca = torch.rand(S, device=G.DEV); cb = torch.rand(S, device=G.DEV)
+    img = torch.randn(B, D, device=G.DEV); txt = torch.randn(B, D, device=G.DEV)
+    seg = torch.randn(2, D, device=G.DEV); pos = torch.randn(512, D, device=G.DEV) * 0.1
+    w = torch.randn(D, device=G.DEV) * 0.1 + 1; b = torch.randn(D, device=G.DEV) * 0.1
+    x_expl = (ca[:, None, None, None] * E[ids.long()][None] + cb[:, None, None, None] * noise[None]).reshape(R, Ltxt, D)
+    if fusion == 0:
+        z_ref = torch.cat([x_expl, img.repeat(S, 1)[:, None], txt.repeat(S, 1)[:, None]], 1) + seg[[0] * Ltxt + [1, 1]] + pos[:Lf]
+    else:
+        z_ref = x_expl + img.repeat(S, 1)[:, None] + (txt.repeat(S, 1)[:, None] if guided else 0) + pos[:Lf]
+    e = G.L.Embed()
+    e.R, e.B, e.Ltxt, e.L, e.D, e.fusion, e.mode, e.guided = R, B, Ltxt, Lf, D, fusion, mode, guided
+    xin = x_expl.contiguous()
+    if mode == 0:
+        e.x_in = xin.data_ptr()
+    else:
+        e.emb_table, e.ids, e.noise, e.coef_a, e.coef_b = E.data_ptr(), ids.data_ptr(), noise.data_ptr(), ca.data_ptr(), cb.data_ptr()
+    e.img_proj, e.txt_proj, e.seg, e.pos = img.data_ptr(), txt.data_ptr(), seg.data_ptr(), pos.data_ptr()
+    e.ln_w, e.ln_b, e.ln_eps = w.data_ptr(), b.data_ptr(), 1e-12
+    zh, zl = G.empty_pair((R * Lf, D), True); hh, hl = G.empty_pair((R * Lf, D), True)
+    e.z, e.h = G.bfp(zh, zl), G.bfp(hh, hl)
+    G.L.check(G.lib().clipdlm_embed_fwd(C.byref(e), G.st()))
+    assert rel(G.join(zh, zl), z_ref.reshape(R * Lf, D)) < 1e-5
+    assert rel(G.join(hh, hl), F.layer_norm(z_ref, (D,), w, b, 1e-12).reshape(R * Lf, D)) < 1e-5
+    # backward of the fusion
+    dz = torch.randn(R * Lf, D, device=G.DEV)
+    dh, dl = G.split(dz, True)
+    dzr = G.join(dh, dl).view(S, B, Lf, D).double()
+    d_pos = torch.zeros(512, D, device=G.DEV); d_seg = torch.zeros(2, D, device=G.DEV)
+    d_img = torch.zeros(B, D, device=G.DEV); d_txt = torch.zeros(B, D, device=G.DEV)
+    G.L.check(G.lib().clipdlm_embed_bwd(C.byref(G.bfp(dh, dl)), R, B, Ltxt, Lf, D, fusion, guided, d_pos.data_ptr(), d_seg.data_ptr(),
+                                        d_img.data_ptr(), d_txt.data_ptr(), G.st()))
+    assert rel(d_pos[:Lf], dzr.sum((0, 1))) < 1e-5 and float(d_pos[Lf:].abs().max()) == 0
+    if fusion == 0:
+        assert rel(d_seg[0], dzr[:, :, :Ltxt].sum((0, 1, 2))) < 1e-5 and rel(d_seg[1], dzr[:, :, Ltxt:].sum((0, 1, 2))) < 1e-5
+        assert rel(d_img, dzr[:, :, Ltxt].sum(0)) < 1e-5 and rel(d_txt, dzr[:, :, Ltxt + 1].sum(0)) < 1e-5
+    else:
+        assert rel(d_img, dzr.sum((0, 2))) < 1e-5
+        if guided:
+            assert rel(d_txt, dzr.sum((0, 2))) < 1e-5
+        else:
+            assert float(d_txt.abs().max()) == 0
+
+
+@pytest.mark.parametrize("kind,name", [(0, "series_sum_sample_mean"), (1, "series_sum"), (2, "mse_series_mean"), (3, "mse_series_sum")])
+def test_embed_loss(G, kind, name):
+    B, S, Ltxt, Lf, D, V = 4, 3, 16, 18, 768, 500
+    R = S * B
+    hp = O.default_hparams(); hp["BATCH_SIZE"] = B
+    E = torch.randn(V, D, device=G.DEV) * 0.5
+    ids = torch.randint(0, V, (B, Ltxt), device=G.DEV, dtype=torch.int32)
+    xo = torch.randn(R * Lf, D, device=G.DEV)
+    xh, xl = G.split(xo, True)
+    xr = G.join(xh, xl).view(R, Lf, D).clone().requires_grad_(True)
+    ref = O.LOSS_FUNCS[name](xr[:, :Ltxt], E[ids.long()].repeat(S, 1, 1), hp)
+    ref.backward()
+    acc = torch.zeros(1, device=G.DEV, dtype=torch.float64)
+    gh, gl = G.empty_pair((R * Lf, D), True)
+    gh.fill_(7.0)
+    G.L.check(G.lib().clipdlm_embed_loss(C.byref(G.bfp(xh, xl)), E.data_ptr(), ids.data_ptr(), None, 0, R, B, Ltxt, Lf, D, kind, R, B, 1.0,
+                                         acc.data_ptr(), C.byref(G.bfp(gh, gl)), G.st()))
+    assert abs(acc.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel(G.join(gh, gl).view(R, Lf, D), xr.grad) < 1e-5
+    # explicit target tensor (x_{t-1}-prediction objective)
+    tgt = torch.randn(R, Ltxt, D, device=G.DEV)
+    xr2 = G.join(xh, xl).view(R, Lf, D).clone().requires_grad_(True)
+    ref2 = O.LOSS_FUNCS[name](xr2[:, :Ltxt], tgt, hp)
+    acc.zero_()
+    G.L.check(G.lib().clipdlm_embed_loss(C.byref(G.bfp(xh, xl)), None, None, tgt.data_ptr(), R, R, B, Ltxt, Lf, D, kind, R, B, 1.0,
+                                         acc.data_ptr(), None, G.st()))
+    assert abs(acc.item() - ref2.item()) < 1e-5 * abs(ref2.item())
+
+
+def test_colsum_small_linear_qsample_convert(G):
+    lib, L = G.lib(), G.L
+    x = torch.randn(5000, 3072, device=G.DEV)
+    xh, xl = G.split(x, True)
+    out = torch.full((3072,), 1.0, device=G.DEV)
+    L.check(lib.clipdlm_colsum(C.byref(G.bfp(xh, xl)), 5000, 3072, out.data_ptr(), G.st()))
+    assert rel(out - 1.0, G.join(xh, xl).double().sum(0)) < 1e-5
+    B, K, N = 13, 512, 768
+    xi = torch.randn(B, K, device=G.DEV); w = torch.randn(N, K, device=G.DEV) * 0.05; b = torch.randn(N, device=G.DEV)
+    y = torch.zeros(B, N, device=G.DEV)
+    L.check(lib.clipdlm_small_linear_fwd(xi.data_ptr(), w.data_ptr(), b.data_ptr(), B, K, N, y.data_ptr(), G.st()))
+    assert rel(y, F.linear(xi, w, b)) < 1e-5
+    dy = torch.randn(B, N, device=G.DEV); dw = torch.zeros(N, K, device=G.DEV); db = torch.zeros(N, device=G.DEV)
+    L.check(lib.clipdlm_small_linear_bwd(xi.data_ptr(), dy.data_ptr(), B, K, N, dw.data_ptr(), db.data_ptr(), G.st()))
+    assert rel(dw, dy.t() @ xi) < 1e-5 and rel(db, dy.sum(0)) < 1e-5
+    x0 = torch.randn(4, 16, 768, device=G.DEV); nz = torch.randn(4, 16, 768, device=G.DEV)
+    hp = O.default_hparams()
+    t = torch.tensor([0, 1, 500, 999, 7], device=G.DEV)
+    got = clipdlm_mod().diffuse_t(x0, t, hp, nz)
+    ref = O.diffuse_t(x0.cpu(), t.cpu().reshape(5, 1, 1), O.alpha_cumprod(hp), nz.cpu())
+    assert rel(got, ref) < 1e-6 and torch.equal(got[:4].cpu(), x0.cpu())
+    f = torch.randn(1000, 768, device=G.DEV)
+    hi = torch.zeros(1000, 768, device=G.DEV, dtype=torch.bfloat16); lo = torch.zeros_like(hi); back = torch.zeros_like(f)
+    L.check(lib.clipdlm_to_bf16(f.data_ptr(), hi.data_ptr(), lo.data_ptr(), f.numel(), G.st()))
+    L.check(lib.clipdlm_to_f32(hi.data_ptr(), lo.data_ptr(), back.data_ptr(), f.numel(), G.st()))
+    assert torch.equal(hi, f.bfloat16()) and rel(back, f) < 1e-5
+    g = torch.zeros(10 * 16, 768, device=G.DEV)
+    src_h, src_l = G.split(torch.randn(10 * 18, 768, device=G.DEV), True)
+    L.check(lib.clipdlm_gather_rows_f32(C.byref(G.bfp(src_h, src_l)), 160, 16, 18, 768, g.data_ptr(), G.st()))
+    assert torch.equal(g.view(10, 16, 768), G.join(src_h, src_l).view(10, 18, 768)[:, :16])
+
+
+def clipdlm_mod():
+    import clipdlm
+    return clipdlm
+
+
+def test_adamw_matches_torch(G):
+    n = 4096 * 3 + 8
+    p0 = torch.randn(n, device=G.DEV)
+    p = p0.clone(); m = torch.zeros(n, device=G.DEV); v = torch.zeros(n, device=G.DEV)
+    hi = torch.zeros(n, device=G.DEV, dtype=torch.bfloat16); lo = torch.zeros_like(hi)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-3)
+    for step in range(1, 4):
+        g = torch.randn(n, device=G.DEV) * (10.0 ** (step - 2))
+        g[:100] = 0
+        ref_p.grad = g.clone() / 2  # grad_scale = 0.5 below
+        opt.step()
+        gg = g.clone()
+        G.L.check(G.lib().clipdlm_adamw(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, 1e-3, 0.9,
+                                        0.999, 1e-8, 0.01, step, 0.5, 1, G.st()))
+        assert float(gg.abs().max()) == 0.0  # zero_grad fused
+        assert rel(p, ref_p.detach()) < 2e-6
+        assert rel(hi.float() + lo.float(), p) < 1e-5 and torch.equal(hi, p.bfloat16())
