@@ -94,6 +94,13 @@ class LossCfg(C.Structure):
 
 EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD = 0, 1, 2, 3
 
+PROF_CATEGORIES = ("gemm_fwd", "gemm_dgrad", "gemm_wgrad", "gemm_lse", "gemm_smgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "embed",
+                   "loss", "colsum", "other")
+
+
+class Prof(C.Structure):
+    _fields_ = [("ms", f64), ("flops", f64), ("bytes", f64), ("launches", i64)]
+
 # parameter slots (enum in clipdlm.h)
 (P_POS, P_EMB_LN_W, P_EMB_LN_B, P_VT_W, P_VT_B, P_VLN_W, P_VLN_B, P_IMG_W, P_IMG_B, P_TXT_W, P_TXT_B, P_SEG,
  P_LAYER0) = range(13)
@@ -135,6 +142,8 @@ _SIGS = {
     "clipdlm_engine_lm_head": (C.c_int, [c_p, c_p, i64, c_p, c_p]),
     "clipdlm_engine_loss_backward": (C.c_int, [c_p, C.POINTER(LossCfg), c_p, c_p]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
+    "clipdlm_engine_profile": (C.c_int, [c_p, i32]),
+    "clipdlm_engine_profile_read": (C.c_int, [c_p, c_p, i32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())

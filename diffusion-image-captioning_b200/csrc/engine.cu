@@ -6,6 +6,7 @@
 #include "../../include/clipdlm.h"
 #include <string.h>
 #include <new>
+#include <vector>
 
 namespace clipdlm {
 
@@ -86,6 +87,20 @@ typedef clipdlm_bf_t Act;
 
 struct LayerBufs { Act qkv, ctx, z1, h1, u, g, z2; };
 
+// Optional per-launch timing: every launch is bracketed by two CUDA events on the caller's stream (bench.py's roofline leg).
+struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
 }  // namespace clipdlm
 
 using namespace clipdlm;
@@ -108,6 +123,7 @@ struct clipdlm_engine {
   float *part_max, *part_sum, *tgt_logit, *lse;
   int32_t* part_arg;
   long long launches;
+  Profiler* prof;
   // last forward
   clipdlm_pass_t last;
   int have_fwd;
@@ -212,7 +228,50 @@ static clipdlm_gemm_t gemm_desc(const Act& a, long long lda, int a_major, const 
   g.epilogue = CLIPDLM_EPI_STORE;
   return g;
 }
-#define RUN(expr) do { int _rc = (expr); if (_rc) return _rc; e->launches++; } while (0)
+struct ProfScope {
+  clipdlm_engine* e; cudaStream_t st; int idx;
+  ProfScope(clipdlm_engine* e_, cudaStream_t st_, int cat, double flops, double bytes) : e(e_), st(st_), idx(-1) {
+    if (e->prof && e->prof->on) {
+      ProfRec r; r.a = e->prof->get(); r.b = e->prof->get(); r.cat = cat; r.flops = flops; r.bytes = bytes;
+      cudaEventRecord(r.a, st);
+      e->prof->recs.push_back(r);
+      idx = (int)e->prof->recs.size() - 1;
+    }
+  }
+  void end() { if (idx >= 0) cudaEventRecord(e->prof->recs[idx].b, st); }
+};
+#define RUNP(CAT, FLOPS, BYTES, expr)                                     \
+  do {                                                                    \
+    ProfScope _ps(e, st, (CAT), (double)(FLOPS), (double)(BYTES));        \
+    int _rc = (expr);                                                     \
+    _ps.end();                                                            \
+    if (_rc) return _rc;                                                  \
+    e->launches++;                                                        \
+  } while (0)
+#define RUN(expr) RUNP(CLIPDLM_PROF_OTHER, 0, 0, expr)
+// a GEMM launch: category from the operand majors / epilogue, algorithmic flops 2MNK, bytes = operands + outputs once
+static int gemm_cat(const clipdlm_gemm_t& g) {
+  switch (g.epilogue) {
+    case CLIPDLM_EPI_WGRAD: return CLIPDLM_PROF_GEMM_WGRAD;
+    case CLIPDLM_EPI_LSE: return CLIPDLM_PROF_GEMM_LSE;
+    case CLIPDLM_EPI_SMGRAD: return CLIPDLM_PROF_GEMM_SMGRAD;
+    default: return g.b_major ? CLIPDLM_PROF_GEMM_DGRAD : CLIPDLM_PROF_GEMM_FWD;
+  }
+}
+static double gemm_bytes(const clipdlm_gemm_t& g, int es) {
+  double b = ((double)g.M * g.K + (double)g.N * g.K) * es;
+  if (g.epilogue == CLIPDLM_EPI_WGRAD) b += (double)g.M * g.N * 8;  // fp32 accumulate: read + write
+  else if (g.epilogue == CLIPDLM_EPI_SMGRAD) b += (double)g.M * g.N * es;
+  else if (g.epilogue == CLIPDLM_EPI_STORE) {
+    if (g.out_hi) b += (double)g.M * g.N * es;
+    if (g.out2_hi) b += (double)g.M * g.N * es;
+    if (g.out_f32) b += (double)g.M * g.N * 4;
+    if (g.res_hi) b += (double)g.M * g.N * es;
+    if (g.u_hi) b += (double)g.M * g.N * es;
+  }
+  return b;
+}
+#define RUNG(gd) RUNP(gemm_cat(gd), 2.0 * (gd).M * (gd).N * (gd).K, gemm_bytes((gd), e->pair ? 4 : 2), gemm_dispatch(&(gd), st))
 
 // y[T, N] = x[T, K] W[N, K]^T + bias  (+ fused extras set by the caller on the descriptor)
 static clipdlm_gemm_t linear_fwd(const Act& x, const Act& w, const float* bias, int T, int N, int K, const Act& out) {
@@ -259,33 +318,33 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
   em.ln_w = param(e, CLIPDLM_P_EMB_LN_W); em.ln_b = param(e, CLIPDLM_P_EMB_LN_B); em.ln_eps = c.ln_eps;
   em.z = e->z0; em.h = e->h[0];
   em.drop_seed = p->drop_seed; em.drop_site = 0; em.drop_p = pdrop;
-  RUN(embed_fwd_dispatch(&em, st));
+  RUNP(CLIPDLM_PROF_EMBED, 0, (double)T * D * (e->pair ? 4.0 : 2.0) * (train ? 2 : 1) + (double)B * Ltxt * D * 8, embed_fwd_dispatch(&em, st));
 
   for (int l = 0; l < NL; ++l) {
     const LayerBufs& b = e->lay[l];
     const Act& hin = e->h[l];
     clipdlm_gemm_t g = linear_fwd(hin, shadow(e, lslot(l, CLIPDLM_PL_QKV_W)), param(e, lslot(l, CLIPDLM_PL_QKV_B)), T, 3 * D, D, b.qkv);
-    RUN(gemm_dispatch(&g, st));
-    RUN(attn_fwd_dispatch(&b.qkv, e->keymask, R, L, D, c.n_heads, &b.ctx, p->drop_seed, 1 + 2 * l, padrop, st));
+    RUNG(g);
+    RUNP(CLIPDLM_PROF_ATTN_FWD, 4.0 * R * L * L * D, (double)T * 4 * D * (e->pair ? 4.0 : 2.0), attn_fwd_dispatch(&b.qkv, e->keymask, R, L, D, c.n_heads, &b.ctx, p->drop_seed, 1 + 2 * l, padrop, st));
     g = linear_fwd(b.ctx, shadow(e, lslot(l, CLIPDLM_PL_O_W)), param(e, lslot(l, CLIPDLM_PL_O_B)), T, D, D, b.z1);
     g.res_hi = hin.hi; g.res_lo = hin.lo; g.ldr = D;
-    RUN(gemm_dispatch(&g, st));
-    RUN(layernorm_fwd_dispatch(&b.z1, param(e, lslot(l, CLIPDLM_PL_LN1_W)), param(e, lslot(l, CLIPDLM_PL_LN1_B)), c.ln_eps, T, D, &b.h1,
+    RUNG(g);
+    RUNP(CLIPDLM_PROF_LN_FWD, 0, (double)T * 2 * D * (e->pair ? 4.0 : 2.0), layernorm_fwd_dispatch(&b.z1, param(e, lslot(l, CLIPDLM_PL_LN1_W)), param(e, lslot(l, CLIPDLM_PL_LN1_B)), c.ln_eps, T, D, &b.h1,
                                nullptr, 0, 0, 0.f, st));
     g = linear_fwd(b.h1, shadow(e, lslot(l, CLIPDLM_PL_FF1_W)), param(e, lslot(l, CLIPDLM_PL_FF1_B)), T, F, D, b.u);
     g.out2_hi = b.g.hi; g.out2_lo = b.g.lo;
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     g = linear_fwd(b.g, shadow(e, lslot(l, CLIPDLM_PL_FF2_W)), param(e, lslot(l, CLIPDLM_PL_FF2_B)), T, D, F, b.z2);
     g.res_hi = b.h1.hi; g.res_lo = b.h1.lo; g.ldr = D;
     g.drop_seed = p->drop_seed; g.drop_site = 2 + 2 * l; g.drop_p = pdrop;
-    RUN(gemm_dispatch(&g, st));
-    RUN(layernorm_fwd_dispatch(&b.z2, param(e, lslot(l, CLIPDLM_PL_LN2_W)), param(e, lslot(l, CLIPDLM_PL_LN2_B)), c.ln_eps, T, D, &e->h[l + 1],
+    RUNG(g);
+    RUNP(CLIPDLM_PROF_LN_FWD, 0, (double)T * 2 * D * (e->pair ? 4.0 : 2.0), layernorm_fwd_dispatch(&b.z2, param(e, lslot(l, CLIPDLM_PL_LN2_W)), param(e, lslot(l, CLIPDLM_PL_LN2_B)), c.ln_eps, T, D, &e->h[l + 1],
                                nullptr, 0, 0, 0.f, st));
   }
   clipdlm_gemm_t g = linear_fwd(e->h[NL], shadow(e, CLIPDLM_P_VT_W), param(e, CLIPDLM_P_VT_B), T, D, D, e->uv);
   g.out2_hi = e->gv.hi; g.out2_lo = e->gv.lo;
-  RUN(gemm_dispatch(&g, st));
-  RUN(layernorm_fwd_dispatch(&e->gv, param(e, CLIPDLM_P_VLN_W), param(e, CLIPDLM_P_VLN_B), c.ln_eps, T, D, &e->xo, p->x_out, 0, 0, 0.f, st));
+  RUNG(g);
+  RUNP(CLIPDLM_PROF_LN_FWD, 0, (double)T * 2 * D * (e->pair ? 4.0 : 2.0), layernorm_fwd_dispatch(&e->gv, param(e, CLIPDLM_P_VLN_W), param(e, CLIPDLM_P_VLN_B), c.ln_eps, T, D, &e->xo, p->x_out, 0, 0, 0.f, st));
   e->last = *p;
   e->have_fwd = 1;
   return 0;
@@ -302,8 +361,8 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   g.epilogue = CLIPDLM_EPI_LSE;
   g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = e->part_arg; g.tgt_logit = e->tgt_logit;
   g.targets = targets; g.tgt_period = tgt_period;
-  RUN(gemm_dispatch(&g, st));
-  RUN(lse_combine_dispatch(e->part_max, e->part_sum, e->part_arg, e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
+  RUNG(g);
+  RUNP(CLIPDLM_PROF_LOSS, 0, 3.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, e->part_arg, e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
                            scale, st));
   return 0;
 }
@@ -327,7 +386,7 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
 
   // 1. embedding-space loss (+ its gradient written over every row of g0)
   if (lc->use_embed_loss || bwd)
-    RUN(embed_loss_dispatch(&e->xo, e->bufs.emb_table, p.ids, lc->target, lc->target_rows, R, B, Ltxt, L, D, lc->loss_kind, R_total, lc->batch_size,
+    RUNP(CLIPDLM_PROF_LOSS, 0, ((double)M16 + (bwd ? T : 0)) * D * (e->pair ? 4.0 : 2.0) + (double)M16 * D * 4, embed_loss_dispatch(&e->xo, e->bufs.emb_table, p.ids, lc->target, lc->target_rows, R, B, Ltxt, L, D, lc->loss_kind, R_total, lc->batch_size,
                             lc->use_embed_loss ? 1.f : 0.f, lc->use_embed_loss ? &losses[0] : nullptr, bwd ? &e->g0 : nullptr, st));
   // 2. rounding cross-entropy through the frozen lm_head
   if (lc->use_prob_loss) {
@@ -341,24 +400,24 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
       g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
       g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
       g.grad_scale = (float)(lc->rounding_weight * ce_scale);
-      RUN(gemm_dispatch(&g, st));
+      RUNG(g);
       // d x_out[:, :Ltxt] += dlogits[M16, V] E[V, D]
       g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
       g.out_hi = e->g0.hi; g.out_lo = e->g0.lo; g.ldo = D;
       g.res_hi = e->g0.hi; g.res_lo = e->g0.lo; g.ldr = D;
       g.scatter_len = Ltxt; g.scatter_stride = L;
-      RUN(gemm_dispatch(&g, st));
+      RUNG(g);
     }
   }
   if (!bwd) return 0;
 
   // 3. MLM transform head: x_out = LN_v(gelu(h W_t^T + b_t))
-  RUN(layernorm_bwd_dispatch(&e->gv, &e->g0, param(e, CLIPDLM_P_VLN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_VLN_W),
+  RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&e->gv, &e->g0, param(e, CLIPDLM_P_VLN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_VLN_W),
                              grad(e, CLIPDLM_P_VLN_B), 0, 0, 0.f, nullptr, 0, 0.f, &e->uv, grad(e, CLIPDLM_P_VT_B), st));
   clipdlm_gemm_t g = linear_wgrad(e->g1, e->h[NL], T, D, D, grad(e, CLIPDLM_P_VT_W));
-  RUN(gemm_dispatch(&g, st));
+  RUNG(g);
   g = linear_dgrad(e->g1, shadow(e, CLIPDLM_P_VT_W), T, D, D, e->g0);
-  RUN(gemm_dispatch(&g, st));
+  RUNG(g);
 
   // 4. transformer blocks, last to first.  g0 holds d(block output).
   for (int l = NL - 1; l >= 0; --l) {
@@ -366,39 +425,39 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
     const Act& hin = e->h[l];
     const bool drop = pdrop > 0.f;
     // h_out = LN2(drop(ffn) + h1)
-    RUN(layernorm_bwd_dispatch(&b.z2, &e->g0, param(e, lslot(l, CLIPDLM_PL_LN2_W)), c.ln_eps, T, D, &e->g1, grad(e, lslot(l, CLIPDLM_PL_LN2_W)),
+    RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&b.z2, &e->g0, param(e, lslot(l, CLIPDLM_PL_LN2_W)), c.ln_eps, T, D, &e->g1, grad(e, lslot(l, CLIPDLM_PL_LN2_W)),
                                grad(e, lslot(l, CLIPDLM_PL_LN2_B)), p.drop_seed, 0, 0.f, drop ? &e->g2 : nullptr, 2 + 2 * l, pdrop, nullptr,
                                grad(e, lslot(l, CLIPDLM_PL_FF2_B)), st));
     const Act& dffn = drop ? e->g2 : e->g1;  // gradient of the lin2 output
     g = linear_wgrad(dffn, b.g, T, D, F, grad(e, lslot(l, CLIPDLM_PL_FF2_W)));
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     g = linear_dgrad(dffn, shadow(e, lslot(l, CLIPDLM_PL_FF2_W)), T, D, F, e->gf);
     g.u_hi = b.u.hi; g.u_lo = b.u.lo; g.ldu = F;  // * gelu'(u)
-    RUN(gemm_dispatch(&g, st));
-    RUN(colsum_dispatch(&e->gf, T, F, grad(e, lslot(l, CLIPDLM_PL_FF1_B)), st));
+    RUNG(g);
+    RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * F * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gf, T, F, grad(e, lslot(l, CLIPDLM_PL_FF1_B)), st));
     g = linear_wgrad(e->gf, b.h1, T, F, D, grad(e, lslot(l, CLIPDLM_PL_FF1_W)));
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     g = linear_dgrad(e->gf, shadow(e, lslot(l, CLIPDLM_PL_FF1_W)), T, F, D, e->g0);
     g.res_hi = e->g1.hi; g.res_lo = e->g1.lo; g.ldr = D;  // + residual branch d(h1)
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     // h1 = LN1(attn_out + h_in)
-    RUN(layernorm_bwd_dispatch(&b.z1, &e->g0, param(e, lslot(l, CLIPDLM_PL_LN1_W)), c.ln_eps, T, D, &e->g1, grad(e, lslot(l, CLIPDLM_PL_LN1_W)),
+    RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&b.z1, &e->g0, param(e, lslot(l, CLIPDLM_PL_LN1_W)), c.ln_eps, T, D, &e->g1, grad(e, lslot(l, CLIPDLM_PL_LN1_W)),
                                grad(e, lslot(l, CLIPDLM_PL_LN1_B)), 0, 0, 0.f, nullptr, 0, 0.f, nullptr, grad(e, lslot(l, CLIPDLM_PL_O_B)), st));
     g = linear_wgrad(e->g1, b.ctx, T, D, D, grad(e, lslot(l, CLIPDLM_PL_O_W)));
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     g = linear_dgrad(e->g1, shadow(e, lslot(l, CLIPDLM_PL_O_W)), T, D, D, e->g0);
-    RUN(gemm_dispatch(&g, st));
-    RUN(attn_bwd_dispatch(&b.qkv, e->keymask, &e->g0, R, L, D, c.n_heads, &e->gq, p.drop_seed, 1 + 2 * l, padrop, st));
-    RUN(colsum_dispatch(&e->gq, T, 3 * D, grad(e, lslot(l, CLIPDLM_PL_QKV_B)), st));
+    RUNG(g);
+    RUNP(CLIPDLM_PROF_ATTN_BWD, 10.0 * R * L * L * D, (double)T * 7 * D * (e->pair ? 4.0 : 2.0), attn_bwd_dispatch(&b.qkv, e->keymask, &e->g0, R, L, D, c.n_heads, &e->gq, p.drop_seed, 1 + 2 * l, padrop, st));
+    RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gq, T, 3 * D, grad(e, lslot(l, CLIPDLM_PL_QKV_B)), st));
     g = linear_wgrad(e->gq, hin, T, 3 * D, D, grad(e, lslot(l, CLIPDLM_PL_QKV_W)));
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
     g = linear_dgrad(e->gq, shadow(e, lslot(l, CLIPDLM_PL_QKV_W)), T, 3 * D, D, e->g0);
     g.res_hi = e->g1.hi; g.res_lo = e->g1.lo; g.ldr = D;
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
   }
 
   // 5. embeddings: h0 = drop(LN_e(z0)); z0 = fuse(x, CLIP projections) + segment + position
-  RUN(layernorm_bwd_dispatch(&e->z0, &e->g0, param(e, CLIPDLM_P_EMB_LN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_EMB_LN_W),
+  RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&e->z0, &e->g0, param(e, CLIPDLM_P_EMB_LN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_EMB_LN_W),
                              grad(e, CLIPDLM_P_EMB_LN_B), p.drop_seed, 0, pdrop, nullptr, 0, 0.f, nullptr, nullptr, st));
   CLIPDLM_CUDA_OK(cudaMemsetAsync(e->d_img_proj, 0, (size_t)B * D * 4, st));
   CLIPDLM_CUDA_OK(cudaMemsetAsync(e->d_txt_proj, 0, (size_t)B * D * 4, st));
@@ -425,7 +484,7 @@ static int lm_head_impl(clipdlm_engine* e, float* logits, int64_t ld_logits, int
     clipdlm_gemm_t g = gemm_desc(e->xo, c.dim, 0, emb, c.dim, 0, M, N32, c.dim);  // emb shadow is zero-padded to a 256-row multiple
     g.gather_len = e->Ltxt; g.gather_stride = e->L;
     g.out_f32 = logits; g.ldo = ld_logits;
-    RUN(gemm_dispatch(&g, st));
+    RUNG(g);
   }
   return 0;
 }
@@ -472,11 +531,17 @@ clipdlm_engine_t* clipdlm_engine_create(const clipdlm_config_t* cfg, const clipd
     if (need > bufs->workspace_bytes) { set_last_error("workspace too small: need %zu bytes, got %zu", need, bufs->workspace_bytes); ok = false; }
   }
   if (!ok) { delete[] e->h; delete[] e->lay; delete e; return nullptr; }
+  e->prof = new (std::nothrow) Profiler;
   return e;
 }
 
 void clipdlm_engine_destroy(clipdlm_engine_t* e) {
   if (!e) return;
+  if (e->prof) {
+    for (auto& r : e->prof->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : e->prof->pool) cudaEventDestroy(ev);
+    delete e->prof;
+  }
   delete[] e->h;
   delete[] e->lay;
   delete e;
@@ -495,5 +560,26 @@ int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* 
   return loss_backward_impl(e, lc, losses, (cudaStream_t)stream);
 }
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e) { return e ? e->launches : -1; }
+
+int clipdlm_engine_profile(clipdlm_engine_t* e, int32_t enable) {
+  CLIPDLM_CHECK(e != nullptr && e->prof != nullptr, "null engine");
+  e->prof->on = enable != 0;
+  return 0;
+}
+int clipdlm_engine_profile_read(clipdlm_engine_t* e, clipdlm_prof_t* out, int32_t reset) {
+  CLIPDLM_CHECK(e != nullptr && e->prof != nullptr && out != nullptr, "null engine / output");
+  for (int c = 0; c < CLIPDLM_PROF_NCAT; ++c) { out[c].ms = 0; out[c].flops = 0; out[c].bytes = 0; out[c].launches = 0; }
+  for (auto& r : e->prof->recs) {
+    CLIPDLM_CUDA_OK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CLIPDLM_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    out[r.cat].ms += ms; out[r.cat].flops += r.flops; out[r.cat].bytes += r.bytes; out[r.cat].launches += 1;
+  }
+  if (reset) {
+    for (auto& r : e->prof->recs) { e->prof->pool.push_back(r.a); e->prof->pool.push_back(r.b); }
+    e->prof->recs.clear();
+  }
+  return 0;
+}
 
 }  // extern "C"

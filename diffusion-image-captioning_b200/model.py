@@ -282,12 +282,30 @@ class DistilBertModel:
         if not h:
             raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
         self._engines[key] = (h, rows, batch, ws)
+        if getattr(self, "_profiling", False):
+            L.check(lib.clipdlm_engine_profile(h, 1))
         return h
 
     def launch_count(self) -> int:
         """Kernel launches issued by this model's engines so far (bench `gpu_launches`)."""
         lib = L.load()
         return self._launches_retired + sum(int(lib.clipdlm_engine_launch_count(e[0])) for e in self._engines.values())
+
+    def profile(self, enable: bool = True):
+        """Bracket every engine launch with CUDA events (per-kernel-category device times for the roofline report)."""
+        self._profiling = bool(enable)
+        for e in self._engines.values():
+            L.check(L.load().clipdlm_engine_profile(e[0], 1 if enable else 0))
+
+    def profile_read(self, reset: bool = True) -> Dict[str, dict]:
+        lib = L.load()
+        tot = {k: dict(ms=0.0, flops=0.0, bytes=0.0, launches=0) for k in L.PROF_CATEGORIES}
+        for e in self._engines.values():
+            arr = (L.Prof * len(L.PROF_CATEGORIES))()
+            L.check(lib.clipdlm_engine_profile_read(e[0], C.cast(arr, C.c_void_p), 1 if reset else 0))
+            for k, r in zip(L.PROF_CATEGORIES, arr):
+                tot[k]["ms"] += r.ms; tot[k]["flops"] += r.flops; tot[k]["bytes"] += r.bytes; tot[k]["launches"] += int(r.launches)
+        return tot
 
     def __del__(self):
         try:

@@ -252,6 +252,18 @@ int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* 
 /* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e);
 
+/* Per-launch device timing for the roofline report: when enabled every engine launch is bracketed by two CUDA events on
+ * the caller's stream; profile_read() waits for them and returns per-category totals (ms on the device, ALGORITHMIC flops
+ * = 2MNK for GEMMs, algorithmic bytes for the HBM-bound kernels, launch count); reset = 1 recycles the events. */
+enum {
+  CLIPDLM_PROF_GEMM_FWD = 0, CLIPDLM_PROF_GEMM_DGRAD, CLIPDLM_PROF_GEMM_WGRAD, CLIPDLM_PROF_GEMM_LSE, CLIPDLM_PROF_GEMM_SMGRAD,
+  CLIPDLM_PROF_ATTN_FWD, CLIPDLM_PROF_ATTN_BWD, CLIPDLM_PROF_LN_FWD, CLIPDLM_PROF_LN_BWD, CLIPDLM_PROF_EMBED, CLIPDLM_PROF_LOSS,
+  CLIPDLM_PROF_COLSUM, CLIPDLM_PROF_OTHER, CLIPDLM_PROF_NCAT
+};
+typedef struct clipdlm_prof { double ms; double flops; double bytes; int64_t launches; } clipdlm_prof_t;
+int clipdlm_engine_profile(clipdlm_engine_t* e, int32_t enable);
+int clipdlm_engine_profile_read(clipdlm_engine_t* e, clipdlm_prof_t* out /* [CLIPDLM_PROF_NCAT] */, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,7 +89,7 @@ def test_golden_train_step(pkg, name):
     for n, ref_norm, gn in zip(names, g["after_norms"], g["grad_norms"]):
         if 0.0 < gn < 1e-3 * gscale:
             continue  # analytically-zero gradients (k_lin.bias): Adam's first step is sign(noise) in the reference too
-        assert abs(float(after[n].double().norm()) - ref_norm) <= 1e-4 * max(ref_norm, 1e-3), n
+        assert abs(float(after[n].double().norm()) - ref_norm) <= 5e-4 * max(ref_norm, 1e-3), n
     for n in ("model.vocab_layer_norm.weight", "model.distilbert.transformer.layer.0.ffn.lin1.bias", "image_linear.bias"):
         ref = torch.from_numpy(g["after::" + n])
         # Adam's first step moves every element by ~lr * sign(g): compare where the reference gradient is not noise-level
