@@ -74,7 +74,7 @@ class Buffers(C.Structure):
 
 class Pass(C.Structure):
     _fields_ = [
-        ("R", i32), ("B", i32), ("mode", i32), ("guided", i32), ("train", i32),
+        ("R", i32), ("B", i32), ("mode", i32), ("guided", i32), ("train", i32), ("reuse_proj", i32),
         ("x_in", c_p), ("x_in_stride", i64),
         ("ids", c_p), ("noise", c_p), ("coef_a", c_p), ("coef_b", c_p),
         ("image_clip", c_p), ("text_clip", c_p), ("attn_mask", c_p),
@@ -121,6 +121,7 @@ _SIGS = {
                                         u64, u32, f32, C.POINTER(Bf), u32, f32, C.POINTER(Bf), c_p, c_p]),
     "clipdlm_attn_fwd": (C.c_int, [C.POINTER(Bf), c_p, i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
     "clipdlm_attn_bwd": (C.c_int, [C.POINTER(Bf), c_p, C.POINTER(Bf), i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
+    "clipdlm_attn_force_simt": (None, [i32]),
     "clipdlm_colsum": (C.c_int, [C.POINTER(Bf), i64, i32, c_p, c_p]),
     "clipdlm_embed_loss": (C.c_int, [C.POINTER(Bf), c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p,
                                      C.POINTER(Bf), c_p]),

@@ -42,6 +42,7 @@ int to_f32_dispatch(const void* hi, const void* lo, float* y, long long n, cudaS
 int gather_rows_f32_dispatch(const clipdlm_bf_t* x, long long rows_out, int len, int stride, int D, float* y, cudaStream_t st);
 int q_sample_dispatch(const float* x0, const float* noise, const float* ca, const float* cb, long long n, int S, float* out, cudaStream_t st);
 int keymask_dispatch(const int* attn_mask, int R, int B, int Ltxt, int L, int fusion, int guided, uint32_t* km, cudaStream_t st);
+void attn_force_simt(int on);
 int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, int L, int D, int H, const clipdlm_bf_t* ctx,
                       unsigned long long seed, uint32_t site, float p, cudaStream_t st);
 int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int R, int L, int D, int H,
@@ -98,6 +99,7 @@ int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cli
                      const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream) {
   return attn_bwd_dispatch(qkv, keymask, dctx, R, L, D, H, dqkv, drop_seed, drop_site, drop_p, ST);
 }
+void clipdlm_attn_force_simt(int32_t on) { attn_force_simt(on); }
 int clipdlm_colsum(const clipdlm_bf_t* x, int64_t rows, int32_t N, float* out, clipdlm_stream stream) { return colsum_dispatch(x, rows, N, out, ST); }
 int clipdlm_embed_loss(const clipdlm_bf_t* x_out, const float* emb_table, const int32_t* ids, const float* target, int32_t target_rows,
                        int32_t R, int32_t B, int32_t Ltxt, int32_t L,

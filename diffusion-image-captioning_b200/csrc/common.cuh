@@ -141,12 +141,32 @@ __device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, unsigned 
   return m;
 }
 
-// exact-erf GELU (HF activations.py GELUActivation -> nn.functional.gelu) and its derivative
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (HF activations.py GELUActivation -> nn.functional.gelu) and its derivative.
+// erf is evaluated branch-free with Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 round-off level), one MUFU.RCP
+// and one MUFU.EX2 per element: libdevice erff() is ~3x the instructions and branches per element, which made the GEMM
+// epilogues (4 warps, one per scheduler) the bottleneck of the K = 768 GEMMs.  phi(x) = 0.5 * erfc(-x / sqrt(2)) is formed
+// without cancellation on either tail; exp(-x^2 / 2) is shared between cdf and pdf in the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  e = __expf(-ax * ax);                 // = exp(-x^2 / 2)
+  const float half_erfc = 0.5f * poly * e;  // 0.5 * erfc(|x| / sqrt 2)
+  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -304,9 +304,13 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
   const bool train = p->train != 0;
   const float pdrop = train ? c.dropout : 0.f, padrop = train ? c.attn_dropout : 0.f;
 
-  RUN(small_linear_fwd_dispatch(p->image_clip, param(e, CLIPDLM_P_IMG_W), param(e, CLIPDLM_P_IMG_B), B, c.clip_dim, D, e->img_proj, st));
-  RUN(small_linear_fwd_dispatch(p->text_clip, param(e, CLIPDLM_P_TXT_W), param(e, CLIPDLM_P_TXT_B), B, c.clip_dim, D, e->txt_proj, st));
-  RUN(keymask_dispatch(p->attn_mask, R, B, Ltxt, L, c.fusion, p->guided, e->keymask, st));
+  if (p->reuse_proj) {
+    CLIPDLM_CHECK(e->have_fwd && e->last.R == R && e->last.B == B && e->last.guided == p->guided, "reuse_proj: previous pass had a different shape");
+  } else {
+    RUN(small_linear_fwd_dispatch(p->image_clip, param(e, CLIPDLM_P_IMG_W), param(e, CLIPDLM_P_IMG_B), B, c.clip_dim, D, e->img_proj, st));
+    RUN(small_linear_fwd_dispatch(p->text_clip, param(e, CLIPDLM_P_TXT_W), param(e, CLIPDLM_P_TXT_B), B, c.clip_dim, D, e->txt_proj, st));
+    RUN(keymask_dispatch(p->attn_mask, R, B, Ltxt, L, c.fusion, p->guided, e->keymask, st));
+  }
 
   clipdlm_embed_t em;
   memset(&em, 0, sizeof(em));

@@ -88,6 +88,33 @@ __device__ __forceinline__ void tile_load_bf16(const GemmArgs& g, const __nv_bfl
   }
   __syncwarp();
 }
+// Split version of tile_load_bf16 for latency hiding: issue the 4 coalesced 16-byte loads of a 32x32 bf16 tile early ...
+__device__ __forceinline__ void tile_issue(const GemmArgs& g, const __nv_bfloat16* base, long long ld, int row_base, int n0, uint4 (&raw)[4]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int m = row_base + (lane >> 2) + 8 * j;
+    raw[j] = make_uint4(0, 0, 0, 0);
+    if (m < g.M) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8));
+  }
+}
+// ... and consume them later: transpose through the warp's staging tile into "thread owns a row", then v = v + x or v * gelu'(x).
+template <bool DGELU>
+__device__ __forceinline__ void tile_consume(const uint4 (&raw)[4], uint8_t* stg, float (&v)[32]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * j) * STG_PITCH + (lane & 3) * 16) = raw[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + i * 16);
+    const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
+    const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[i * 8 + e] = DGELU ? v[i * 8 + e] * dgelu_f(f[e]) : v[i * 8 + e] + f[e];
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void tile_load_pair(const GemmArgs& g, const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long ld,
                                                int row_base, int n0, uint8_t* stg, float (&r)[32]) {
   tile_load_bf16(g, hi, ld, row_base, n0, stg, r, false);
@@ -274,6 +301,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
 
+      // plain-bf16 residual / gelu'(u) operand: prefetch its first 32-column chunk while the MMAs of this tile are still running
+      const bool aux_is_u = g.u_hi != nullptr;
+      const __nv_bfloat16* aux = aux_is_u ? g.u_hi : g.res_hi;
+      const long long ld_aux = aux_is_u ? g.ldu : g.ldr;
+      const bool fast_aux = EPI == CLIPDLM_EPI_STORE && aux != nullptr && g.u_lo == nullptr && g.res_lo == nullptr &&
+                            !(g.u_hi != nullptr && g.res_hi != nullptr);
+      uint4 aux_nxt[4];
+      if (fast_aux) tile_issue(g, aux, ld_aux, row_base, n_blk * BN, aux_nxt);
+
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -330,6 +366,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             }
             tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
           } else {  // STORE
+            uint4 aux_cur[4];
+            if (fast_aux) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
+              if (c + 1 < BN / 32 && n0 + 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n0 + 32, aux_nxt);
+            }
             if (g.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += sbias[c * 32 + j];
@@ -343,17 +385,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = ((keep >> i) & 1u) ? v[j8 * 8 + i] * g.drop.scale : 0.f;
               }
             }
-            if (g.u_hi != nullptr) {
-              float u[32];
-              tile_load_pair(g, g.u_hi, g.u_lo, g.ldu, row_base, n0, stg, u);
+            if (fast_aux) {
+              if (aux_is_u) tile_consume<true>(aux_cur, stg, v);
+              else tile_consume<false>(aux_cur, stg, v);
+            } else {
+              if (g.u_hi != nullptr) {
+                float u[32];
+                tile_load_pair(g, g.u_hi, g.u_lo, g.ldu, row_base, n0, stg, u);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= dgelu_f(u[j]);
-            }
-            if (g.res_hi != nullptr) {
-              float r[32];
-              tile_load_pair(g, g.res_hi, g.res_lo, g.ldr, row_base, n0, stg, r);
+                for (int j = 0; j < 32; ++j) v[j] *= dgelu_f(u[j]);
+              }
+              if (g.res_hi != nullptr) {
+                float r[32];
+                tile_load_pair(g, g.res_hi, g.res_lo, g.ldr, row_base, n0, stg, r);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += r[j];
+                for (int j = 0; j < 32; ++j) v[j] += r[j];
+              }
             }
             if (g.out_hi != nullptr) tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
             if (g.out_f32 != nullptr) tile_store_f32<false>(g, g.out_f32, g.ldo, row_base, n0, stg, v);

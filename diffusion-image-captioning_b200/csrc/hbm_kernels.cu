@@ -254,8 +254,8 @@ struct LnBwdArgs {
 };
 
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdArgs a) {
-  extern __shared__ float red[];  // [8 warps][D] reused for dw, db, dbias
+__global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a) {
+  extern __shared__ float red[];  // [4 warps][D] reused for dw, db, dbias
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   float pdw[NV][8], pdb[NV][8], pbias[NV][8];
@@ -263,10 +263,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdArgs a) {
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { pdw[v][i] = 0.f; pdb[v][i] = 0.f; pbias[v][i] = 0.f; }
-  float wv[NV][8];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) load8_f32(a.w + (v * 32 + lane) * 8, wv[v]);
-
   for (long long row = (long long)blockIdx.x * nwarps + warp; row < a.rows; row += (long long)gridDim.x * nwarps) {
     float x[NV][8], g[NV][8];
 #pragma unroll
@@ -280,16 +276,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdArgs a) {
     row_stats<NV>(x, a.D, a.eps, mean, rstd);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
+    for (int v = 0; v < NV; ++v) {
+      float wv[8];  // re-read per row (L1-resident): keeping w in registers costs occupancy on this HBM-bound kernel
+      load8_f32(a.w + (v * 32 + lane) * 8, wv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float xh = (x[v][i] - mean) * rstd;
-        const float gw = g[v][i] * wv[v][i];
+        const float gw = g[v][i] * wv[i];
         pdw[v][i] += g[v][i] * xh;
         pdb[v][i] += g[v][i];
         s1 += gw; s2 += gw * xh;
         x[v][i] = xh; g[v][i] = gw;
       }
+    }
     s1 = warp_sum(s1) / (float)a.D;
     s2 = warp_sum(s2) / (float)a.D;
 #pragma unroll
@@ -667,10 +666,10 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
   a.drop_in = make_drop(seed, site_in, p_in);
   a.gelu_u = cbf(gelu_u);
   a.dbias = dbias;
-  long long want = (rows + 7) / 8;
-  int grid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
-  const size_t smem = (size_t)8 * D * sizeof(float);
-  DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 256, smem, st>>>(a));
+  long long want = (rows + 3) / 4;
+  int grid = (int)(want < 3LL * num_sms() ? want : 3LL * num_sms());  // 3 resident CTAs of 4 warps per SM (register-limited)
+  const size_t smem = (size_t)4 * D * sizeof(float);
+  DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 128, smem, st>>>(a));
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -282,9 +282,9 @@ def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, r
     eng = model._engine(B, B, False)
     model._last_eng = eng
     outs = []
-    for _ in range(n_steps):
+    for i in range(n_steps):
         model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=cur,
-                           x_in_stride=Lfull * D, x_out=nxt)
+                           x_in_stride=Lfull * D, x_out=nxt, reuse_proj=i > 0)  # the CLIP projections do not change across steps
         cur, nxt = nxt, cur
         if return_all:
             outs.append(model.argmax_last(B))

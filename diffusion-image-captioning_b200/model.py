@@ -316,8 +316,8 @@ class DistilBertModel:
             pass
 
     def _run_forward(self, eng, *, R, B, mode, guided, train, image_clip, text_clip, attn_mask, x_in=None, x_in_stride=0, ids=None,
-                     noise=None, coef_a=None, coef_b=None, drop_seed=0, x_out=None):
-        p = L.Pass(R, B, mode, 1 if guided else 0, 1 if train else 0, L.ptr(x_in), x_in_stride, L.ptr(ids), L.ptr(noise), L.ptr(coef_a),
+                     noise=None, coef_a=None, coef_b=None, drop_seed=0, x_out=None, reuse_proj=False):
+        p = L.Pass(R, B, mode, 1 if guided else 0, 1 if train else 0, 1 if reuse_proj else 0, L.ptr(x_in), x_in_stride, L.ptr(ids), L.ptr(noise), L.ptr(coef_a),
                    L.ptr(coef_b), L.ptr(image_clip), L.ptr(text_clip), L.ptr(attn_mask), drop_seed, L.ptr(x_out))
         with torch.cuda.device(self.device):
             L.check(L.load().clipdlm_engine_forward(eng, C.byref(p), self._stream()))

@@ -128,6 +128,9 @@ int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cli
                      int32_t H, const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p,
                      clipdlm_stream stream);
 
+/* Test hook: 1 forces the fp32 SIMT attention kernels even where the tensor-core (mma.sync) path applies (plain bf16, L <= 32). */
+void clipdlm_attn_force_simt(int32_t on);
+
 /* Column sums (bias gradients): out[n] += sum_m x[m, n]. */
 int clipdlm_colsum(const clipdlm_bf_t* x, int64_t rows, int32_t N, float* out, clipdlm_stream stream);
 
@@ -219,6 +222,7 @@ void clipdlm_engine_destroy(clipdlm_engine_t* e);
  * train = 1 enables dropout and keeps activations for clipdlm_engine_backward. x_out (fp32 [R, L, D]) may be NULL. */
 typedef struct clipdlm_pass {
   int32_t R, B, mode, guided, train;
+  int32_t reuse_proj; /* 1: image_clip / text_clip / attn_mask / guided are those of the previous pass (denoise loop): skip the CLIP projections + key mask */
   const float* x_in; int64_t x_in_stride; /* mode 0 input and its row pitch in elements (0 = dense max_len * dim) */
   const int32_t* ids; const float* noise; const float* coef_a; const float* coef_b;
   const float* image_clip; const float* text_clip; const int32_t* attn_mask;

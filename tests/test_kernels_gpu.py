@@ -263,6 +263,33 @@ def test_attention_dropout_fwd_bwd_consistent(G):
     assert rel(G.join(gh, gl), qr.grad) < 3e-5
 
 
+def test_attention_mma_path_matches_simt_with_dropout(G):
+    """plain bf16, L <= 32 runs on mma.sync tensor-core tiles; the SIMT kernel must see the same dropout mask."""
+    R, L, D, H, p = 13, 18, 768, 12, 0.1
+    qkv = (torch.randn(R * L, 3 * D, device=G.DEV)).bfloat16()
+    dctx = torch.randn(R * L, D, device=G.DEV).bfloat16()
+    km = torch.rand(R, L, device=G.DEV) > 0.2
+    km[:, 16] = True
+    words = torch.zeros(R, 1, device=G.DEV, dtype=torch.int64)
+    for j in range(L):
+        words[:, 0] |= km[:, j].long() << j
+    words = words.to(torch.int32).contiguous()
+    lib, Lb = G.lib(), G.L
+    outs = {}
+    for simt in (0, 1):
+        lib.clipdlm_attn_force_simt(simt)
+        ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
+        dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
+        Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx, None)), 4242, 9, p, G.st()))
+        Lb.check(lib.clipdlm_attn_bwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), C.byref(G.bfp(dctx, None)), R, L, D, H, C.byref(G.bfp(dq, None)),
+                                      4242, 9, p, G.st()))
+        torch.cuda.synchronize()
+        outs[simt] = (ctx.float(), dq.float())
+    lib.clipdlm_attn_force_simt(0)
+    assert rel(outs[0][0], outs[1][0]) < 1e-2 and rel(outs[0][1], outs[1][1]) < 1.5e-2
+    # a differing mask would change ~10 % of the probabilities by 100 %: far outside these bounds
+
+
 # ------------------------------------------------------------------------------------------------------------ embed / loss / misc
 @pytest.mark.parametrize("fusion,guided", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("mode", [0, 1])
