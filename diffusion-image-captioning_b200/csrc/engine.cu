@@ -179,9 +179,10 @@ static size_t carve(clipdlm_engine* e, uint8_t* base) {
   e->d_img_proj = (float*)cv.take((size_t)e->batch * D * 4);
   e->d_txt_proj = (float*)cv.take((size_t)e->batch * D * 4);
   e->keymask = (uint32_t*)cv.take((size_t)e->max_rows * ((e->L + 31) / 32) * 4);
-  e->part_max = (float*)cv.take((size_t)e->n_vtiles * T16 * 4);
-  e->part_sum = (float*)cv.take((size_t)e->n_vtiles * T16 * 4);
-  e->part_arg = (int32_t*)cv.take((size_t)e->n_vtiles * T16 * 4);
+  const size_t lse_slots = 2 * (size_t)e->n_vtiles;  // the LSE epilogue emits one partial per 128-column half tile
+  e->part_max = (float*)cv.take(lse_slots * T16 * 4);
+  e->part_sum = (float*)cv.take(lse_slots * T16 * 4);
+  e->part_arg = (int32_t*)cv.take(lse_slots * T16 * 4);
   e->tgt_logit = (float*)cv.take(T16 * 4);
   e->lse = (float*)cv.take(T16 * 4);
   return (cv.off + 255) & ~size_t(255);
@@ -366,7 +367,7 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = e->part_arg; g.tgt_logit = e->tgt_logit;
   g.targets = targets; g.tgt_period = tgt_period;
   RUNG(g);
-  RUNP(CLIPDLM_PROF_LOSS, 0, 3.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, e->part_arg, e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
+  RUNP(CLIPDLM_PROF_LOSS, 0, 6.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, e->part_arg, 2 * e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
                            scale, st));
   return 0;
 }

@@ -22,11 +22,12 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16384
 constexpr int B_STAGE_BYTES = BN * BK * 2;          // 32768
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int STG_PITCH = 144;                      // bytes per staged row (128 B payload + 16 B pad: conflict-free 16 B accesses)
-constexpr int STG_WARP_BYTES = 32 * STG_PITCH;      // 4608
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quadrant, each owning 128 of the 256 tile columns
+constexpr int STG_PITCH = 80;                       // bytes per staged row (64 B payload = 32 bf16 or 16 fp32, + 16 B pad)
+constexpr int STG_WARP_BYTES = 32 * STG_PITCH;      // 2560
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 
 struct GemmArgs {
   int M, N, K;
@@ -151,30 +152,34 @@ __device__ __forceinline__ void tile_store_pair(const GemmArgs& g, __nv_bfloat16
     tile_store_bf16(g, lo, ld, row_base, n0, stg, r);
   }
 }
-// fp32 tile 32 rows x 32 cols (128 B per row). Coalesced side: lane l handles row (l>>3)+4j, 16-byte piece (l&7).
+// fp32 tile 32 rows x 32 cols, staged as two 16-column halves (64 B per row). Coalesced side: lane l handles row (l>>2)+8j, piece (l&3).
 template <bool RED>
 __device__ __forceinline__ void tile_store_f32(const GemmArgs& g, float* base, long long ld, int row_base, int n0, uint8_t* stg,
                                                const float (&v)[32]) {
   const int lane = lane_id();
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(stg + lane * STG_PITCH + i * 16) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-  __syncwarp();
+  for (int h = 0; h < 2; ++h) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int rr = (lane >> 3) + 4 * j;
-    const int m = row_base + rr;
-    if (m < g.M) {
-      const float4 x = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + (lane & 7) * 16);
-      float* dst = base + map_row(g, m) * ld + n0 + (lane & 7) * 4;
-      if (RED) {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-      } else {
-        *reinterpret_cast<float4*>(dst) = x;
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(stg + lane * STG_PITCH + i * 16) =
+          make_float4(v[h * 16 + i * 4], v[h * 16 + i * 4 + 1], v[h * 16 + i * 4 + 2], v[h * 16 + i * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = (lane >> 2) + 8 * j;
+      const int m = row_base + rr;
+      if (m < g.M) {
+        const float4 x = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + (lane & 3) * 16);
+        float* dst = base + map_row(g, m) * ld + n0 + h * 16 + (lane & 3) * 4;
+        if (RED) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst) = x;
+        }
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 template <int AMAJ, int BMAJ, int EPI>
@@ -185,7 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
   uint8_t* staging = smem + STAGES * STAGE_BYTES;
-  float* sbias = reinterpret_cast<float*>(staging + 4 * STG_WARP_BYTES);
+  float* sbias = reinterpret_cast<float*>(staging + EPI_WARPS * STG_WARP_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + BN * 4);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
@@ -203,7 +208,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -283,8 +288,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
-    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
-    uint8_t* stg = staging + q * STG_WARP_BYTES;
+    const int ew = warp - 4;
+    const int q = ew & 3;       // TMEM lane quadrant == warp % 4
+    const int hsel = ew >> 2;   // which 128-column half of the tile this warp drains
+    const int c_lo = hsel * (BN / 64), c_hi = c_lo + BN / 64;
+    uint8_t* stg = staging + ew * STG_WARP_BYTES;
     int as = 0; uint32_t aphase = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const int tile = w / g.k_splits;
@@ -293,12 +301,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int m = row_base + lane;
 
       if (EPI == CLIPDLM_EPI_STORE && g.bias != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers done
-        for (int i = threadIdx.x - 128; i < BN; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's readers done
+        for (int i = threadIdx.x - 128; i < BN; i += 32 * EPI_WARPS) {
           const int n = n_blk * BN + i;
           sbias[i] = n < g.N ? g.bias[n] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
 
       // plain-bf16 residual / gelu'(u) operand: prefetch its first 32-column chunk while the MMAs of this tile are still running
@@ -308,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const bool fast_aux = EPI == CLIPDLM_EPI_STORE && aux != nullptr && g.u_lo == nullptr && g.res_lo == nullptr &&
                             !(g.u_hi != nullptr && g.res_hi != nullptr);
       uint4 aux_nxt[4];
-      if (fast_aux) tile_issue(g, aux, ld_aux, row_base, n_blk * BN, aux_nxt);
+      if (fast_aux && n_blk * BN + c_lo * 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n_blk * BN + c_lo * 32, aux_nxt);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -319,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         const int tgt = (m < g.M && g.targets != nullptr) ? g.targets[m % g.tgt_period] : -1;
         float tl = 0.f; bool has_t = false;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= g.N) break;
           float v[32];
@@ -339,15 +347,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) csum += __expf(v[j] - mx);
           sum = sum * __expf(prev_max - mx) + csum;
         }
-        if (m < g.M) {
-          g.part_max[(size_t)n_blk * g.M + m] = mx;
-          g.part_sum[(size_t)n_blk * g.M + m] = sum;
-          g.part_arg[(size_t)n_blk * g.M + m] = arg;
+        if (m < g.M) {  // one partial per (row, 128-column half tile); an all-padding half leaves the neutral (-inf, 0)
+          const size_t slot = (size_t)(n_blk * 2 + hsel) * g.M + m;
+          g.part_max[slot] = mx;
+          g.part_sum[slot] = sum;
+          g.part_arg[slot] = arg;
           if (has_t && g.tgt_logit != nullptr) g.tgt_logit[m] = tl;
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           const int n0 = n_blk * BN + c * 32;
           if (EPI != CLIPDLM_EPI_SMGRAD && n0 >= g.N) break;
           float v[32];
@@ -370,7 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             if (fast_aux) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
-              if (c + 1 < BN / 32 && n0 + 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n0 + 32, aux_nxt);
+              if (c + 1 < c_hi && n0 + 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n0 + 32, aux_nxt);
             }
             if (g.bias != nullptr) {
 #pragma unroll

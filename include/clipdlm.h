@@ -36,7 +36,7 @@ int clipdlm_device_ok(void);
 enum {
   CLIPDLM_EPI_STORE = 0,  /* out = f(acc): +bias, dropout, +residual, gelu dual-store, *gelu'(u); bf16 pair / f32 */
   CLIPDLM_EPI_WGRAD = 1,  /* acc_f32[M,N] += acc   (split-K, fp32 red.add) */
-  CLIPDLM_EPI_LSE = 2,    /* per (row, 256-col tile) max / sum-exp / argmax partials + target logit; no logits in HBM */
+  CLIPDLM_EPI_LSE = 2,    /* per (row, 128-col half tile) max / sum-exp / argmax partials + target logit; no logits in HBM */
   CLIPDLM_EPI_SMGRAD = 3  /* out = (exp(acc - lse[m]) - [n == tgt[m]]) * scale   (softmax-CE gradient, bf16 pair) */
 };
 
@@ -60,7 +60,7 @@ typedef struct clipdlm_gemm {
   /* WGRAD */
   float* acc_f32;                 /* [M, ldo] fp32, accumulated in place */
   /* LSE / SMGRAD */
-  float* part_max; float* part_sum; int32_t* part_arg; /* [ceil(N/256)][M] */
+  float* part_max; float* part_sum; int32_t* part_arg; /* [2 * ceil(N/256)][M]: slot 2 * tile + half */
   float* tgt_logit;               /* [M] */
   const int32_t* targets; int32_t tgt_period; /* target of row m = targets[m % tgt_period] */
   const float* lse;               /* [M] (SMGRAD) */

@@ -81,13 +81,13 @@ def test_gemm_lse_smgrad_gather_scatter(G, R, pair):
     B = max(1, R // 3) if R % 3 == 0 else R
     tgt = torch.randint(0, V, (B * Ltxt,), device=G.DEV, dtype=torch.int32)
     nt = (V + 255) // 256
-    pm = torch.zeros(nt, M, device=G.DEV); ps = torch.zeros(nt, M, device=G.DEV); pa = torch.zeros(nt, M, device=G.DEV, dtype=torch.int32)
+    pm = torch.zeros(2 * nt, M, device=G.DEV); ps = torch.zeros(2 * nt, M, device=G.DEV); pa = torch.zeros(2 * nt, M, device=G.DEV, dtype=torch.int32)
     tl = torch.zeros(M, device=G.DEV)
     G.gemm(a_hi=xh, a_lo=xl, b_hi=eh, b_lo=el, lda=D, ldb=D, M=M, N=V, K=D, gather_len=Ltxt, gather_stride=Lf, epilogue=2,
            part_max=pm, part_sum=ps, part_arg=pa, tgt_logit=tl, targets=tgt, tgt_period=B * Ltxt)
     lse = torch.zeros(M, device=G.DEV); am = torch.zeros(M, device=G.DEV, dtype=torch.int32)
     acc = torch.zeros(1, device=G.DEV, dtype=torch.float64)
-    G.L.check(G.lib().clipdlm_lse_combine(pm.data_ptr(), ps.data_ptr(), pa.data_ptr(), nt, M, tl.data_ptr(), lse.data_ptr(), am.data_ptr(),
+    G.L.check(G.lib().clipdlm_lse_combine(pm.data_ptr(), ps.data_ptr(), pa.data_ptr(), 2 * nt, M, tl.data_ptr(), lse.data_ptr(), am.data_ptr(),
                                           acc.data_ptr(), 1.0 / R, G.st()))
     xg = G.join(xh, xl).view(R, Lf, D)[:, :Ltxt].reshape(M, D).double()
     logits = xg @ G.join(eh, el)[:V].double().t()
