@@ -46,6 +46,7 @@ struct GemmArgs {
   const __nv_bfloat16 *u_hi, *u_lo;
   long long ldu;
   int scatter_len, scatter_stride;
+  int al32;  // every bf16 epilogue operand is 32-byte aligned with a pitch that is a multiple of 16 elements
   DropoutCfg drop;
   float* part_max;
   float* part_sum;
@@ -61,95 +62,67 @@ __device__ __forceinline__ long long map_row(const GemmArgs& g, int m) {
   return g.scatter_len > 0 ? (long long)(m / g.scatter_len) * g.scatter_stride + (m % g.scatter_len) : (long long)m;
 }
 
-// ---- per-warp smem transposes: thread-owns-row <-> coalesced global access --------------------------------------
-// bf16 tile 32 rows x 32 cols. Coalesced side: lane l handles row (l>>2)+8j, 16-byte piece (l&3).
-__device__ __forceinline__ void tile_load_bf16(const GemmArgs& g, const __nv_bfloat16* base, long long ld, int row_base, int n0,
-                                               uint8_t* stg, float (&r)[32], bool accumulate) {
-  const int lane = lane_id();
+// ---- row-wise epilogue I/O --------------------------------------------------------------------------------------
+// After tcgen05.ld (32x32b) thread i of a TMEM lane quadrant owns row i of the tile and 32 consecutive columns, i.e. 64
+// contiguous bytes of a bf16 row. Those are read / written directly with two 256-bit accesses (LDG/STG.256: one full 32-byte
+// sector per access) - no shared-memory transpose, no extra synchronisation. Falls back to 128-bit accesses when the
+// operand is only 16-byte aligned.
+__device__ __forceinline__ void ld_row64(const __nv_bfloat16* p, bool al32, uint32_t (&r)[16]) {
+  if (al32) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int rr = (lane >> 2) + 8 * j;
-    const int m = row_base + rr;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (m < g.M) val = __ldg(reinterpret_cast<const uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8));
-    *reinterpret_cast<uint4*>(stg + rr * STG_PITCH + (lane & 3) * 16) = val;
-  }
-  __syncwarp();
+    for (int h = 0; h < 2; ++h)
+      asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[h * 8 + 0]), "=r"(r[h * 8 + 1]), "=r"(r[h * 8 + 2]), "=r"(r[h * 8 + 3]), "=r"(r[h * 8 + 4]), "=r"(r[h * 8 + 5]),
+                     "=r"(r[h * 8 + 6]), "=r"(r[h * 8 + 7])
+                   : "l"(p + h * 16));
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 x = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + i * 16);
-    float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
-    if (accumulate) {
-      r[i * 8 + 0] += a.x; r[i * 8 + 1] += a.y; r[i * 8 + 2] += b.x; r[i * 8 + 3] += b.y;
-      r[i * 8 + 4] += c.x; r[i * 8 + 5] += c.y; r[i * 8 + 6] += d.x; r[i * 8 + 7] += d.y;
-    } else {
-      r[i * 8 + 0] = a.x; r[i * 8 + 1] = a.y; r[i * 8 + 2] = b.x; r[i * 8 + 3] = b.y;
-      r[i * 8 + 4] = c.x; r[i * 8 + 5] = c.y; r[i * 8 + 6] = d.x; r[i * 8 + 7] = d.y;
+    for (int h = 0; h < 4; ++h) {
+      const uint4 x = *reinterpret_cast<const uint4*>(p + h * 8);
+      r[h * 4 + 0] = x.x; r[h * 4 + 1] = x.y; r[h * 4 + 2] = x.z; r[h * 4 + 3] = x.w;
     }
   }
-  __syncwarp();
 }
-// Split version of tile_load_bf16 for latency hiding: issue the 4 coalesced 16-byte loads of a 32x32 bf16 tile early ...
-__device__ __forceinline__ void tile_issue(const GemmArgs& g, const __nv_bfloat16* base, long long ld, int row_base, int n0, uint4 (&raw)[4]) {
-  const int lane = lane_id();
+__device__ __forceinline__ void st_row64(__nv_bfloat16* p, bool al32, const uint32_t (&r)[16]) {
+  if (al32) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int m = row_base + (lane >> 2) + 8 * j;
-    raw[j] = make_uint4(0, 0, 0, 0);
-    if (m < g.M) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8));
+    for (int h = 0; h < 2; ++h)
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + h * 16), "r"(r[h * 8 + 0]), "r"(r[h * 8 + 1]),
+                   "r"(r[h * 8 + 2]), "r"(r[h * 8 + 3]), "r"(r[h * 8 + 4]), "r"(r[h * 8 + 5]), "r"(r[h * 8 + 6]), "r"(r[h * 8 + 7])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) *reinterpret_cast<uint4*>(p + h * 8) = make_uint4(r[h * 4 + 0], r[h * 4 + 1], r[h * 4 + 2], r[h * 4 + 3]);
   }
 }
-// ... and consume them later: transpose through the warp's staging tile into "thread owns a row", then v = v + x or v * gelu'(x).
-template <bool DGELU>
-__device__ __forceinline__ void tile_consume(const uint4 (&raw)[4], uint8_t* stg, float (&v)[32]) {
-  const int lane = lane_id();
+// v (+)= unpack(raw)
+template <bool ACC>
+__device__ __forceinline__ void row_unpack(const uint32_t (&raw)[16], float (&v)[32]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * j) * STG_PITCH + (lane & 3) * 16) = raw[j];
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + i * 16);
-    const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
-    const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[i * 8 + e] = DGELU ? v[i * 8 + e] * dgelu_f(f[e]) : v[i * 8 + e] + f[e];
+  for (int i = 0; i < 16; ++i) {
+    const float2 f = unpack_bf16x2(raw[i]);
+    if (ACC) { v[2 * i] += f.x; v[2 * i + 1] += f.y; } else { v[2 * i] = f.x; v[2 * i + 1] = f.y; }
   }
-  __syncwarp();
 }
-__device__ __forceinline__ void tile_load_pair(const GemmArgs& g, const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long ld,
-                                               int row_base, int n0, uint8_t* stg, float (&r)[32]) {
-  tile_load_bf16(g, hi, ld, row_base, n0, stg, r, false);
-  if (lo != nullptr) tile_load_bf16(g, lo, ld, row_base, n0, stg, r, true);
-}
-__device__ __forceinline__ void tile_store_bf16(const GemmArgs& g, __nv_bfloat16* base, long long ld, int row_base, int n0,
-                                                uint8_t* stg, const float (&v)[32]) {
-  const int lane = lane_id();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 x;
-    x.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]); x.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
-    x.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); x.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
-    *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + i * 16) = x;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int rr = (lane >> 2) + 8 * j;
-    const int m = row_base + rr;
-    if (m < g.M)
-      *reinterpret_cast<uint4*>(base + map_row(g, m) * ld + n0 + (lane & 3) * 8) =
-          *reinterpret_cast<const uint4*>(stg + rr * STG_PITCH + (lane & 3) * 16);
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void tile_store_pair(const GemmArgs& g, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld, int row_base,
-                                                int n0, uint8_t* stg, const float (&v)[32]) {
-  tile_store_bf16(g, hi, ld, row_base, n0, stg, v);
+// 32 values of a bf16 (pair) row segment -> floats
+__device__ __forceinline__ void row_load_pair(const __nv_bfloat16* hi, const __nv_bfloat16* lo, bool al32, float (&r)[32]) {
+  uint32_t raw[16];
+  ld_row64(hi, al32, raw);
+  row_unpack<false>(raw, r);
   if (lo != nullptr) {
-    float r[32];
+    ld_row64(lo, al32, raw);
+    row_unpack<true>(raw, r);
+  }
+}
+__device__ __forceinline__ void row_store_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, bool al32, const float (&v)[32]) {
+  uint32_t raw[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = v[i] - bf16_round(v[i]);
-    tile_store_bf16(g, lo, ld, row_base, n0, stg, r);
+  for (int i = 0; i < 16; ++i) raw[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  st_row64(hi, al32, raw);
+  if (lo != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) raw[i] = pack_bf16x2(v[2 * i] - bf16_round(v[2 * i]), v[2 * i + 1] - bf16_round(v[2 * i + 1]));
+    st_row64(lo, al32, raw);
   }
 }
 // fp32 tile 32 rows x 32 cols, staged as two 16-column halves (64 B per row). Coalesced side: lane l handles row (l>>2)+8j, piece (l&3).
@@ -310,13 +283,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       }
 
       // plain-bf16 residual / gelu'(u) operand: prefetch its first 32-column chunk while the MMAs of this tile are still running
+      const bool valid = m < g.M;
+      const long long mr = valid ? map_row(g, m) : 0;
+      const bool al32 = g.al32 != 0;
       const bool aux_is_u = g.u_hi != nullptr;
       const __nv_bfloat16* aux = aux_is_u ? g.u_hi : g.res_hi;
       const long long ld_aux = aux_is_u ? g.ldu : g.ldr;
       const bool fast_aux = EPI == CLIPDLM_EPI_STORE && aux != nullptr && g.u_lo == nullptr && g.res_lo == nullptr &&
                             !(g.u_hi != nullptr && g.res_hi != nullptr);
-      uint4 aux_nxt[4];
-      if (fast_aux && n_blk * BN + c_lo * 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n_blk * BN + c_lo * 32, aux_nxt);
+      uint32_t aux_nxt[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) aux_nxt[i] = 0u;
+      if (fast_aux && valid && n_blk * BN + c_lo * 32 < g.N) ld_row64(aux + mr * ld_aux + n_blk * BN + c_lo * 32, al32, aux_nxt);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -373,13 +351,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               if (n == tgt) p -= 1.f;
               v[j] = p * g.grad_scale;
             }
-            tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
+            if (valid) row_store_pair(g.out_hi + mr * g.ldo + n0, g.out_lo ? g.out_lo + mr * g.ldo + n0 : nullptr, al32, v);
           } else {  // STORE
-            uint4 aux_cur[4];
+            uint32_t aux_cur[16];
             if (fast_aux) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
-              if (c + 1 < c_hi && n0 + 32 < g.N) tile_issue(g, aux, ld_aux, row_base, n0 + 32, aux_nxt);
+              for (int j = 0; j < 16; ++j) aux_cur[j] = aux_nxt[j];
+              if (valid && c + 1 < c_hi && n0 + 32 < g.N) ld_row64(aux + mr * ld_aux + n0 + 32, al32, aux_nxt);
             }
             if (g.bias != nullptr) {
 #pragma unroll
@@ -395,28 +373,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               }
             }
             if (fast_aux) {
-              if (aux_is_u) tile_consume<true>(aux_cur, stg, v);
-              else tile_consume<false>(aux_cur, stg, v);
-            } else {
+              if (aux_is_u) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float2 f = unpack_bf16x2(aux_cur[j]);
+                  v[2 * j] *= dgelu_f(f.x);
+                  v[2 * j + 1] *= dgelu_f(f.y);
+                }
+              } else {
+                row_unpack<true>(aux_cur, v);
+              }
+            } else if (valid) {
               if (g.u_hi != nullptr) {
                 float u[32];
-                tile_load_pair(g, g.u_hi, g.u_lo, g.ldu, row_base, n0, stg, u);
+                row_load_pair(g.u_hi + mr * g.ldu + n0, g.u_lo ? g.u_lo + mr * g.ldu + n0 : nullptr, al32, u);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= dgelu_f(u[j]);
               }
               if (g.res_hi != nullptr) {
                 float r[32];
-                tile_load_pair(g, g.res_hi, g.res_lo, g.ldr, row_base, n0, stg, r);
+                row_load_pair(g.res_hi + mr * g.ldr + n0, g.res_lo ? g.res_lo + mr * g.ldr + n0 : nullptr, al32, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += r[j];
               }
             }
-            if (g.out_hi != nullptr) tile_store_pair(g, g.out_hi, g.out_lo, g.ldo, row_base, n0, stg, v);
-            if (g.out_f32 != nullptr) tile_store_f32<false>(g, g.out_f32, g.ldo, row_base, n0, stg, v);
-            if (g.out2_hi != nullptr) {
+            if (valid) {
+              if (g.out_hi != nullptr) row_store_pair(g.out_hi + mr * g.ldo + n0, g.out_lo ? g.out_lo + mr * g.ldo + n0 : nullptr, al32, v);
+              if (g.out_f32 != nullptr) {
+                float* dst = g.out_f32 + mr * g.ldo + n0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
-              tile_store_pair(g, g.out2_hi, g.out2_lo, g.ldo, row_base, n0, stg, v);
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+              if (g.out2_hi != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+                row_store_pair(g.out2_hi + mr * g.ldo + n0, g.out2_lo ? g.out2_lo + mr * g.ldo + n0 : nullptr, al32, v);
+              }
             }
           }
         }
@@ -596,6 +588,17 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   ga.res_hi = (const __nv_bfloat16*)g->res_hi; ga.res_lo = (const __nv_bfloat16*)g->res_lo; ga.ldr = g->ldr;
   ga.u_hi = (const __nv_bfloat16*)g->u_hi; ga.u_lo = (const __nv_bfloat16*)g->u_lo; ga.ldu = g->ldu;
   ga.scatter_len = g->scatter_len; ga.scatter_stride = g->scatter_stride;
+  {
+    const void* ptrs[8] = {g->out_hi, g->out_lo, g->out2_hi, g->out2_lo, g->res_hi, g->res_lo, g->u_hi, g->u_lo};
+    bool ok = (g->ldo % 16 == 0) && (!g->res_hi || g->ldr % 16 == 0) && (!g->u_hi || g->ldu % 16 == 0);
+    for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 31) == 0);
+    ga.al32 = ok ? 1 : 0;
+    ok = (g->ldo % 8 == 0) && (!g->res_hi || g->ldr % 8 == 0) && (!g->u_hi || g->ldu % 8 == 0);
+    for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    if (g->epilogue == CLIPDLM_EPI_STORE || g->epilogue == CLIPDLM_EPI_SMGRAD)
+      CLIPDLM_CHECK(ok && (!g->out_f32 || ((reinterpret_cast<uintptr_t>(g->out_f32) & 15) == 0 && g->ldo % 4 == 0)),
+                    "GEMM epilogue operands must be 16-byte aligned with pitches that are multiples of 8 elements");
+  }
   ga.drop.seed = g->drop_seed; ga.drop.site = g->drop_site;
   ga.drop.thresh16 = g->drop_p > 0.f ? (uint32_t)(g->drop_p * 65536.f + 0.5f) : 0u;
   ga.drop.scale = g->drop_p > 0.f ? 1.f / (1.f - g->drop_p) : 1.f;
