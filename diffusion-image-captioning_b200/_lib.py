@@ -113,6 +113,7 @@ _SIGS = {
     "clipdlm_device_ok": (C.c_int, []),
     "clipdlm_gemm": (C.c_int, [C.POINTER(Gemm), c_p]),
     "clipdlm_gemm_debug_mn_desc": (None, [u32, u32]),
+    "clipdlm_gemm_debug_flags": (None, [u32]),
     "clipdlm_lse_combine": (C.c_int, [c_p, c_p, c_p, i32, i32, c_p, c_p, c_p, c_p, f64, c_p]),
     "clipdlm_embed_fwd": (C.c_int, [C.POINTER(Embed), c_p]),
     "clipdlm_embed_bwd": (C.c_int, [C.POINTER(Bf), i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p, c_p, c_p]),

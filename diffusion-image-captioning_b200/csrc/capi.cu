@@ -20,6 +20,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st);
 int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
                          int* argmax, double* loss_acc, double scale, cudaStream_t st);
 void gemm_debug_mn_desc(uint32_t lbo, uint32_t sbo);
+void gemm_debug_flags(uint32_t flags);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
 int embed_bwd_dispatch(const clipdlm_bf_t* dz, int R, int B, int Ltxt, int L, int D, int fusion, int guided, float* d_pos, float* d_seg,
                        float* d_img, float* d_txt, cudaStream_t st);
@@ -67,6 +68,7 @@ int clipdlm_device_ok(void) {
 int clipdlm_gemm(const clipdlm_gemm_t* g, clipdlm_stream stream) { return gemm_dispatch(g, (cudaStream_t)stream); }
 
 void clipdlm_gemm_debug_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes) { gemm_debug_mn_desc(lbo_bytes, sbo_bytes); }
+void clipdlm_gemm_debug_flags(uint32_t flags) { gemm_debug_flags(flags); }
 
 int clipdlm_lse_combine(const float* part_max, const float* part_sum, const int32_t* part_arg, int32_t n_tiles, int32_t M,
                         const float* tgt_logit, float* lse, int32_t* argmax, double* loss_acc, double scale, clipdlm_stream stream) {

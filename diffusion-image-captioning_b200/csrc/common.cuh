@@ -141,32 +141,36 @@ __device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, unsigned 
   return m;
 }
 
-// exact-erf GELU (HF activations.py GELUActivation -> nn.functional.gelu) and its derivative.
-// erf is evaluated branch-free with Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 round-off level), one MUFU.RCP
-// and one MUFU.EX2 per element: libdevice erff() is ~3x the instructions and branches per element, which made the GEMM
-// epilogues (4 warps, one per scheduler) the bottleneck of the K = 768 GEMMs.  phi(x) = 0.5 * erfc(-x / sqrt(2)) is formed
-// without cancellation on either tail; exp(-x^2 / 2) is shared between cdf and pdf in the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  e = __expf(-ax * ax);                 // = exp(-x^2 / 2)
-  const float half_erfc = 0.5f * poly * e;  // 0.5 * erfc(|x| / sqrt 2)
-  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+// exact-erf GELU (HF activations.py GELUActivation -> nn.functional.gelu) and its derivative, built for the GEMM epilogues
+// (8 warps have to finish 128 x 256 outputs inside one K = 768 mainloop, ~6 k cycles): the normal tail
+//   h(a) = Phi(-a) = 0.5 erfc(a / sqrt 2),  a = |x|,  is evaluated as 2^(-p(a)) with p a degree-6 polynomial (p(0) = 1, minimax
+// fit of -log2 h on [0, 5.6] weighted by h; |abs error of Phi| <= 1.9e-7 in fp32, i.e. round-off level - the A&S 7.1.26 form
+// used before has 1.5e-7) - ONE MUFU.EX2 and 7 FMA-pipe instructions, no reciprocal, no branches.  Beyond a = 5.6 the argument
+// is clamped (h < 1.1e-8 there).  gelu(x) = max(x, 0) - |x| h(|x|);  gelu'(x) = Phi(x) + x phi(x) with phi through a second EX2.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float phi_tail(float a) {   // a >= 0
+  a = fminf(a, 5.6f);
+  float p = fmaf(a, 1.775593238e-05f, -6.477629528e-04f);
+  p = fmaf(a, p, 7.724055995e-03f);
+  p = fmaf(a, p, -5.292675105e-02f);
+  p = fmaf(a, p, -4.590827311e-01f);
+  p = fmaf(a, p, -1.151116857e+00f);
+  p = fmaf(a, p, -1.0f);
+  return ex2_ftz(p);
 }
 __device__ __forceinline__ float gelu_f(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+  const float a = fabsf(x);
+  return fmaf(-a, phi_tail(a), fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float dgelu_f(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143268f, e, cdf);
+  const float h = phi_tail(fabsf(x));
+  const float pdf = ex2_ftz(fmaf(x * x, -0.72134752044448170f, -1.32574806473616470f));  // exp(-x^2/2) / sqrt(2 pi)
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  return fmaf(x, pdf, cdf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,6 +211,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// thread-block cluster (CTA pair) helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// Arrive on an mbarrier that may live in the peer CTA. Default .release.cta semantics on purpose: a .cluster-scope release
+// compiles to MEMBAR.ALL.GPU + CCTL per arrive (measured: 4x slower pipeline); the data these barriers order travels
+// through the async proxy (TMA complete_tx) or TMEM (tcgen05.wait::ld + tcgen05 fences), not through generic memory.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads, completing on an mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
@@ -225,6 +263,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// CTA-pair variants: the data lands in THIS CTA's shared memory, the transaction bytes are signalled on the mbarrier at
+// shared::cluster address `bar_cluster` (the leader CTA's barrier, which the MMA-issuing thread waits on).
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------
@@ -234,6 +287,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// CTA-pair (cta_group::2) variants: one warp of EACH CTA of the pair executes alloc / dealloc.
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -250,6 +311,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// CTA-pair MMA: issued by one thread of the leader CTA; A (M = 256: 128 rows from each CTA) and B (N split in halves, one
+// per CTA) are read from the same shared-memory offsets in both CTAs, each CTA's TMEM receives its 128 accumulator rows.
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all prior MMAs of this thread completed) on the mbarrier at the same shared-memory offset in both CTAs.
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i gets lane base+i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {

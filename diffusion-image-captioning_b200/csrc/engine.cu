@@ -364,10 +364,10 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   clipdlm_gemm_t g = gemm_desc(e->xo, c.dim, 0, emb, c.dim, 0, M, c.vocab, c.dim);
   g.gather_len = e->Ltxt; g.gather_stride = e->L;
   g.epilogue = CLIPDLM_EPI_LSE;
-  g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = e->part_arg; g.tgt_logit = e->tgt_logit;
+  g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = argmax ? e->part_arg : nullptr; g.tgt_logit = e->tgt_logit;
   g.targets = targets; g.tgt_period = tgt_period;
   RUNG(g);
-  RUNP(CLIPDLM_PROF_LOSS, 0, 6.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, e->part_arg, 2 * e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
+  RUNP(CLIPDLM_PROF_LOSS, 0, 6.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, argmax ? e->part_arg : nullptr, 2 * e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
                            scale, st));
   return 0;
 }

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues.  D[M,N] = A[M,K] * B[N,K]^T.
 //
-// One persistent, warp-specialised kernel (256 threads, 1 CTA / SM):
+// One persistent, warp-specialised kernel (384 threads, 1 CTA / SM), run as CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles)
+// or single CTAs (cta_group::1, 128 x 256 tiles; see Geo<CG>):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages x (A 16 KB + B 32 KB))
 //   warp 1   : MMA issuer    (one lane issues tcgen05.mma kind::f16, 128x256x16, accumulators in TMEM)
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
@@ -15,18 +16,29 @@
 #include "../../include/clipdlm.h"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace clipdlm {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16384
-constexpr int B_STAGE_BYTES = BN * BK * 2;          // 32768
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quadrant, each owning 128 of the 256 tile columns
 constexpr int STG_PITCH = 80;                       // bytes per staged row (64 B payload = 32 bf16 or 16 fp32, + 16 B pad)
 constexpr int STG_WARP_BYTES = 32 * STG_PITCH;      // 2560
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
+// Geometry per CTA-group size.  CG = 1: one CTA computes a 128 x 256 tile (tcgen05.mma.cta_group::1, M = 128).
+// CG = 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256): each CTA
+// stages its own 128 rows of A and only HALF of the B tile (128 of the 256 N rows), so the shared-memory traffic per MMA
+// (TMA writes + tensor-core operand reads) drops by a third - the CG = 1 kernel is shared-memory-bandwidth bound at ~65 % of
+// the tensor pipe - and the freed shared memory deepens the ring from 4 to 6 stages.
+template <int CG>
+struct Geo {
+  static constexpr int BN_CTA = BN / CG;
+  static constexpr int B_STAGE_BYTES = BN_CTA * BK * 2;   // 32768 / 16384
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
+};
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 
 struct GemmArgs {
@@ -47,6 +59,7 @@ struct GemmArgs {
   long long ldu;
   int scatter_len, scatter_stride;
   int al32;  // every bf16 epilogue operand is 32-byte aligned with a pitch that is a multiple of 16 elements
+  uint32_t dbg;  // clipdlm_gemm_debug_flags
   DropoutCfg drop;
   float* part_max;
   float* part_sum;
@@ -155,10 +168,12 @@ __device__ __forceinline__ void tile_store_f32(const GemmArgs& g, float* base, l
   }
 }
 
-template <int AMAJ, int BMAJ, int EPI>
+template <int AMAJ, int BMAJ, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs g) {
+  using G = Geo<CG>;
+  constexpr int STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -174,19 +189,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_items = g.num_m_tiles * g.num_n_tiles * g.k_splits;
+  // work units: CTAs (CG = 1) or CTA pairs (CG = 2); both CTAs of a pair walk the same item list in lockstep
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_stride = CG == 2 ? (int)num_clusters_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB0);
     if (g.nparts > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+    // full: the leader's barrier collects the leader's arrive.expect_tx (bytes of BOTH CTAs) + the peer's plain arrive
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS * CG); }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits + TMEM allocation visible (pair-wide for CG = 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -194,10 +216,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const uint32_t full0_cluster = CG == 2 ? mapa_u32(&full_bar[0], 0) : 0u;  // leader's full barriers (shared::cluster)
+      for (int w = unit0; w < total_items; w += unit_stride) {
         const int split = w % g.k_splits;
         const int tile = w / g.k_splits;
         const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
+        const int m0 = (m_blk * CG + cta_rank) * BM;           // first A row of this CTA
+        const int n0 = n_blk * BN + cta_rank * G::BN_CTA;      // first B row this CTA stages
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(kb0 + g.kb_per_split, g.kb_total);
         for (int part = 0; part < g.nparts; ++part) {
@@ -207,19 +232,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stages + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            if (AMAJ == 0) {
-              if (g.gather_len > 0) tma_load_3d(sa, ta, &full_bar[stage], kb * BK, 0, m_blk * (BM / g.gather_len));
-              else tma_load_2d(sa, ta, &full_bar[stage], kb * BK, m_blk * BM);
-            } else {
+            if (g.dbg & 32u) {   // triage: no loads at all, the MMAs run on whatever is in shared memory
+              if (CG == 1 || cta_rank == 0) mbar_arrive(&full_bar[stage]);
+              else mbar_arrive_cluster(full0_cluster + stage * 8);
+            } else if (CG == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+              if (AMAJ == 0) {
+                if (g.gather_len > 0) tma_load_3d(sa, ta, &full_bar[stage], kb * BK, 0, m0 / g.gather_len);
+                else tma_load_2d(sa, ta, &full_bar[stage], kb * BK, m0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ta, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
-            }
-            if (BMAJ == 0) {
-              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, n_blk * BN);
-            } else {
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ta, &full_bar[stage], m0 + j * 64, kb * BK);
+              }
+              if (BMAJ == 0) {
+                tma_load_2d(sb, tb, &full_bar[stage], kb * BK, n0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, tb, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+                for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d(sb + j * 8192, tb, &full_bar[stage], n0 + j * 64, kb * BK);
+              }
+            } else {
+              const uint32_t fb = full0_cluster + stage * 8;
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              else mbar_arrive_cluster(fb);
+              if (AMAJ == 0) {
+                if (g.gather_len > 0) tma_load_3d_cg2(sa, ta, fb, kb * BK, 0, m0 / g.gather_len);
+                else tma_load_2d_cg2(sa, ta, fb, kb * BK, m0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sa + j * 8192, ta, fb, m0 + j * 64, kb * BK);
+              }
+              if (BMAJ == 0) {
+                tma_load_2d_cg2(sb, tb, fb, kb * BK, n0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d_cg2(sb + j * 8192, tb, fb, n0 + j * 64, kb * BK);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -227,12 +274,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, AMAJ, BMAJ);
+    // ===================================== MMA issuer (leader CTA of the pair only) =====================================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, AMAJ, BMAJ);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      for (int w = unit0; w < total_items; w += unit_stride) {
         const int split = w % g.k_splits;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(kb0 + g.kb_per_split, g.kb_total);
@@ -250,12 +297,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           constexpr uint32_t a_step = (AMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;  // K advance per MMA, 16-byte units
           constexpr uint32_t b_step = (BMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (g.dbg & 16u) continue;   // triage: no MMAs, the commits below fire immediately
+            if (CG == 2) umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);       // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_cg2(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -267,10 +319,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const int c_lo = hsel * (BN / 64), c_hi = c_lo + BN / 64;
     uint8_t* stg = staging + ew * STG_WARP_BYTES;
     int as = 0; uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    const uint32_t tempty0_leader = CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
+    for (int w = unit0; w < total_items; w += unit_stride) {
       const int tile = w / g.k_splits;
       const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
-      const int row_base = m_blk * BM + q * 32;
+      const int row_base = (m_blk * CG + cta_rank) * BM + q * 32;
       const int m = row_base + lane;
 
       if (EPI == CLIPDLM_EPI_STORE && g.bias != nullptr) {
@@ -291,18 +344,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const long long ld_aux = aux_is_u ? g.ldu : g.ldr;
       const bool fast_aux = EPI == CLIPDLM_EPI_STORE && aux != nullptr && g.u_lo == nullptr && g.res_lo == nullptr &&
                             !(g.u_hi != nullptr && g.res_hi != nullptr);
+      const bool dbg_nostore = (g.dbg & 1u) != 0, dbg_noaux = (g.dbg & 2u) != 0, dbg_drain = (g.dbg & 4u) != 0;
       uint32_t aux_nxt[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) aux_nxt[i] = 0u;
-      if (fast_aux && valid && n_blk * BN + c_lo * 32 < g.N) ld_row64(aux + mr * ld_aux + n_blk * BN + c_lo * 32, al32, aux_nxt);
+      if (fast_aux && valid && !dbg_noaux && n_blk * BN + c_lo * 32 < g.N) ld_row64(aux + mr * ld_aux + n_blk * BN + c_lo * 32, al32, aux_nxt);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
       if (EPI == CLIPDLM_EPI_LSE) {
+        // Online log-sum-exp over this warp's 128 columns, in the base-2 domain: one FMNMX + FFMA + MUFU.EX2 + FADD per logit.
+        // The running arg-max (3 more instructions per logit) is only tracked when the caller asked for it (denoise loop).
+        constexpr float LOG2E = 1.4426950408889634f;
         float mx = -INFINITY, sum = 0.f; int arg = 0;
         const int tgt = (m < g.M && g.targets != nullptr) ? g.targets[m % g.tgt_period] : -1;
+        const bool want_arg = g.part_arg != nullptr;
         float tl = 0.f; bool has_t = false;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
@@ -310,26 +368,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           if (n0 >= g.N) break;
           float v[32];
           tmem_ld32(taddr + c * 32, v);
-          const float prev_max = mx;
+          if (n0 + 32 > g.N) {   // vocabulary tail (last tile only): padding columns never win and add exp(-inf) = 0
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = (n0 + j) < g.N;
-            const float x = ok ? v[j] : -INFINITY;
-            v[j] = x;
-            if (x > mx) { mx = x; arg = n0 + j; }  // strict '>' keeps the first maximum (torch.argmax tie rule)
-            if (n0 + j == tgt) { tl = x; has_t = true; }
+            for (int j = 0; j < 32; ++j) v[j] = (n0 + j) < g.N ? v[j] : -INFINITY;
           }
-          // online softmax: rescale the running sum from prev_max to the new max (chunk has >= 1 valid column)
-          float csum = 0.f;
+          const float prev_max = mx;
+          if (want_arg) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) csum += __expf(v[j] - mx);
-          sum = sum * __expf(prev_max - mx) + csum;
+            for (int j = 0; j < 32; ++j)
+              if (v[j] > mx) { mx = v[j]; arg = n0 + j; }  // strict '>' keeps the first maximum (torch.argmax tie rule)
+          } else {
+            float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
+#pragma unroll
+            for (int j = 8; j < 32; j += 4) { m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]); }
+            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          }
+          if ((unsigned)(tgt - n0) < 32u) {   // the target logit lives in this chunk (1 chunk in ~950 per row)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + j == tgt) tl = v[j];
+            has_t = true;
+          }
+          // rescale the running sum from prev_max to the new max (every chunk has >= 1 valid column, so mx is finite)
+          const float nb = -mx * LOG2E;
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            c0 += ex2_ftz(fmaf(v[j], LOG2E, nb)); c1 += ex2_ftz(fmaf(v[j + 1], LOG2E, nb));
+            c2 += ex2_ftz(fmaf(v[j + 2], LOG2E, nb)); c3 += ex2_ftz(fmaf(v[j + 3], LOG2E, nb));
+          }
+          sum = fmaf(sum, ex2_ftz(fmaf(prev_max, LOG2E, nb)), (c0 + c1) + (c2 + c3));
         }
         if (m < g.M) {  // one partial per (row, 128-column half tile); an all-padding half leaves the neutral (-inf, 0)
           const size_t slot = (size_t)(n_blk * 2 + hsel) * g.M + m;
           g.part_max[slot] = mx;
           g.part_sum[slot] = sum;
-          g.part_arg[slot] = arg;
+          if (want_arg) g.part_arg[slot] = arg;
           if (has_t && g.tgt_logit != nullptr) g.tgt_logit[m] = tl;
         }
       } else {
@@ -342,26 +415,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           if (EPI == CLIPDLM_EPI_WGRAD) {
             tile_store_f32<true>(g, g.out_f32, g.ldo, row_base, n0, stg, v);
           } else if (EPI == CLIPDLM_EPI_SMGRAD) {
+            // (softmax - onehot) * scale with the scale folded into the exponent: one FFMA + MUFU.EX2 per logit
+            constexpr float LOG2E = 1.4426950408889634f;
             const int tgt = (m < g.M) ? g.targets[m % g.tgt_period] : -1;
             const float l = (m < g.M) ? g.lse[m] : 0.f;
+            const float nb = g.grad_scale > 0.f ? fmaf(-l, LOG2E, __log2f(g.grad_scale)) : -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              float p = (n < g.N) ? __expf(v[j] - l) : 0.f;
-              if (n == tgt) p -= 1.f;
-              v[j] = p * g.grad_scale;
+            for (int j = 0; j < 32; ++j) v[j] = ex2_ftz(fmaf(v[j], LOG2E, nb));
+            if (n0 + 32 > g.N) {   // zero the padding columns of the vocabulary tail
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (n0 + j) < g.N ? v[j] : 0.f;
+            }
+            if ((unsigned)(tgt - n0) < 32u) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n0 + j == tgt) v[j] -= g.grad_scale;
             }
             if (valid) row_store_pair(g.out_hi + mr * g.ldo + n0, g.out_lo ? g.out_lo + mr * g.ldo + n0 : nullptr, al32, v);
           } else {  // STORE
+            if (dbg_drain) {
+              if (v[0] == 1.2345e-30f && valid) g.out_hi[0] = __float2bfloat16(v[1]);  // keep the TMEM load live
+              continue;
+            }
             uint32_t aux_cur[16];
             if (fast_aux) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) aux_cur[j] = aux_nxt[j];
-              if (valid && c + 1 < c_hi && n0 + 32 < g.N) ld_row64(aux + mr * ld_aux + n0 + 32, al32, aux_nxt);
+              if (valid && !dbg_noaux && c + 1 < c_hi && n0 + 32 < g.N) ld_row64(aux + mr * ld_aux + n0 + 32, al32, aux_nxt);
             }
-            if (g.bias != nullptr) {
+            if (g.bias != nullptr) {   // explicit ld.shared (warp-wide broadcast): through the generic pointer these compile to LD
+              const uint32_t sb = smem_u32(sbias) + c * 128;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += sbias[c * 32 + j];
+              for (int j = 0; j < 8; ++j) {
+                float4 b4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
             }
             if (g.drop.thresh16 != 0) {
 #pragma unroll
@@ -397,7 +485,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 for (int j = 0; j < 32; ++j) v[j] += r[j];
               }
             }
-            if (valid) {
+            if (valid && dbg_nostore) {
+              float sacc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sacc += (g.out2_hi != nullptr) ? gelu_f(v[j]) + v[j] : v[j];
+              if (sacc == 1.2345e-30f) g.out_hi[0] = __float2bfloat16(sacc);
+            } else if (valid) {
               if (g.out_hi != nullptr) row_store_pair(g.out_hi + mr * g.ldo + n0, g.out_lo ? g.out_lo + mr * g.ldo + n0 : nullptr, al32, v);
               if (g.out_f32 != nullptr) {
                 float* dst = g.out_f32 + mr * g.ldo + n0;
@@ -415,14 +508,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty0_leader + as * 8);   // the MMA issuer lives in the leader CTA
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: nobody leaves while the peer may still read its smem / signal its barriers
+  if (warp == 2) {
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 
@@ -438,7 +536,7 @@ __global__ void lse_combine_kernel(const float* __restrict__ pmax, const float* 
     float mx = -INFINITY; int arg = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const float v = pmax[(size_t)t * M + m];
-      if (v > mx) { mx = v; arg = parg[(size_t)t * M + m]; }
+      if (v > mx) { mx = v; if (parg != nullptr) arg = parg[(size_t)t * M + m]; }
     }
     float s = 0.f;
     for (int t = 0; t < n_tiles; ++t) s += psum[(size_t)t * M + m] * __expf(pmax[(size_t)t * M + m] - mx);
@@ -518,21 +616,57 @@ static int operand_map(CUtensorMap* tm, const void* base, int major, int rows, i
   return encode_map(tm, base, 2, dims, str, box);
 }
 
-static uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0;
+static uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_flags = 0;
 static int g_num_sms = 0;
 
-template <int AMAJ, int BMAJ, int EPI>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
-                       int grid, cudaStream_t st) {
+template <int AMAJ, int BMAJ, int EPI, int CG>
+static int launch_gemm_cg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
+                          int units, cudaStream_t st) {
   static bool attr_set = false;
-  auto kfn = gemm_kernel<AMAJ, BMAJ, EPI>;
+  static int max_units = 0;   // co-resident work units (CTAs / CTA pairs) of this instantiation: the kernel is persistent
+  auto kfn = gemm_kernel<AMAJ, BMAJ, EPI, CG>;
   if (!attr_set) {
-    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::SMEM_BYTES));
+    max_units = g_num_sms / CG;
+    if (CG == 2) {
+      // SM floor-sweeping can leave TPCs with a single SM: only complete TPCs can host a CTA pair. A persistent grid larger
+      // than the number of co-resident pairs would run its tail as a second wave (2x the time), so ask the driver.
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)g_num_sms, 1, 1);
+      q.blockDim = dim3(NUM_THREADS, 1, 1);
+      q.dynamicSmemBytes = Geo<CG>::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CG; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      CLIPDLM_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kfn, &q));
+      if (n > 0 && n < max_units) max_units = n;
+      if (getenv("CLIPDLM_DEBUG")) fprintf(stderr, "clipdlm: gemm<%d,%d,%d,cg2> max active CTA pairs %d (SMs %d)\n", AMAJ, BMAJ, EPI, n, g_num_sms);
+    }
     attr_set = true;
   }
-  kfn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a0, a1, b0, b1, ga);
-  CLIPDLM_CUDA_OK(cudaGetLastError());
+  if (units > max_units) units = max_units;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(units * CG), 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Geo<CG>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLIPDLM_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, ga));
   return 0;
+}
+template <int AMAJ, int BMAJ, int EPI>
+static int launch_gemm(int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
+                       int units, cudaStream_t st) {
+  if (cg == 2) return launch_gemm_cg<AMAJ, BMAJ, EPI, 2>(a0, a1, b0, b1, ga, units, st);
+  return launch_gemm_cg<AMAJ, BMAJ, EPI, 1>(a0, a1, b0, b1, ga, units, st);
 }
 
 int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
@@ -544,29 +678,40 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
     CLIPDLM_CUDA_OK(cudaGetDevice(&dev));
     CLIPDLM_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // CTA pairs (256 x 256 tiles, tcgen05.mma.cta_group::2) unless the problem has a single 128-row tile or the debug hook says no
+  const int cg = (g->M > BM && !(g_dbg_flags & 8u) && g_num_sms >= 2) ? 2 : 1;
+  const int units_max = g_num_sms / cg;
   CUtensorMap a0, a1, b0, b1;
   int rc;
   if ((rc = operand_map(&a0, g->a_hi, g->a_major, g->M, g->K, g->lda, BM, g->gather_len, g->gather_stride))) return rc;
-  if ((rc = operand_map(&b0, g->b_hi, g->b_major, g->N, g->K, g->ldb, BN, 0, 0))) return rc;
+  if ((rc = operand_map(&b0, g->b_hi, g->b_major, g->N, g->K, g->ldb, BN / cg, 0, 0))) return rc;
   a1 = a0; b1 = b0;
   if (g->a_lo && (rc = operand_map(&a1, g->a_lo, g->a_major, g->M, g->K, g->lda, BM, g->gather_len, g->gather_stride))) return rc;
-  if (g->b_lo && (rc = operand_map(&b1, g->b_lo, g->b_major, g->N, g->K, g->ldb, BN, 0, 0))) return rc;
+  if (g->b_lo && (rc = operand_map(&b1, g->b_lo, g->b_major, g->N, g->K, g->ldb, BN / cg, 0, 0))) return rc;
 
   GemmArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.M = g->M; ga.N = g->N; ga.K = g->K;
-  ga.num_m_tiles = (g->M + BM - 1) / BM;
+  ga.num_m_tiles = (g->M + BM * cg - 1) / (BM * cg);
   ga.num_n_tiles = (g->N + BN - 1) / BN;
   ga.kb_total = (g->K + BK - 1) / BK;
   ga.k_splits = 1;
   if (g->epilogue == CLIPDLM_EPI_WGRAD) {
-    int tiles = ga.num_m_tiles * ga.num_n_tiles;
+    const int tiles = ga.num_m_tiles * ga.num_n_tiles;
     int ks = g->k_splits;
     if (ks <= 0) {
-      ks = (2 * g_num_sms + tiles - 1) / tiles;
-      int max_ks = ga.kb_total / 16;
-      if (ks > max_ks) ks = max_ks;
-      if (ks < 1) ks = 1;
+      // split-K factor minimising the makespan: waves x (k-blocks per split + the cost of draining one accumulator tile with
+      // fp32 red.add, ~12 k-block times), k-blocks per split kept >= 8
+      const int max_ks = ga.kb_total / 8 > 0 ? ga.kb_total / 8 : 1;
+      long long best = -1;
+      ks = 1;
+      for (int c = 1; c <= max_ks && c <= 4096; ++c) {
+        const int per = (ga.kb_total + c - 1) / c;
+        const int eff = (ga.kb_total + per - 1) / per;
+        const long long waves = ((long long)tiles * eff + units_max - 1) / units_max;
+        const long long cost = waves * (per + 12);
+        if (best < 0 || cost < best) { best = cost; ks = eff; }
+      }
     }
     if (ks > ga.kb_total) ks = ga.kb_total;
     ga.kb_per_split = (ga.kb_total + ks - 1) / ks;
@@ -605,30 +750,31 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   ga.part_max = g->part_max; ga.part_sum = g->part_sum; ga.part_arg = g->part_arg; ga.tgt_logit = g->tgt_logit;
   ga.targets = g->targets; ga.tgt_period = g->tgt_period > 0 ? g->tgt_period : 1;
   ga.lse = g->lse; ga.grad_scale = g->grad_scale;
+  ga.dbg = g_dbg_flags;
 
   const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  const int grid = total < units_max ? total : units_max;   // work units: CTAs (cg = 1) or CTA pairs (cg = 2)
 
   switch (g->epilogue) {
     case CLIPDLM_EPI_STORE:
       CLIPDLM_CHECK(g->N % 32 == 0, "STORE epilogue needs N %% 32 == 0 (N = %d)", g->N);
       CLIPDLM_CHECK(g->out_hi || g->out_f32 || g->out2_hi, "STORE epilogue without output");
       CLIPDLM_CHECK(g->a_major == 0, "STORE epilogue expects K-major A");
-      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
-      return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(a0, a1, b0, b1, ga, grid, st);
+      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_WGRAD:
       CLIPDLM_CHECK(g->a_major == 1 && g->b_major == 1, "WGRAD epilogue expects MN-major A and B");
       CLIPDLM_CHECK(g->N % 32 == 0 && g->acc_f32, "WGRAD needs N %% 32 == 0 and an fp32 accumulator");
-      return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(cg, a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_LSE:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE epilogue expects K-major operands");
-      CLIPDLM_CHECK(g->part_max && g->part_sum && g->part_arg && (!g->targets || g->tgt_logit), "LSE epilogue buffers missing");
-      return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(a0, a1, b0, b1, ga, grid, st);
+      CLIPDLM_CHECK(g->part_max && g->part_sum && (!g->targets || g->tgt_logit), "LSE epilogue buffers missing");
+      return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(cg, a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
       CLIPDLM_CHECK(g->out_hi && g->lse && g->targets, "SMGRAD epilogue buffers missing");
       CLIPDLM_CHECK(g->ldo >= (long long)ga.num_n_tiles * BN, "SMGRAD output pitch %lld < %d", (long long)g->ldo, ga.num_n_tiles * BN);
-      return launch_gemm<0, 0, CLIPDLM_EPI_SMGRAD>(a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<0, 0, CLIPDLM_EPI_SMGRAD>(cg, a0, a1, b0, b1, ga, grid, st);
     default:
       CLIPDLM_CHECK(false, "unknown epilogue %d", g->epilogue);
   }
@@ -645,5 +791,6 @@ int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, 
 }
 
 void gemm_debug_mn_desc(uint32_t lbo, uint32_t sbo) { g_dbg_mn_lbo = lbo; g_dbg_mn_sbo = sbo; }
+void gemm_debug_flags(uint32_t flags) { g_dbg_flags = flags; }
 
 }  // namespace clipdlm

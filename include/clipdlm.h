@@ -60,7 +60,7 @@ typedef struct clipdlm_gemm {
   /* WGRAD */
   float* acc_f32;                 /* [M, ldo] fp32, accumulated in place */
   /* LSE / SMGRAD */
-  float* part_max; float* part_sum; int32_t* part_arg; /* [2 * ceil(N/256)][M]: slot 2 * tile + half */
+  float* part_max; float* part_sum; int32_t* part_arg; /* [2 * ceil(N/256)][M]: slot 2 * tile + half; part_arg NULL = no arg-max tracking */
   float* tgt_logit;               /* [M] */
   const int32_t* targets; int32_t tgt_period; /* target of row m = targets[m % tgt_period] */
   const float* lse;               /* [M] (SMGRAD) */
@@ -70,6 +70,9 @@ typedef struct clipdlm_gemm {
 int clipdlm_gemm(const clipdlm_gemm_t* g, clipdlm_stream stream);
 /* Debug hook for bring-up: override the MN-major smem descriptor strides (bytes); 0,0 restores defaults. */
 void clipdlm_gemm_debug_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes);
+/* Debug hook for performance triage (tools/gemm_perf.py): bit 0 = drop the epilogue's global stores, bit 1 = drop its auxiliary
+ * operand loads (residual / gelu' input), bit 2 = drain TMEM only (no epilogue math), bit 3 = force single-CTA tiles (cta_group::1), bit 4 = issue no MMAs, bit 5 = issue no TMA loads. 0 restores normal operation. */
+void clipdlm_gemm_debug_flags(uint32_t flags);
 
 /* Reduce LSE partials: lse[m], argmax[m] (may be NULL), and adds sum_m(lse[m] - tgt_logit[m]) * scale to *loss_acc (double).
  * Replaces softmax -> gather -> log -> sum -> mean (CLIP-DDPM.py:436-437) and softmax/argmax (CLIP-DDPM.py:620). */
