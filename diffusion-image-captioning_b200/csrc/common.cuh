@@ -263,6 +263,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous bytes, multiple of 16, both addresses 16-byte aligned), completing on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 8 consecutive bf16 (pair) elements from shared memory as floats
+__device__ __forceinline__ void lds8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float (&v)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi);
+  float2 a = unpack_bf16x2(h.x), b = unpack_bf16x2(h.y), c = unpack_bf16x2(h.z), d = unpack_bf16x2(h.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  if (lo != nullptr) {
+    const uint4 l = *reinterpret_cast<const uint4*>(lo);
+    a = unpack_bf16x2(l.x); b = unpack_bf16x2(l.y); c = unpack_bf16x2(l.z); d = unpack_bf16x2(l.w);
+    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+  }
+}
 // CTA-pair variants: the data lands in THIS CTA's shared memory, the transaction bytes are signalled on the mbarrier at
 // shared::cluster address `bar_cluster` (the leader CTA's barrier, which the MMA-issuing thread waits on).
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {

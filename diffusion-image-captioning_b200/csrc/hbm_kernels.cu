@@ -253,24 +253,69 @@ struct LnBwdArgs {
   float* dbias;          // optional: += column sums of (dz_drop if set else dz)   -> bias grad of the producing Linear
 };
 
+// Rows are streamed through a per-warp ring of shared-memory stages filled by 1-D bulk copies (cp.async.bulk, one elected lane,
+// completion on an mbarrier): the 72 column-partial accumulators per lane leave room for only 12 warps per SM, far too few to
+// cover HBM latency with register loads (measured 2.1 TB/s); with LNB_STAGES rows in flight per warp the kernel keeps
+// > 100 KB per SM outstanding at zero register cost.
+constexpr int LNB_STAGES = 3;
 template <int NV>
 __global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a) {
-  extern __shared__ float red[];  // [4 warps][D] reused for dw, db, dbias
+  extern __shared__ __align__(16) uint8_t lnb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
+  const bool pair = a.z.lo != nullptr;
+  const int D = a.D;
+  const int narr = pair ? 4 : 2;                       // z.hi, dy.hi (, z.lo, dy.lo)
+  const uint32_t row_bytes = (uint32_t)D * 2;
+  float* red = reinterpret_cast<float*>(lnb_smem);      // [nwarps][D] reused for dw, db, dbias
+  uint8_t* ring = lnb_smem + (size_t)nwarps * D * sizeof(float) + (size_t)warp * LNB_STAGES * narr * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnb_smem + (size_t)nwarps * D * sizeof(float) + (size_t)nwarps * LNB_STAGES * narr * row_bytes) +
+                   warp * LNB_STAGES;
+  const long long row0 = (long long)blockIdx.x * nwarps + warp, row_step = (long long)gridDim.x * nwarps;
+  if (lane == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto issue = [&](int s, long long row) {   // lane 0 only
+    uint8_t* dst = ring + (size_t)s * narr * row_bytes;
+    mbar_arrive_expect_tx(&bars[s], narr * row_bytes);
+    bulk_load_1d(dst, a.z.hi + (size_t)row * D, row_bytes, &bars[s]);
+    bulk_load_1d(dst + row_bytes, a.dy.hi + (size_t)row * D, row_bytes, &bars[s]);
+    if (pair) {
+      bulk_load_1d(dst + 2 * row_bytes, a.z.lo + (size_t)row * D, row_bytes, &bars[s]);
+      bulk_load_1d(dst + 3 * row_bytes, a.dy.lo + (size_t)row * D, row_bytes, &bars[s]);
+    }
+  };
+  if (lane == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s)
+      if (row0 + s * row_step < a.rows) issue(s, row0 + s * row_step);
+  }
   float pdw[NV][8], pdb[NV][8], pbias[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { pdw[v][i] = 0.f; pdb[v][i] = 0.f; pbias[v][i] = 0.f; }
-  for (long long row = (long long)blockIdx.x * nwarps + warp; row < a.rows; row += (long long)gridDim.x * nwarps) {
+  int stage = 0; uint32_t phase = 0;
+  for (long long row = row0; row < a.rows; row += row_step) {
     float x[NV][8], g[NV][8];
+    mbar_wait(&bars[stage], phase);
+    {
+      const __nv_bfloat16* sz = reinterpret_cast<const __nv_bfloat16*>(ring + (size_t)stage * narr * row_bytes);
+      const __nv_bfloat16* sdy = sz + D;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const size_t off = (size_t)row * a.D + (v * 32 + lane) * 8;
-      load8(a.z, off, x[v]);
-      load8(a.dy, off, g[v]);
-      if (a.drop_out.thresh16 != 0) apply_drop8(a.drop_out, (unsigned long long)off, g[v]);
+      for (int v = 0; v < NV; ++v) {
+        const int c = (v * 32 + lane) * 8;
+        lds8(sz + c, pair ? sz + 2 * D + c : nullptr, x[v]);
+        lds8(sdy + c, pair ? sdy + 2 * D + c : nullptr, g[v]);
+      }
+    }
+    __syncwarp();   // every lane has consumed the stage: refill it with the row LNB_STAGES ahead
+    if (lane == 0 && row + LNB_STAGES * row_step < a.rows) issue(stage, row + LNB_STAGES * row_step);
+    if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
+    if (a.drop_out.thresh16 != 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) apply_drop8(a.drop_out, (unsigned long long)row * D + (v * 32 + lane) * 8, g[v]);
     }
     float mean, rstd;
     row_stats<NV>(x, a.D, a.eps, mean, rstd);
@@ -441,40 +486,62 @@ __global__ void __launch_bounds__(256) embed_loss_kernel(CBfPtr x_out, const flo
 // ------------------------------------------------------------------------------------------------------------------
 // small linear (CLIP projections), fp32
 // ------------------------------------------------------------------------------------------------------------------
-// one warp per output feature n, 8 captions per block.y slab: W row read once per 8 captions
-__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, int B, int K, int N, float* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int b0 = blockIdx.y * 8;
-  if (n >= N) return;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k = lane; k < K; k += 32) {
-    const float wk = __ldg(w + (size_t)n * K + k);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (b0 + j < B) acc[j] += wk * __ldg(x + (size_t)(b0 + j) * K + k);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float s = warp_sum(acc[j]);
-    if (lane == 0 && b0 + j < B) y[(size_t)(b0 + j) * N + n] = s + (bias != nullptr ? bias[n] : 0.f);
-  }
-}
-// dW[n, k] += sum_b dy[b, n] x[b, k]; db[n] += sum_b dy[b, n].  grid (ceil(K/256), N)
-__global__ void __launch_bounds__(256) small_linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int K, int N,
-                                                               float* dw, float* db) {
-  const int n = blockIdx.y;
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  float acc = 0.f, accb = 0.f;
-  if (k < K) {
-    for (int b = 0; b < B; ++b) {
-      const float g = __ldg(dy + (size_t)b * N + n);
-      acc += g * __ldg(x + (size_t)b * K + k);
-      accb += g;
+// Shared-memory tiled fp32 SIMT GEMM, 64 x 64 output tile per block of 256 threads (4 x 4 per thread), k-step 16.
+//   KCONTIG = true : C[m, n] = sum_k A[m, k] Bm[n, k] + bias[n]          (A [M][K], Bm [N][K]; forward  y = x W^T + b)
+//   KCONTIG = false: C[m, n] += sum_k A[k, m] Bm[k, n]; csum[m] += sum_k A[k, m]   (A [K][M], Bm [K][N]; backward dW += dy^T x, db += colsum dy)
+// fp32 on purpose: the CLIP projections feed the parity-mode (fp32-class) path and are 0.4 GFLOP per call.
+template <bool KCONTIG>
+__global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ bias,
+                                                         int M, int N, int K, float* __restrict__ C, float* __restrict__ csum) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][68];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  float asum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    if (KCONTIG) {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (m0 + r < M && k0 + kq < K) a = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * K + k0 + kq));
+      if (n0 + r < N && k0 + kq < K) b = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(n0 + r) * K + k0 + kq));
+      As[kq][r] = a.x; As[kq + 1][r] = a.y; As[kq + 2][r] = a.z; As[kq + 3][r] = a.w;
+      Bs[kq][r] = b.x; Bs[kq + 1][r] = b.y; Bs[kq + 2][r] = b.z; Bs[kq + 3][r] = b.w;
+    } else {
+      const int kk = tid >> 4, q = (tid & 15) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (k0 + kk < K && m0 + q < M) a = __ldg(reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * M + m0 + q));
+      if (k0 + kk < K && n0 + q < N) b = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kk) * N + n0 + q));
+      *reinterpret_cast<float4*>(&As[kk][q]) = a;
+      *reinterpret_cast<float4*>(&Bs[kk][q]) = b;
     }
-    dw[(size_t)n * K + k] += acc;
-    if (k == 0 && db != nullptr) db[n] += accb;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!KCONTIG) asum[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      if (KCONTIG) C[(size_t)m * N + n] = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
+      else C[(size_t)m * N + n] += acc[i][j];
+    }
+    if (!KCONTIG && csum != nullptr && blockIdx.y == 0 && tx == 0) csum[m] += asum[i];
   }
 }
 
@@ -668,7 +735,19 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
   a.dbias = dbias;
   long long want = (rows + 3) / 4;
   int grid = (int)(want < 3LL * num_sms() ? want : 3LL * num_sms());  // 3 resident CTAs of 4 warps per SM (register-limited)
-  const size_t smem = (size_t)4 * D * sizeof(float);
+  const int narr = a.z.lo != nullptr ? 4 : 2;
+  CLIPDLM_CHECK((a.z.lo != nullptr) == (a.dy.lo != nullptr), "layernorm_bwd: z and dy must use the same storage mode");
+  const size_t smem = (size_t)4 * D * sizeof(float) + (size_t)4 * LNB_STAGES * narr * D * 2 + 4 * LNB_STAGES * sizeof(uint64_t);
+  {
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      smem_set = 120 * 1024;
+    }
+  }
   DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 128, smem, st>>>(a));
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
@@ -704,16 +783,16 @@ int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* 
 }
 
 int small_linear_fwd_dispatch(const float* x, const float* w, const float* b, int B, int K, int N, float* y, cudaStream_t st) {
-  CLIPDLM_CHECK(x && w && y && B > 0, "small_linear_fwd: bad arguments");
-  dim3 grid((N + 7) / 8, (B + 7) / 8);
-  small_linear_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, B, K, N, y);
+  CLIPDLM_CHECK(x && w && y && B > 0 && K % 4 == 0, "small_linear_fwd: bad arguments (K must be a multiple of 4)");
+  dim3 grid((B + 63) / 64, (N + 63) / 64);
+  small_gemm_kernel<true><<<grid, 256, 0, st>>>(x, w, b, B, N, K, y, nullptr);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int small_linear_bwd_dispatch(const float* x, const float* dy, int B, int K, int N, float* dw, float* db, cudaStream_t st) {
-  CLIPDLM_CHECK(x && dy && dw && B > 0, "small_linear_bwd: bad arguments");
-  dim3 grid((K + 255) / 256, N);
-  small_linear_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, B, K, N, dw, db);
+  CLIPDLM_CHECK(x && dy && dw && B > 0 && K % 4 == 0 && N % 4 == 0, "small_linear_bwd: bad arguments (K, N must be multiples of 4)");
+  dim3 grid((N + 63) / 64, (K + 63) / 64);   // dW [N, K]: rows = output features, reduction over the B captions
+  small_gemm_kernel<false><<<grid, 256, 0, st>>>(dy, x, nullptr, N, K, B, dw, db);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }
