@@ -8,6 +8,7 @@
 // from the counter-based RNG, so no [R, H, L, L] tensor ever exists in memory.
 #include "common.cuh"
 #include "../../include/clipdlm.h"
+#include <cudaTypedefs.h>
 
 namespace clipdlm {
 
@@ -232,86 +233,73 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(CBfPtr qkv, const uint32_
 
 
 // ==================================================================================================================
-// Tensor-core path for L <= 32, plain bf16 storage: mma.sync.m16n8k16 (bf16 in, fp32 accumulate) on a padded 32 x 32
-// score tile per (row, head).  The per-(row, head) problems are far too small for a 128-row tcgen05 tile (packing 7
-// sequences per tile wastes 7x on the block-diagonal), so the warp-level MMA is the right tensor-core instruction here:
-// ~64 (fwd) / ~160 (bwd) MMAs per warp instead of ~5 k / ~14 k FMA-issue slots in the SIMT kernels above.
+// Tensor-core path for L <= 32, plain bf16 storage.
+//
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) on a padded 32 x 32 score tile per (row, head): the per-(row, head) problems are
+// far too small for a 128-row tcgen05 tile, so the warp-level MMA is the right tensor-core instruction here.  What bounds this
+// kernel is HBM latency, not math, hence the structure: ONE persistent CTA per SM = 1 TMA producer warp + W consumer warps
+// around a ring of S shared-memory stages (S > W).  The producer streams the q / k / v (/ dO) head slices of task after task
+// into the ring with cp.async.bulk.tensor (128-byte swizzle, one 18 x 128 B box per tensor, completion on an mbarrier), always
+// S - W tasks ahead of the math; a consumer warp waits for its stage, computes straight out of it with ldmatrix on the swizzled
+// rows (conflict-free, no padding), stages its result in tile space that is already dead, writes it out with coalesced 16-byte
+// stores and hands the stage back.  P^T / dS^T for the backward products come from movmatrix (register transposes): no score
+// tile ever touches shared memory.  The first version (one warp per task, per-lane LDG/STS staging, 4-8 warps per SM because
+// of the staging tiles) sat at 2 TB/s with the load latency fully exposed.
 // ==================================================================================================================
-constexpr int QP = 72;  // bf16 row pitch of the q / k / v / dO tiles (144 B: ldmatrix rows hit distinct 16-byte bank groups)
-constexpr int PP = 40;  // bf16 row pitch of the P / dS tiles (80 B)
-constexpr int TILE_E = 32 * QP;
 constexpr float LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ void ldsm_x4(const __nv_bfloat16* p, uint32_t (&r)[4]) {
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, unsigned long long inner, unsigned long long outer, unsigned long long pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void ldsm_x4_t(const __nv_bfloat16* p, uint32_t (&r)[4]) {
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {   // 8 x 8 b16 block held in the fragment layout -> its transpose
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// ldmatrix lane addresses (l = lane, mi = l >> 3 selects the 8x8 matrix the lane supplies a row address for)
-//  A  (16 x 16 at (m0, k0)) from row-major X[m][k]            : X[m0 + (l & 7) + (mi & 1) * 8][k0 + (mi >> 1) * 8]
-//  A^T(16 x 16 at (m0, k0)) from X[k][m] (use .trans)          : X[k0 + (l & 7) + (mi >> 1) * 8][m0 + (mi & 1) * 8]
-//  B  (k16 x two n8 tiles at (k0, n0)) from Bt[n][k]           : Bt[n0 + (l & 7) + (mi >> 1) * 8][k0 + (mi & 1) * 8]   -> {b0, b1 | b0', b1'}
-//  B  (k16 x two n8 tiles at (k0, n0)) from B[k][n] (.trans)   : B[k0 + (l & 7) + (mi & 1) * 8][n0 + (mi >> 1) * 8]    -> {b0, b1 | b0', b1'}
-__device__ __forceinline__ const __nv_bfloat16* addr_a(const __nv_bfloat16* x, int pitch, int m0, int k0, int l) {
-  const int mi = l >> 3;
-  return x + (m0 + (l & 7) + (mi & 1) * 8) * pitch + k0 + (mi >> 1) * 8;
+// Tile = rows of 128 B (one head slice row), 16-byte chunk c of row i stored at chunk c ^ (i & 7) (what TMA SWIZZLE_128B writes
+// into a 1024-byte aligned tile).
+__device__ __forceinline__ uint32_t sw_addr(uint32_t tile, int row, int chunk) { return tile + row * 128 + ((chunk ^ (row & 7)) << 4); }
+// ldmatrix lane addresses (l = lane; matrix index mi = l >> 3 selects which 8 x 8 block the lane addresses a row of)
+//  A  (16 x 16 at (m0, k0)) from row-major X[m][k]           : row m0 + (l & 7) + (mi & 1) * 8, chunk k0 / 8 + (mi >> 1)
+//  B  (k16 x two n8 tiles at (k0, n0)) from Bt[n][k]          : row n0 + (l & 7) + (mi >> 1) * 8, chunk k0 / 8 + (mi & 1)
+//  B  (k16 x two n8 tiles at (k0, n0)) from B[k][n] (.trans)  : row k0 + (l & 7) + (mi & 1) * 8, chunk n0 / 8 + (mi >> 1)
+__device__ __forceinline__ uint32_t addr_a(uint32_t tile, int m0, int k0, int l) {
+  return sw_addr(tile, m0 + (l & 7) + ((l >> 3) & 1) * 8, (k0 >> 3) + (l >> 4));
 }
-__device__ __forceinline__ const __nv_bfloat16* addr_at(const __nv_bfloat16* x, int pitch, int m0, int k0, int l) {
-  const int mi = l >> 3;
-  return x + (k0 + (l & 7) + (mi >> 1) * 8) * pitch + m0 + (mi & 1) * 8;
+__device__ __forceinline__ uint32_t addr_bt(uint32_t tile, int k0, int n0, int l) {
+  return sw_addr(tile, n0 + (l & 7) + (l >> 4) * 8, (k0 >> 3) + ((l >> 3) & 1));
 }
-__device__ __forceinline__ const __nv_bfloat16* addr_bt(const __nv_bfloat16* bt, int pitch, int k0, int n0, int l) {
-  const int mi = l >> 3;
-  return bt + (n0 + (l & 7) + (mi >> 1) * 8) * pitch + k0 + (mi & 1) * 8;
-}
-__device__ __forceinline__ const __nv_bfloat16* addr_b(const __nv_bfloat16* b, int pitch, int k0, int n0, int l) {
-  const int mi = l >> 3;
-  return b + (k0 + (l & 7) + (mi & 1) * 8) * pitch + n0 + (mi >> 1) * 8;
+__device__ __forceinline__ uint32_t addr_b(uint32_t tile, int k0, int n0, int l) {
+  return sw_addr(tile, k0 + (l & 7) + ((l >> 3) & 1) * 8, (n0 >> 3) + (l >> 4));
 }
 
-// stage rows [0, L) of one head slice (64 bf16 per row) into a [32][QP] tile, zero-filling rows >= L
-__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, size_t row_elems, int L, __nv_bfloat16* tile, int lane) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = it * 32 + lane;
-    const int i = idx >> 3, part = idx & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (i < L) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)i * row_elems + part * 8));
-    *reinterpret_cast<uint4*>(tile + i * QP + part * 8) = v;
-  }
-}
-__device__ __forceinline__ void unstage_tile(const __nv_bfloat16* tile, __nv_bfloat16* __restrict__ dst, size_t row_elems, int L, int lane) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = it * 32 + lane;
-    const int i = idx >> 3, part = idx & 7;
-    if (i < L) *reinterpret_cast<uint4*>(dst + (size_t)i * row_elems + part * 8) = *reinterpret_cast<const uint4*>(tile + i * QP + part * 8);
-  }
-}
-// C-fragment accumulators [2 m-tiles][8 n-tiles][4] (32 x 64 fp32) -> bf16 tile [32][QP]
-__device__ __forceinline__ void acc_to_tile(const float (&o)[2][8][4], __nv_bfloat16* tile, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      *reinterpret_cast<uint32_t*>(tile + (mt * 16 + g) * QP + nt * 8 + 2 * t) = pack_bf16x2(o[mt][nt][0], o[mt][nt][1]);
-      *reinterpret_cast<uint32_t*>(tile + (mt * 16 + g + 8) * QP + nt * 8 + 2 * t) = pack_bf16x2(o[mt][nt][2], o[mt][nt][3]);
-    }
+struct AttGeo {
+  int L, MT, NT, KB;      // sequence length; 16-row query tiles, 8-column key tiles, 16-key reduction blocks that hold real data
+  int tile_rows;          // rows a tile occupies in shared memory (24 or 32); rows [L, tile_rows) are never written by TMA
+  uint32_t tile_bytes;
+};
+__device__ __forceinline__ AttGeo att_geo(int L) {
+  AttGeo g;
+  g.L = L; g.MT = (L + 15) >> 4; g.NT = (L + 7) >> 3; g.KB = (L + 15) >> 4;
+  g.tile_rows = L <= 24 ? 24 : 32;
+  g.tile_bytes = (uint32_t)g.tile_rows * 128u;
+  return g;
 }
 
-// S = scale * Q K^T on the padded 32 x 32 tile, masked softmax in registers. Returns probabilities in p (C-fragment layout:
-// p[mt][nt][e] is row mt*16 + g + (e >> 1) * 8, column nt*8 + 2t + (e & 1)).
-__device__ __forceinline__ void scores_softmax(const __nv_bfloat16* q, const __nv_bfloat16* k, uint32_t keybits, int L, float scale,
-                                               int lane, float (&p)[2][4][4]) {
-  const int t = lane & 3;
+// acc (+)= X[m][:] . Y[n][:]^T over the 64-wide head dim: A = X tile (queries), B = Y tile (keys) - S = Q K^T and dP = dO V^T
+__device__ __forceinline__ void qk_product(uint32_t x, uint32_t y, const AttGeo& ge, int lane, float (&p)[2][4][4]) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -320,16 +308,26 @@ __device__ __forceinline__ void scores_softmax(const __nv_bfloat16* q, const __n
       for (int e = 0; e < 4; ++e) p[mt][nt][e] = 0.f;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a0[4], a1[4], b01[4], b23[4];
-    ldsm_x4(addr_a(q, QP, 0, ks * 16, lane), a0);
-    ldsm_x4(addr_a(q, QP, 16, ks * 16, lane), a1);
-    ldsm_x4(addr_bt(k, QP, ks * 16, 0, lane), b01);
-    ldsm_x4(addr_bt(k, QP, ks * 16, 16, lane), b23);
-    mma16816(p[0][0], a0, b01[0], b01[1]); mma16816(p[0][1], a0, b01[2], b01[3]);
-    mma16816(p[0][2], a0, b23[0], b23[1]); mma16816(p[0][3], a0, b23[2], b23[3]);
-    mma16816(p[1][0], a1, b01[0], b01[1]); mma16816(p[1][1], a1, b01[2], b01[3]);
-    mma16816(p[1][2], a1, b23[0], b23[1]); mma16816(p[1][3], a1, b23[2], b23[3]);
+    uint32_t a0[4], a1[4] = {0u, 0u, 0u, 0u}, b01[4], b23[4] = {0u, 0u, 0u, 0u};
+    ldsm_x4(addr_a(x, 0, ks * 16, lane), a0);
+    if (ge.MT > 1) ldsm_x4(addr_a(x, 16, ks * 16, lane), a1);
+    ldsm_x4(addr_bt(y, ks * 16, 0, lane), b01);
+    if (ge.NT > 2) ldsm_x4(addr_bt(y, ks * 16, 16, lane), b23);   // keys 24..31 of a 24-row tile alias the next tile: never used (NT <= 3)
+    mma16816(p[0][0], a0, b01[0], b01[1]);
+    if (ge.NT > 1) mma16816(p[0][1], a0, b01[2], b01[3]);
+    if (ge.NT > 2) mma16816(p[0][2], a0, b23[0], b23[1]);
+    if (ge.NT > 3) mma16816(p[0][3], a0, b23[2], b23[3]);
+    if (ge.MT > 1) {
+      mma16816(p[1][0], a1, b01[0], b01[1]);
+      if (ge.NT > 1) mma16816(p[1][1], a1, b01[2], b01[3]);
+      if (ge.NT > 2) mma16816(p[1][2], a1, b23[0], b23[1]);
+      if (ge.NT > 3) mma16816(p[1][3], a1, b23[2], b23[3]);
+    }
   }
+}
+// masked softmax of scale * S in registers (C-fragment layout: p[mt][nt][e] is row mt*16 + g + (e >> 1) * 8, column nt*8 + 2t + (e & 1))
+__device__ __forceinline__ void softmax_rows(float (&p)[2][4][4], uint32_t keybits, int L, float scale, int lane) {
+  const int t = lane & 3;
   const float sl = scale * LOG2E;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -348,12 +346,13 @@ __device__ __forceinline__ void scores_softmax(const __nv_bfloat16* q, const __n
         }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      if (mx == -INFINITY) mx = 0.f;   // garbage query rows (>= L) of a fully NaN/-inf tile: keep the arithmetic finite
       float sum = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          const float ev = exp2f(p[mt][nt][hh * 2 + cc] - mx);
+          const float ev = ex2_ftz(p[mt][nt][hh * 2 + cc] - mx);
           p[mt][nt][hh * 2 + cc] = ev;
           sum += ev;
         }
@@ -366,11 +365,12 @@ __device__ __forceinline__ void scores_softmax(const __nv_bfloat16* q, const __n
         for (int cc = 0; cc < 2; ++cc) p[mt][nt][hh * 2 + cc] *= inv;
     }
 }
-// keep-scale (0 or 1 / (1 - p)) of every element of the thread's C fragments
-__device__ __forceinline__ void dropout_scales(const DropoutCfg& d, unsigned long long rh, int lane, float (&ks)[2][4][4]) {
+// keep-scale (0 or 1 / (1 - p)) of every element of the thread's C fragments; row blocks of 8 beyond L draw nothing
+__device__ __forceinline__ void dropout_scales(const DropoutCfg& d, unsigned long long rh, int lane, int L, float (&ks)[2][4][4]) {
 #pragma unroll
   for (int ib = 0; ib < 4; ++ib) {  // ib = i / 8 = mt * 2 + hh
-    const uint4 rnd = attn_rand_block(d, rh, lane, ib * 4);
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+    if (ib * 8 < L) rnd = attn_rand_block(d, rh, lane, ib * 4);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -378,227 +378,266 @@ __device__ __forceinline__ void dropout_scales(const DropoutCfg& d, unsigned lon
         ks[ib >> 1][nt][(ib & 1) * 2 + cc] = attn_field16(rnd, nt * 2 + cc) >= d.thresh16 ? d.scale : 0.f;
   }
 }
-// C fragments of a 32 x 32 fp32 tile -> A fragments (bf16) for the k16 block kb (keys 16*kb .. 16*kb + 15) of m-tile mt
+// C fragments of a 32 x 32 fp32 tile -> A fragments (bf16) for the k16 block kb (columns 16*kb .. 16*kb + 15) of m-tile mt
 __device__ __forceinline__ void c_to_a(const float (&c)[2][4][4], int mt, int kb, uint32_t (&a)[4]) {
   a[0] = pack_bf16x2(c[mt][2 * kb][0], c[mt][2 * kb][1]);
   a[1] = pack_bf16x2(c[mt][2 * kb][2], c[mt][2 * kb][3]);
   a[2] = pack_bf16x2(c[mt][2 * kb + 1][0], c[mt][2 * kb + 1][1]);
   a[3] = pack_bf16x2(c[mt][2 * kb + 1][2], c[mt][2 * kb + 1][3]);
 }
-
-__global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint32_t* __restrict__ keymask, int R, int L,
-                                                           int D, int H, __nv_bfloat16* __restrict__ ctx, DropoutCfg drop, float scale) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long rh = (long long)blockIdx.x * 4 + warp;
-  if (rh >= (long long)R * H) return;
-  const int r = (int)(rh / H), h = (int)(rh % H);
-  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(smem_raw) + (size_t)warp * 3 * TILE_E;
-  __nv_bfloat16* k = q + TILE_E;
-  __nv_bfloat16* v = k + TILE_E;
-  const __nv_bfloat16* base = qkv + (size_t)r * L * 3 * D + h * DH;
-  stage_tile(base, 3 * (size_t)D, L, q, lane);
-  stage_tile(base + D, 3 * (size_t)D, L, k, lane);
-  stage_tile(base + 2 * D, 3 * (size_t)D, L, v, lane);
-  __syncwarp();
-  float p[2][4][4];
-  scores_softmax(q, k, keymask[r], L, scale, lane, p);
-  if (drop.thresh16 != 0) {
-    float ks[2][4][4];
-    dropout_scales(drop, (unsigned long long)rh, lane, ks);
+// acc[mt][0..7] (+)= A (given as C fragments of a [32 x 32] matrix, reduction over its columns) . B tile [k][d] (64 wide)
+__device__ __forceinline__ void av_product(const float (&c)[2][4][4], uint32_t btile, const AttGeo& ge, int lane, float (&o)[2][8][4]) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+  for (int kb = 0; kb < 2; ++kb) {
+    if (kb >= ge.KB) break;
+    const bool hi_ok = kb * 16 + 16 <= ge.tile_rows;   // rows 24..31 of a 24-row tile are not ours: feed zeros instead
+    uint32_t a0[4], a1[4];
+    c_to_a(c, 0, kb, a0);
+    c_to_a(c, 1, kb, a1);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) p[mt][nt][e] *= ks[mt][nt][e];
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_t(addr_b(btile, kb * 16, dp * 16, lane), b);
+      if (!hi_ok) { b[1] = 0u; b[3] = 0u; }
+      mma16816(o[0][2 * dp], a0, b[0], b[1]); mma16816(o[0][2 * dp + 1], a0, b[2], b[3]);
+      if (ge.MT > 1) { mma16816(o[1][2 * dp], a1, b[0], b[1]); mma16816(o[1][2 * dp + 1], a1, b[2], b[3]); }
+    }
   }
-  float o[2][8][4];
+}
+// acc[mj][0..7] (+)= X^T . B tile: xt[jb][ib] is the transposed 8 x 8 block (rows ib, columns jb) of X in fragment layout, the
+// reduction runs over X's rows (queries), the result rows are X's columns (keys)
+__device__ __forceinline__ void atv_product(const uint32_t (&xt)[4][4], uint32_t btile, const AttGeo& ge, int lane, float (&o)[2][8][4]) {
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    if (kb >= ge.KB) break;
+    const bool hi_ok = kb * 16 + 16 <= ge.tile_rows;
+    const uint32_t a0[4] = {xt[0][2 * kb], xt[1][2 * kb], xt[0][2 * kb + 1], xt[1][2 * kb + 1]};
+    const uint32_t a1[4] = {xt[2][2 * kb], xt[3][2 * kb], xt[2][2 * kb + 1], xt[3][2 * kb + 1]};
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_t(addr_b(btile, kb * 16, dp * 16, lane), b);
+      if (!hi_ok) { b[1] = 0u; b[3] = 0u; }
+      mma16816(o[0][2 * dp], a0, b[0], b[1]); mma16816(o[0][2 * dp + 1], a0, b[2], b[3]);
+      if (ge.MT > 1) { mma16816(o[1][2 * dp], a1, b[0], b[1]); mma16816(o[1][2 * dp + 1], a1, b[2], b[3]); }
+    }
+  }
+}
+__device__ __forceinline__ void zero_acc(float (&o)[2][8][4]) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
-#pragma unroll
-  for (int kb = 0; kb < 2; ++kb) {
-    uint32_t a0[4], a1[4];
-    c_to_a(p, 0, kb, a0);
-    c_to_a(p, 1, kb, a1);
-#pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
-      uint32_t b[4];
-      ldsm_x4_t(addr_b(v, QP, kb * 16, dp * 16, lane), b);
-      mma16816(o[0][2 * dp], a0, b[0], b[1]); mma16816(o[0][2 * dp + 1], a0, b[2], b[3]);
-      mma16816(o[1][2 * dp], a1, b[0], b[1]); mma16816(o[1][2 * dp + 1], a1, b[2], b[3]);
-    }
-  }
-  __syncwarp();  // all ldmatrix reads of q are long done; reuse its tile as the output staging buffer
-  acc_to_tile(o, q, lane);
-  __syncwarp();
-  unstage_tile(q, ctx + (size_t)r * L * D + h * DH, (size_t)D, L, lane);
 }
-
-__global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint32_t* __restrict__ keymask,
-                                                           const __nv_bfloat16* __restrict__ dctx, int R, int L, int D, int H,
-                                                           __nv_bfloat16* __restrict__ dqkv, DropoutCfg drop, float scale) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long rh = (long long)blockIdx.x * 4 + warp;
-  if (rh >= (long long)R * H) return;
-  const int r = (int)(rh / H), h = (int)(rh % H);
+// C-fragment accumulators (32 x 64 fp32) -> bf16 rows [0, L) of a swizzled tile
+__device__ __forceinline__ void acc_to_tile(const float (&o)[2][8][4], uint32_t tile, int L, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  constexpr int WARP_E = 4 * TILE_E + 2 * 32 * PP;
-  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(smem_raw) + (size_t)warp * WARP_E;
-  __nv_bfloat16* k = q + TILE_E;
-  __nv_bfloat16* v = k + TILE_E;
-  __nv_bfloat16* dO = v + TILE_E;
-  __nv_bfloat16* pd = dO + TILE_E;   // dropped probabilities  [32][PP]
-  __nv_bfloat16* ds = pd + 32 * PP;  // d(scores)              [32][PP]
-  const __nv_bfloat16* base = qkv + (size_t)r * L * 3 * D + h * DH;
-  stage_tile(base, 3 * (size_t)D, L, q, lane);
-  stage_tile(base + D, 3 * (size_t)D, L, k, lane);
-  stage_tile(base + 2 * D, 3 * (size_t)D, L, v, lane);
-  stage_tile(dctx + (size_t)r * L * D + h * DH, (size_t)D, L, dO, lane);
-  __syncwarp();
-  float p[2][4][4];
-  scores_softmax(q, k, keymask[r], L, scale, lane, p);
-  // dP = dO V^T
-  float dp[2][4][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) dp[mt][nt][e] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a0[4], a1[4], b01[4], b23[4];
-    ldsm_x4(addr_a(dO, QP, 0, ks * 16, lane), a0);
-    ldsm_x4(addr_a(dO, QP, 16, ks * 16, lane), a1);
-    ldsm_x4(addr_bt(v, QP, ks * 16, 0, lane), b01);
-    ldsm_x4(addr_bt(v, QP, ks * 16, 16, lane), b23);
-    mma16816(dp[0][0], a0, b01[0], b01[1]); mma16816(dp[0][1], a0, b01[2], b01[3]);
-    mma16816(dp[0][2], a0, b23[0], b23[1]); mma16816(dp[0][3], a0, b23[2], b23[3]);
-    mma16816(dp[1][0], a1, b01[0], b01[1]); mma16816(dp[1][1], a1, b01[2], b01[3]);
-    mma16816(dp[1][2], a1, b23[0], b23[1]); mma16816(dp[1][3], a1, b23[2], b23[3]);
-  }
-  if (drop.thresh16 != 0) {
-    float ksc[2][4][4];
-    dropout_scales(drop, (unsigned long long)rh, lane, ksc);
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dp[mt][nt][e] *= ksc[mt][nt][e];  // gradient through the dropout
-    // pd = p * keep_scale is what multiplied V in the forward
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<uint32_t*>(pd + (mt * 16 + g) * PP + nt * 8 + 2 * t) = pack_bf16x2(p[mt][nt][0] * ksc[mt][nt][0], p[mt][nt][1] * ksc[mt][nt][1]);
-        *reinterpret_cast<uint32_t*>(pd + (mt * 16 + g + 8) * PP + nt * 8 + 2 * t) = pack_bf16x2(p[mt][nt][2] * ksc[mt][nt][2], p[mt][nt][3] * ksc[mt][nt][3]);
-      }
-  } else {
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<uint32_t*>(pd + (mt * 16 + g) * PP + nt * 8 + 2 * t) = pack_bf16x2(p[mt][nt][0], p[mt][nt][1]);
-        *reinterpret_cast<uint32_t*>(pd + (mt * 16 + g + 8) * PP + nt * 8 + 2 * t) = pack_bf16x2(p[mt][nt][2], p[mt][nt][3]);
-      }
-  }
-  // dS = P o (dP - rowsum(dP o P)) * scale
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      float dot = 0.f;
+      const int row = mt * 16 + g + hh * 8;
+      if (row < L) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) dot += dp[mt][nt][hh * 2 + cc] * p[mt][nt][hh * 2 + cc];
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g + hh * 8) * PP + nt * 8 + 2 * t) =
-            pack_bf16x2(p[mt][nt][hh * 2] * (dp[mt][nt][hh * 2] - dot) * scale, p[mt][nt][hh * 2 + 1] * (dp[mt][nt][hh * 2 + 1] - dot) * scale);
+        for (int nt = 0; nt < 8; ++nt)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(tile, row, nt) + 4 * t), "r"(pack_bf16x2(o[mt][nt][hh * 2], o[mt][nt][hh * 2 + 1])) : "memory");
+      }
     }
-  __syncwarp();
-  float acc[2][8][4];
-  // ---- dV[j][d] = sum_i pd[i][j] dO[i][d]  -> staged into the v tile (v is dead after dP)
+}
+// rows [0, L) of a swizzled tile -> global rows of 64 bf16 (row pitch row_elems), coalesced 16-byte stores
+__device__ __forceinline__ void unstage_tile(uint32_t tile, __nv_bfloat16* __restrict__ dst, size_t row_elems, int L, int lane) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-#pragma unroll
-  for (int kb = 0; kb < 2; ++kb) {  // reduction over queries i in blocks of 16
-    uint32_t a0[4], a1[4];
-    ldsm_x4_t(addr_at(pd, PP, 0, kb * 16, lane), a0);
-    ldsm_x4_t(addr_at(pd, PP, 16, kb * 16, lane), a1);
-#pragma unroll
-    for (int dpi = 0; dpi < 4; ++dpi) {
-      uint32_t b[4];
-      ldsm_x4_t(addr_b(dO, QP, kb * 16, dpi * 16, lane), b);
-      mma16816(acc[0][2 * dpi], a0, b[0], b[1]); mma16816(acc[0][2 * dpi + 1], a0, b[2], b[3]);
-      mma16816(acc[1][2 * dpi], a1, b[0], b[1]); mma16816(acc[1][2 * dpi + 1], a1, b[2], b[3]);
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane;
+    const int i = idx >> 3, part = idx & 7;
+    if (i < L) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw_addr(tile, i, part)));
+      *reinterpret_cast<uint4*>(dst + (size_t)i * row_elems + part * 8) = v;
     }
   }
-  __syncwarp();
-  acc_to_tile(acc, v, lane);
-  // ---- dK[j][d] = sum_i dS[i][j] Q[i][d]  -> staged into the dO tile (dead after dV; the syncwarp below orders the reads)
+}
+
+struct AttArgs {
+  const uint32_t* keymask;
+  __nv_bfloat16* out;      // ctx [T, D] (forward) or dqkv [T, 3D] (backward)
+  int R, L, D, H, stages, consumers;
+  DropoutCfg drop;
+  float scale;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(BWD ? 384 : 512, 1) attn_ring_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                                                           const AttArgs a) {
+  constexpr int NTILES = BWD ? 4 : 3;
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+  const AttGeo ge = att_geo(a.L);
+  const uint32_t stage_bytes = NTILES * ge.tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * stage_bytes + 1024);   // 1 KB pad: aliased ldmatrix rows of the last tile
+  uint64_t* empty_bar = full_bar + a.stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tasks = (long long)a.R * a.H;
+  const long long my_tasks = tasks > blockIdx.x ? (tasks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // zero the ring once: rows [L, tile_rows) are never written by TMA and must stay finite (they meet exact zeros in the MMAs)
+  for (uint32_t off = threadIdx.x * 16; off < (uint32_t)a.stages * stage_bytes + 1024; off += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(ring + off) = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_qkv);
+    if (BWD) tma_prefetch_desc(&tm_do);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA) writes
+  __syncthreads();
+
+  if (warp == a.consumers) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (long long n = 0; n < my_tasks; ++n) {
+        const long long task = blockIdx.x + n * gridDim.x;
+        const int r = (int)(task / a.H), h = (int)(task % a.H);
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = ring + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], NTILES * a.L * 128);
+        tma_load_2d(st, &tm_qkv, &full_bar[s], h * DH, r * a.L);                              // q
+        tma_load_2d(st + ge.tile_bytes, &tm_qkv, &full_bar[s], a.D + h * DH, r * a.L);        // k
+        tma_load_2d(st + 2 * ge.tile_bytes, &tm_qkv, &full_bar[s], 2 * a.D + h * DH, r * a.L);  // v
+        if (BWD) tma_load_2d(st + 3 * ge.tile_bytes, &tm_do, &full_bar[s], h * DH, r * a.L);  // dO
+        if (++s == a.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp < a.consumers) {
+    // ===================================== consumers =====================================
+    const int g = lane >> 2;
+    for (long long n = warp; n < my_tasks; n += a.consumers) {
+      const long long task = blockIdx.x + n * gridDim.x;
+      const int r = (int)(task / a.H), h = (int)(task % a.H);
+      const int s = (int)(n % a.stages);
+      const uint32_t ph = (uint32_t)((n / a.stages) & 1);
+      const uint32_t keybits = a.keymask[r];
+      mbar_wait(&full_bar[s], ph);
+      const uint32_t q = smem_u32(ring + (size_t)s * stage_bytes), k = q + ge.tile_bytes, v = k + ge.tile_bytes, dO = v + ge.tile_bytes;
+      float p[2][4][4];
+      qk_product(q, k, ge, lane, p);
+      softmax_rows(p, keybits, a.L, a.scale, lane);
+      if (!BWD) {
+        if (a.drop.thresh16 != 0) {
+          float ks[2][4][4];
+          dropout_scales(a.drop, (unsigned long long)task, lane, a.L, ks);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+              for (int e = 0; e < 4; ++e) p[mt][nt][e] *= ks[mt][nt][e];
+        }
+        float o[2][8][4];
+        zero_acc(o);
+        av_product(p, v, ge, lane, o);
+        __syncwarp();                      // every lane's ldmatrix reads of q are done: reuse its tile as the output staging buffer
+        acc_to_tile(o, q, a.L, lane);
+        __syncwarp();
+        unstage_tile(q, a.out + (size_t)r * a.L * a.D + h * DH, (size_t)a.D, a.L, lane);
+      } else {
+        float dp[2][4][4];
+        qk_product(dO, v, ge, lane, dp);   // dP = dO V^T
+        if (a.drop.thresh16 != 0) {
+          float ksc[2][4][4];
+          dropout_scales(a.drop, (unsigned long long)task, lane, a.L, ksc);
 #pragma unroll
-  for (int kb = 0; kb < 2; ++kb) {
-    uint32_t a0[4], a1[4];
-    ldsm_x4_t(addr_at(ds, PP, 0, kb * 16, lane), a0);
-    ldsm_x4_t(addr_at(ds, PP, 16, kb * 16, lane), a1);
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int dpi = 0; dpi < 4; ++dpi) {
-      uint32_t b[4];
-      ldsm_x4_t(addr_b(q, QP, kb * 16, dpi * 16, lane), b);
-      mma16816(acc[0][2 * dpi], a0, b[0], b[1]); mma16816(acc[0][2 * dpi + 1], a0, b[2], b[3]);
-      mma16816(acc[1][2 * dpi], a1, b[0], b[1]); mma16816(acc[1][2 * dpi + 1], a1, b[2], b[3]);
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { dp[mt][nt][e] *= ksc[mt][nt][e]; ksc[mt][nt][e] *= p[mt][nt][e]; }  // ksc := dropped probabilities
+          // dV[j][d] = sum_i pd[i][j] dO[i][d]   (pd = dropped probabilities, what multiplied V in the forward)
+          uint32_t xt[4][4];
+#pragma unroll
+          for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb) {
+              const bool live = ib * 8 + g < a.L;   // query rows >= L carry garbage: they must not enter the reduction over queries
+              const uint32_t blk = live ? pack_bf16x2(ksc[ib >> 1][jb][(ib & 1) * 2], ksc[ib >> 1][jb][(ib & 1) * 2 + 1]) : 0u;
+              xt[jb][ib] = movm_t(blk);
+            }
+          float acc[2][8][4];
+          zero_acc(acc);
+          atv_product(xt, dO, ge, lane, acc);
+          __syncwarp();                    // v is dead since dP: stage dV there
+          acc_to_tile(acc, v, a.L, lane);
+        } else {
+          uint32_t xt[4][4];
+#pragma unroll
+          for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb) {
+              const bool live = ib * 8 + g < a.L;
+              const uint32_t blk = live ? pack_bf16x2(p[ib >> 1][jb][(ib & 1) * 2], p[ib >> 1][jb][(ib & 1) * 2 + 1]) : 0u;
+              xt[jb][ib] = movm_t(blk);
+            }
+          float acc[2][8][4];
+          zero_acc(acc);
+          atv_product(xt, dO, ge, lane, acc);
+          __syncwarp();
+          acc_to_tile(acc, v, a.L, lane);
+        }
+        // dS = P o (dP - rowsum(dP o P)) * scale, in place in dp (rows >= L zeroed)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float dot = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) dot += dp[mt][nt][hh * 2 + cc] * p[mt][nt][hh * 2 + cc];
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            const bool live = mt * 16 + hh * 8 + g < a.L;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc)
+                dp[mt][nt][hh * 2 + cc] = live ? p[mt][nt][hh * 2 + cc] * (dp[mt][nt][hh * 2 + cc] - dot) * a.scale : 0.f;
+          }
+        // dK[j][d] = sum_i dS[i][j] Q[i][d]
+        {
+          uint32_t xt[4][4];
+#pragma unroll
+          for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb)
+              xt[jb][ib] = movm_t(pack_bf16x2(dp[ib >> 1][jb][(ib & 1) * 2], dp[ib >> 1][jb][(ib & 1) * 2 + 1]));
+          float acc[2][8][4];
+          zero_acc(acc);
+          atv_product(xt, q, ge, lane, acc);
+          __syncwarp();                    // dO is dead since dV: stage dK there
+          acc_to_tile(acc, dO, a.L, lane);
+        }
+        // dQ[i][d] = sum_j dS[i][j] K[j][d]
+        {
+          float acc[2][8][4];
+          zero_acc(acc);
+          av_product(dp, k, ge, lane, acc);
+          __syncwarp();                    // q is dead since dK: stage dQ there
+          acc_to_tile(acc, q, a.L, lane);
+        }
+        __syncwarp();
+        __nv_bfloat16* out = a.out + (size_t)r * a.L * 3 * a.D + h * DH;
+        unstage_tile(q, out, 3 * (size_t)a.D, a.L, lane);
+        unstage_tile(dO, out + a.D, 3 * (size_t)a.D, a.L, lane);
+        unstage_tile(v, out + 2 * a.D, 3 * (size_t)a.D, a.L, lane);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy accesses to the stage before TMA overwrites it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
-  __syncwarp();
-  acc_to_tile(acc, dO, lane);
-  // ---- dQ[i][d] = sum_j dS[i][j] K[j][d]  -> staged into the q tile (dead after dK)
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-#pragma unroll
-  for (int kb = 0; kb < 2; ++kb) {  // reduction over keys j
-    uint32_t a0[4], a1[4];
-    ldsm_x4(addr_a(ds, PP, 0, kb * 16, lane), a0);
-    ldsm_x4(addr_a(ds, PP, 16, kb * 16, lane), a1);
-#pragma unroll
-    for (int dpi = 0; dpi < 4; ++dpi) {
-      uint32_t b[4];
-      ldsm_x4_t(addr_b(k, QP, kb * 16, dpi * 16, lane), b);
-      mma16816(acc[0][2 * dpi], a0, b[0], b[1]); mma16816(acc[0][2 * dpi + 1], a0, b[2], b[3]);
-      mma16816(acc[1][2 * dpi], a1, b[0], b[1]); mma16816(acc[1][2 * dpi + 1], a1, b[2], b[3]);
-    }
-  }
-  __syncwarp();
-  acc_to_tile(acc, q, lane);
-  __syncwarp();
-  __nv_bfloat16* out = dqkv + (size_t)r * L * 3 * D + h * DH;
-  unstage_tile(q, out, 3 * (size_t)D, L, lane);
-  unstage_tile(dO, out + D, 3 * (size_t)D, L, lane);
-  unstage_tile(v, out + 2 * D, 3 * (size_t)D, L, lane);
 }
 
 static inline CBfPtr cbf(const clipdlm_bf_t* p) {
@@ -623,20 +662,44 @@ static int warps_for(size_t per_warp_bytes) {
   return w;
 }
 
+// Persistent TMA-ring launch (plain bf16, L <= 32): one CTA per SM, ring depth from the shared-memory budget.
+template <bool BWD>
+static int launch_ring(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
+                       __nv_bfloat16* out, const DropoutCfg& drop, cudaStream_t st) {
+  const long long T = (long long)R * L;
+  CUtensorMap tm_qkv, tm_do;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tm_qkv, qkv, 3ull * D, (unsigned long long)T, 3ull * D * 2, DH, (uint32_t)L))) return rc;
+  tm_do = tm_qkv;
+  if (BWD && (rc = make_tmap_2d_bf16(&tm_do, dctx, (unsigned long long)D, (unsigned long long)T, (unsigned long long)D * 2, DH, (uint32_t)L))) return rc;
+  const uint32_t tile_bytes = (L <= 24 ? 24u : 32u) * 128u;
+  const uint32_t stage_bytes = (BWD ? 4u : 3u) * tile_bytes;
+  AttArgs a;
+  a.keymask = keymask; a.out = out; a.R = R; a.L = L; a.D = D; a.H = H; a.drop = drop; a.scale = 0.125f;  // 1 / sqrt(64)
+  a.stages = (int)((216u * 1024u) / stage_bytes);
+  if (a.stages > 32) a.stages = 32;
+  a.consumers = BWD ? 10 : 14;
+  if (a.consumers > a.stages - 4) a.consumers = a.stages - 4;
+  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + 1024 + (size_t)2 * a.stages * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (set_smem(attn_ring_kernel<BWD>, 227 * 1024)) return -1;
+    attr_set = true;
+  }
+  const long long tasks = (long long)R * H;
+  const int grid = (int)(tasks < num_sms() ? tasks : num_sms());
+  attn_ring_kernel<BWD><<<grid, (a.consumers + 1) * 32, smem, st>>>(tm_qkv, tm_do, a);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, int L, int D, int H, const clipdlm_bf_t* ctx,
                       unsigned long long seed, uint32_t site, float p, cudaStream_t st) {
   CLIPDLM_CHECK(qkv && qkv->hi && ctx && ctx->hi && keymask, "attn_fwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_fwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_fwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && !g_force_simt) {
-    const size_t smem = (size_t)4 * 3 * TILE_E * sizeof(__nv_bfloat16);
-    if (set_smem(attn_fwd_mma_kernel, smem)) return -1;
-    const long long items = (long long)R * H;
-    attn_fwd_mma_kernel<<<(unsigned)((items + 3) / 4), 128, smem, st>>>((const __nv_bfloat16*)qkv->hi, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi,
-                                                                       make_drop(seed, site, p), 0.125f);
-    CLIPDLM_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
+  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && !g_force_simt)
+    return launch_ring<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
   const size_t per_warp = (size_t)3 * L * ROWP * sizeof(float);
   const int W = warps_for(per_warp);
   CLIPDLM_CHECK(W >= 1, "attn_fwd: L %d needs too much shared memory", L);
@@ -662,15 +725,9 @@ int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cl
   CLIPDLM_CHECK(qkv && qkv->hi && dctx && dctx->hi && dqkv && dqkv->hi && keymask, "attn_bwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_bwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_bwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && !g_force_simt) {
-    const size_t smem = (size_t)4 * (4 * TILE_E + 2 * 32 * PP) * sizeof(__nv_bfloat16);
-    if (set_smem(attn_bwd_mma_kernel, smem)) return -1;
-    const long long items = (long long)R * H;
-    attn_bwd_mma_kernel<<<(unsigned)((items + 3) / 4), 128, smem, st>>>((const __nv_bfloat16*)qkv->hi, keymask, (const __nv_bfloat16*)dctx->hi, R, L, D,
-                                                                       H, (__nv_bfloat16*)dqkv->hi, make_drop(seed, site, p), 0.125f);
-    CLIPDLM_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
+  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && !g_force_simt)
+    return launch_ring<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
+                             make_drop(seed, site, p), st);
   const size_t per_warp = (size_t)6 * L * ROWP * sizeof(float);
   const int W = warps_for(per_warp);
   CLIPDLM_CHECK(W >= 1, "attn_bwd: L %d needs too much shared memory", L);

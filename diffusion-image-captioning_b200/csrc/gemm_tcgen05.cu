@@ -589,6 +589,16 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
   return 0;
 }
 
+// 2-D bf16 tensor map (128-byte swizzle) for other kernels of the library (attention): dims {inner, outer}, box {box_inner, box_outer}.
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, unsigned long long inner, unsigned long long outer, unsigned long long pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && pitch_bytes % 16 == 0, "tensor map: base / pitch must be 16-byte aligned");
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {pitch_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return encode_map(tm, base, 2, dims, str, box);
+}
+
 // Operand map. major 0: stored [rows][K] pitch ld -> dims {K, rows}, box {64, tile_rows}.
 //              major 1: stored [K][rows] pitch ld -> dims {rows, K}, box {64, 64}.
 static int operand_map(CUtensorMap* tm, const void* base, int major, int rows, int K, long long ld, int tile_rows, int gather_len,
