@@ -647,8 +647,11 @@ static inline BfPtr mbf(const clipdlm_bf_t* p) {
   BfPtr r; r.hi = (__nv_bfloat16*)p->hi; r.lo = (__nv_bfloat16*)p->lo; return r;
 }
 
-static bool g_force_simt = false;
-void attn_force_simt(int on) { g_force_simt = on != 0; }
+static int g_force_path = 0;   // 0 = auto (forward: tcgen05 packed tiles, backward: mma.sync TMA ring), 1 = fp32 SIMT, 2 = ring, 3 = tcgen05
+void attn_force_simt(int on) { g_force_path = on; }
+template <bool BWD>
+int launch_attn_umma(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
+                     __nv_bfloat16* out, const DropoutCfg& drop, cudaStream_t st);
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -698,7 +701,9 @@ int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, i
   CLIPDLM_CHECK(qkv && qkv->hi && ctx && ctx->hi && keymask, "attn_fwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_fwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_fwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && !g_force_simt)
+  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && (g_force_path == 0 || g_force_path == 3))
+    return launch_attn_umma<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
+  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && g_force_path == 2)
     return launch_ring<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
   const size_t per_warp = (size_t)3 * L * ROWP * sizeof(float);
   const int W = warps_for(per_warp);
@@ -725,7 +730,10 @@ int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cl
   CLIPDLM_CHECK(qkv && qkv->hi && dctx && dctx->hi && dqkv && dqkv->hi && keymask, "attn_bwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_bwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_bwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && !g_force_simt)
+  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && g_force_path == 3)
+    return launch_attn_umma<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
+                                  make_drop(seed, site, p), st);
+  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && (g_force_path == 0 || g_force_path == 2))
     return launch_ring<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
                              make_drop(seed, site, p), st);
   const size_t per_warp = (size_t)6 * L * ROWP * sizeof(float);

@@ -1,0 +1,355 @@
+// Short-sequence multi-head attention on the tcgen05 tensor cores (plain bf16 storage, L <= 32, head dim 64).
+// Replaces DistilBertSelfAttention / SDPA (HF modeling_distilbert.py:126-151,177-207) and its autograd backward for the shapes
+// of the reference path (L = MAX_LENGTH + 2 = 18).
+//
+// Packing.  Four sequences of one head form one 128-row UMMA tile: sequence slot s owns rows [32 s, 32 s + L) (TMA zero-fills
+// rows L..31 of each slot through an out-of-bounds box, so padding never has to be written or checked).  S = Q K^T is ONE
+// 128 x 128 x 64 tcgen05.mma group whose four diagonal 32 x 32 blocks are the four score matrices; the off-diagonal blocks are
+// wasted tensor-core work, which is free here (0.4 % of the model FLOPs) and buys the layout that matters: TMEM lane = query
+// row, so each softmax thread owns one complete row of 32 scores in registers (one tcgen05.ld) - max / sum / dropout / dS need
+// no shuffles, no shared-memory round trips and no fragment bookkeeping (the mma.sync version spent ~1500 (fwd) / ~2300 (bwd)
+// instructions per (sequence, head); this one ~150 / ~300 per row-thread, i.e. per 32 rows of a warp).
+// The probabilities are written once, as bf16, into a block-diagonal [128 x 128] shared-memory tile that then serves as
+//   * K-major  A operand:  O  = P V,    dQ = dS K        (contraction over keys)
+//   * MN-major A operand:  dV = P^T dO, dK = dS^T Q      (contraction over queries - the transpose is a descriptor, not a copy)
+// and the q / k / v / dO tiles are likewise used both K-major (contraction over the head dim) and MN-major (contraction over rows).
+//
+// One CTA = TMA producer warp + MMA-issuing warp + 4 softmax/epilogue warps (one per TMEM lane quadrant), persistent over groups;
+// four (forward: 48 KB shared memory, 128 TMEM columns) or two (backward: 112 KB, 256 columns) CTAs per SM overlap one group's
+// softmax with the others' loads and MMAs.
+#include "common.cuh"
+#include "../../include/clipdlm.h"
+#include <cudaTypedefs.h>
+
+namespace clipdlm {
+
+int num_sms();
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                      const uint32_t* box);
+
+constexpr int AU_DH = 64;
+constexpr int AU_THREADS = 192;          // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 softmax / epilogue
+constexpr uint32_t AU_TILE = 16384;      // [128 rows][64 bf16] = 128 rows x 128 B, 128-byte swizzle
+constexpr float AU_LOG2E = 1.4426950408889634f;
+
+// same counter layout as attention.cu (attn_rand_block / attn_keep_ij): element (i, j) of pair rh draws field ((j / 8) % 4) * 2 + j % 2
+// of the Philox block (rh, lane' = (i % 8) * 4 + (j % 8) / 2, q = (i / 8) * 4 + j / 32) - the SIMT and ring kernels see the same masks.
+__device__ __forceinline__ uint4 au_rand_block(const DropoutCfg& d, unsigned long long rh, int lane_p, int q) {
+  return philox4x32_10(make_uint4((uint32_t)rh, (uint32_t)(rh >> 32), (uint32_t)lane_p | ((uint32_t)q << 8), d.site ^ 0xa77e0000u),
+                       make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+}
+// keep-scale (0 or 1 / (1 - p)) for the 32 keys of query row i
+__device__ __forceinline__ void au_row_keep(const DropoutCfg& d, unsigned long long rh, int i, int L, float (&ks)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {   // c = (j % 8) / 2
+    const uint4 rnd = au_rand_block(d, rh, (i & 7) * 4 + c, (i >> 3) * 4);
+    const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      if (jb * 8 >= L) continue;
+      ks[jb * 8 + 2 * c] = (w[jb] & 0xffffu) >= d.thresh16 ? d.scale : 0.f;
+      ks[jb * 8 + 2 * c + 1] = (w[jb] >> 16) >= d.thresh16 ? d.scale : 0.f;
+    }
+  }
+}
+
+// x[j] *= keep-scale, in place (forward)
+__device__ __forceinline__ void au_row_drop(const DropoutCfg& d, unsigned long long rh, int i, int L, float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 rnd = au_rand_block(d, rh, (i & 7) * 4 + c, (i >> 3) * 4);
+    const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      if (jb * 8 >= L) continue;
+      x[jb * 8 + 2 * c] = (w[jb] & 0xffffu) >= d.thresh16 ? x[jb * 8 + 2 * c] * d.scale : 0.f;
+      x[jb * 8 + 2 * c + 1] = (w[jb] >> 16) >= d.thresh16 ? x[jb * 8 + 2 * c + 1] * d.scale : 0.f;
+    }
+  }
+}
+
+struct AttUArgs {
+  const uint32_t* keymask;
+  __nv_bfloat16* out;       // ctx [T, D] (forward) or dqkv [T, 3D] (backward)
+  int R, L, D, H;
+  int groups_per_head;      // ceil(R / 4)
+  long long groups;         // groups_per_head * H
+  DropoutCfg drop;
+  float scale;
+};
+
+// 32 fp32 values of one row -> bf16, into columns [32 * slot, 32 * slot + 32) of row `row` of a [2 chunks][128 rows][128 B] K-major tile
+__device__ __forceinline__ void au_store_row32(uint32_t tile, int row, int slot, const float (&x)[32]) {
+  const uint32_t base = tile + (uint32_t)(slot >> 1) * AU_TILE + (uint32_t)row * 128u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t addr = base + ((((slot & 1) * 4 + c) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(x[8 * c], x[8 * c + 1])),
+                 "r"(pack_bf16x2(x[8 * c + 2], x[8 * c + 3])), "r"(pack_bf16x2(x[8 * c + 4], x[8 * c + 5])),
+                 "r"(pack_bf16x2(x[8 * c + 6], x[8 * c + 7]))
+                 : "memory");
+  }
+}
+// 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (128 contiguous bytes) in global memory
+__device__ __forceinline__ void au_store_out64(uint32_t taddr, __nv_bfloat16* dst, bool valid) {
+  float v[32];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld32(taddr + half * 32, v);
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(dst + half * 32 + c * 8) =
+            make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]), pack_bf16x2(v[8 * c + 4], v[8 * c + 5]),
+                       pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+    }
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                                                                  const AttUArgs a) {
+  extern __shared__ __align__(1024) uint8_t au_smem[];
+  // forward : Q | K | V, P (2 tiles) overlays Q | K once S is done      = 3 tiles (48 KB), 128 TMEM columns: 4 CTAs per SM
+  // backward: Q | K | dO | V + P (P overlays V) | dS(2)                   = 7 tiles (112 KB), 256 TMEM columns: 2 CTAs per SM
+  constexpr int OFF_Q = 0, OFF_K = 1, OFF_DO = 2, OFF_V = BWD ? 3 : 2, OFF_P = BWD ? 3 : 0, OFF_DS = 5;
+  constexpr int NTILES_SMEM = BWD ? 7 : 3;
+  constexpr uint32_t AU_TMEM_COLS = BWD ? 256 : 128;
+  constexpr uint32_t COL_O = BWD ? 128 : 0;     // forward: O reuses the score columns (S has been consumed when P is ready)
+  constexpr int NLOADS = BWD ? 4 : 3;
+  uint8_t* smem = au_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NTILES_SMEM * AU_TILE);
+  uint64_t* in_full = bars + 0; uint64_t* in_empty = bars + 1; uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3; uint64_t* o_full = bars + 4; uint64_t* t_empty = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("clipdlm: attention smem base not 1024-byte aligned\n"); __trap(); }
+
+  // backward: the block-diagonal dS tile and the upper key chunk of P keep their off-diagonal zeros for the life of the CTA
+  // (the forward P tile lives where TMA keeps landing Q and K, so its rows are rewritten completely for every group)
+  if (BWD) {
+    uint8_t* z0 = smem + OFF_P * AU_TILE;
+    const uint32_t zbytes = 4u * AU_TILE;
+    for (uint32_t off = threadIdx.x * 16; off < zbytes; off += AU_THREADS * 16) *reinterpret_cast<uint4*>(z0 + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(in_full, 1); mbar_init(in_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(t_empty, 4);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_qkv);
+    if (BWD) tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, AU_TMEM_COLS);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long my_groups = a.groups > blockIdx.x ? (a.groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      for (long long n = 0; n < my_groups; ++n) {
+        const long long grp = blockIdx.x + n * gridDim.x;
+        const int h = (int)(grp % a.H), r0 = (int)(grp / a.H) * 4;
+        mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+        mbar_arrive_expect_tx(in_full, NLOADS * AU_TILE);   // full boxes: rows >= L and sequences >= R arrive as zeros
+        tma_load_3d(smem + OFF_Q * AU_TILE, &tm_qkv, in_full, h * AU_DH, 0, r0);
+        tma_load_3d(smem + OFF_K * AU_TILE, &tm_qkv, in_full, a.D + h * AU_DH, 0, r0);
+        tma_load_3d(smem + OFF_V * AU_TILE, &tm_qkv, in_full, 2 * a.D + h * AU_DH, 0, r0);
+        if (BWD) tma_load_3d(smem + OFF_DO * AU_TILE, &tm_do, in_full, h * AU_DH, 0, r0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP: both operands K-major (contraction over the head dim)
+      constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);    // O = P V, dQ = dS K: A K-major, B MN-major
+      constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q: both MN-major
+      const uint32_t sq = smem_u32(smem + OFF_Q * AU_TILE), sk = smem_u32(smem + OFF_K * AU_TILE), sv = smem_u32(smem + OFF_V * AU_TILE);
+      const uint32_t sdo = smem_u32(smem + OFF_DO * AU_TILE), sp = smem_u32(smem + OFF_P * AU_TILE), sds = smem_u32(smem + OFF_DS * AU_TILE);
+      for (long long n = 0; n < my_groups; ++n) {
+        const uint32_t par = (uint32_t)n & 1u;
+        mbar_wait(in_full, par);
+        mbar_wait(t_empty, par ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S = Q K^T
+          umma_bf16(tmem_base, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2),
+                    idesc_s, k > 0 ? 1u : 0u);
+        if (BWD) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dP = dO V^T
+            umma_bf16(tmem_base + 128, make_smem_desc_sw128(sdo, 16, 1024) + (uint64_t)(k * 2),
+                      make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, par);
+        tc_fence_after();
+        if (!BWD) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // O = P V  (keys in blocks of 16: P chunk k / 4, 32 B per step; V rows 16 k)
+            umma_bf16(tmem_base + COL_O, make_smem_desc_sw128(sp + (k >> 2) * AU_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
+                      make_smem_desc_sw128(sv, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dV = P^T dO   (queries in blocks of 16: rows 16 k of P and dO)
+            umma_bf16(tmem_base, make_smem_desc_sw128(sp, AU_TILE, 1024) + (uint64_t)(k * 128),
+                      make_smem_desc_sw128(sdo, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dK = dS^T Q
+            umma_bf16(tmem_base + 64, make_smem_desc_sw128(sds, AU_TILE, 1024) + (uint64_t)(k * 128),
+                      make_smem_desc_sw128(sq, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dQ = dS K
+            umma_bf16(tmem_base + 128, make_smem_desc_sw128(sds + (k >> 2) * AU_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
+                      make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(in_empty);   // every operand tile of this group has been consumed
+      }
+    }
+  } else {
+    // ===================================== softmax / epilogue =====================================
+    const int slot = warp & 3;            // TMEM lane quadrant this warp may access == sequence slot of the group
+    const int i = lane;                   // query row (forward/backward) - and key row for the dK / dV outputs
+    const int row = slot * 32 + i;
+    const uint32_t tq = tmem_base + ((uint32_t)(slot * 32) << 16);
+    const uint32_t sp = smem_u32(smem + OFF_P * AU_TILE), sds = smem_u32(smem + OFF_DS * AU_TILE);
+    for (long long n = 0; n < my_groups; ++n) {
+      const uint32_t par = (uint32_t)n & 1u;
+      const long long grp = blockIdx.x + n * gridDim.x;
+      const int h = (int)(grp % a.H), r = (int)(grp / a.H) * 4 + slot;
+      const bool live = r < a.R && i < a.L;
+      const uint32_t keybits = r < a.R ? a.keymask[r] : 0u;
+      const unsigned long long rh = (unsigned long long)r * a.H + h;
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      float p[32];
+      tmem_ld32(tq + 32 * slot, p);       // this row's scores against the 32 key slots of its own sequence (diagonal block)
+      {
+        const float sl = a.scale * AU_LOG2E;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = j < a.L && ((keybits >> j) & 1u);
+          p[j] = ok ? p[j] * sl : -INFINITY;
+          mx = fmaxf(mx, p[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { p[j] = ex2_ftz(p[j] - mx); sum += p[j]; }   // a fully masked row gives NaN, as the reference does
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p[j] = live ? p[j] * inv : 0.f;
+      }
+      const bool dropping = a.drop.thresh16 != 0;
+      if (!BWD) {
+        if (dropping) au_row_drop(a.drop, rh, i, a.L, p);
+        // P lives where Q / K were: write this row of both key chunks completely (zeros off the diagonal block)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          if ((cc >> 2) == slot) continue;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sp + (uint32_t)(cc >> 3) * AU_TILE + (uint32_t)row * 128u + (uint32_t)(((cc & 7) ^ (row & 7)) << 4)),
+                       "r"(0u) : "memory");
+        }
+        au_store_row32(sp, row, slot, p);
+      } else {
+        float ks[32];
+        if (dropping) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ks[j] = 0.f;
+          au_row_keep(a.drop, rh, i, a.L, ks);
+        }
+        float dp[32];
+        tmem_ld32(tq + 128 + 32 * slot, dp);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (dropping) dp[j] *= ks[j];       // gradient through the dropout
+          dot = fmaf(dp[j], p[j], dot);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dp[j] = p[j] * (dp[j] - dot) * a.scale;   // dS (p == 0 on dead rows / masked keys)
+        if (dropping) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) p[j] *= ks[j];   // dropped probabilities: what multiplied V in the forward
+        }
+        // V's tile doubles as the first half (key chunk 0) of P and has just been clobbered by TMA: rewrite this row of it completely
+        if (slot >= 2) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sp + (uint32_t)row * 128u + (uint32_t)(c << 4)), "r"(0u) : "memory");
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sp + (uint32_t)row * 128u + (uint32_t)(((((slot ^ 1) & 1) * 4 + c) ^ (row & 7)) << 4)),
+                         "r"(0u) : "memory");
+        }
+        au_store_row32(sp, row, slot, p);
+        au_store_row32(sds, row, slot, dp);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P / dS (generic proxy) -> tcgen05.mma operand reads (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      mbar_wait(o_full, par);
+      tc_fence_after();
+      if (!BWD) {
+        au_store_out64(tq + COL_O, a.out + ((size_t)r * a.L + i) * a.D + h * AU_DH, live);
+      } else {
+        __nv_bfloat16* o = a.out + ((size_t)r * a.L + i) * 3 * a.D + h * AU_DH;
+        au_store_out64(tq + 128, o, live);               // dQ
+        au_store_out64(tq + 64, o + a.D, live);          // dK (row = key i)
+        au_store_out64(tq, o + 2 * a.D, live);           // dV
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, AU_TMEM_COLS);
+}
+
+template <bool BWD>
+int launch_attn_umma(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
+                     __nv_bfloat16* out, const DropoutCfg& drop, cudaStream_t st) {
+  CUtensorMap tm_qkv, tm_do;
+  int rc;
+  {
+    const unsigned long long dims[3] = {3ull * D, (unsigned long long)L, (unsigned long long)R};
+    const unsigned long long str[2] = {3ull * D * 2, 3ull * D * 2 * L};
+    const uint32_t box[3] = {AU_DH, 32, 4};
+    if ((rc = make_tmap_3d_bf16(&tm_qkv, qkv, dims, str, box))) return rc;
+  }
+  tm_do = tm_qkv;
+  if (BWD) {
+    const unsigned long long dims[3] = {(unsigned long long)D, (unsigned long long)L, (unsigned long long)R};
+    const unsigned long long str[2] = {(unsigned long long)D * 2, (unsigned long long)D * 2 * L};
+    const uint32_t box[3] = {AU_DH, 32, 4};
+    if ((rc = make_tmap_3d_bf16(&tm_do, dctx, dims, str, box))) return rc;
+  }
+  AttUArgs a;
+  a.keymask = keymask; a.out = out; a.R = R; a.L = L; a.D = D; a.H = H; a.drop = drop; a.scale = 0.125f;  // 1 / sqrt(64)
+  a.groups_per_head = (R + 3) / 4;
+  a.groups = (long long)a.groups_per_head * H;
+  const size_t smem = (size_t)(BWD ? 7 : 3) * AU_TILE + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_umma_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long want = (BWD ? 2LL : 4LL) * num_sms();
+  const int grid = (int)(a.groups < want ? a.groups : want);
+  attn_umma_kernel<BWD><<<grid, AU_THREADS, smem, st>>>(tm_qkv, tm_do, a);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int launch_attn_umma<false>(const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int, int, __nv_bfloat16*, const DropoutCfg&,
+                                     cudaStream_t);
+template int launch_attn_umma<true>(const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int, int, __nv_bfloat16*, const DropoutCfg&,
+                                    cudaStream_t);
+
+}  // namespace clipdlm

@@ -599,6 +599,15 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, unsigned long long inne
   return encode_map(tm, base, 2, dims, str, box);
 }
 
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                      const uint32_t* box) {
+  CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && strides_bytes[0] % 16 == 0 && strides_bytes[1] % 16 == 0,
+                "tensor map: base / strides must be 16-byte aligned");
+  uint64_t d[3] = {dims[0], dims[1], dims[2]};
+  uint64_t s[2] = {strides_bytes[0], strides_bytes[1]};
+  return encode_map(tm, base, 3, d, s, box);
+}
+
 // Operand map. major 0: stored [rows][K] pitch ld -> dims {K, rows}, box {64, tile_rows}.
 //              major 1: stored [K][rows] pitch ld -> dims {rows, K}, box {64, 64}.
 static int operand_map(CUtensorMap* tm, const void* base, int major, int rows, int K, long long ld, int tile_rows, int gather_len,

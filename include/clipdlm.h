@@ -131,7 +131,8 @@ int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cli
                      int32_t H, const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p,
                      clipdlm_stream stream);
 
-/* Test hook: 1 forces the fp32 SIMT attention kernels even where the tensor-core (mma.sync) path applies (plain bf16, L <= 32). */
+/* Test hook: attention path for plain bf16, L <= 32: 0 = default (forward: tcgen05 packed tiles, backward: mma.sync TMA ring),
+ * 1 = fp32 SIMT kernels, 2 = mma.sync TMA-ring kernels, 3 = tcgen05 packed tiles for both directions. */
 void clipdlm_attn_force_simt(int32_t on);
 
 /* Column sums (bias gradients): out[n] += sum_m x[m, n]. */

@@ -276,7 +276,7 @@ def test_attention_mma_path_matches_simt_with_dropout(G):
     words = words.to(torch.int32).contiguous()
     lib, Lb = G.lib(), G.L
     outs = {}
-    for simt in (0, 1):
+    for simt in (0, 1, 2, 3):  # default mix, fp32 SIMT, mma.sync TMA ring, tcgen05 packed tiles
         lib.clipdlm_attn_force_simt(simt)
         ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
         dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
@@ -286,7 +286,8 @@ def test_attention_mma_path_matches_simt_with_dropout(G):
         torch.cuda.synchronize()
         outs[simt] = (ctx.float(), dq.float())
     lib.clipdlm_attn_force_simt(0)
-    assert rel(outs[0][0], outs[1][0]) < 1e-2 and rel(outs[0][1], outs[1][1]) < 1.5e-2
+    for path in (0, 2, 3):
+        assert rel(outs[path][0], outs[1][0]) < 1e-2 and rel(outs[path][1], outs[1][1]) < 1.5e-2, path
     # a differing mask would change ~10 % of the probabilities by 100 %: far outside these bounds
 
 

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the attention kernels at the train-chunk shape (R = 4096 sequences x L = 18, 12 heads): paths 0 (tcgen05 packed
+tiles), 2 (mma.sync TMA ring), with and without dropout. Triage tool."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import clipdlm  # noqa: E402,F401
+from clipdlm import _lib as L  # noqa: E402
+
+DEV = "cuda:0"
+R, Ls, D, H = int(os.environ.get("ROWS", 4096)), 18, 768, 12
+lib = L.load()
+st = torch.cuda.current_stream().cuda_stream
+qkv = torch.randn(R * Ls, 3 * D, device=DEV).bfloat16()
+dctx = torch.randn(R * Ls, D, device=DEV).bfloat16()
+ctx = torch.empty(R * Ls, D, device=DEV, dtype=torch.bfloat16)
+dqkv = torch.empty(R * Ls, 3 * D, device=DEV, dtype=torch.bfloat16)
+km = torch.full((R,), (1 << 17) - 1, device=DEV, dtype=torch.int32)
+bq, bc, bd, bg = L.Bf(qkv.data_ptr(), None), L.Bf(ctx.data_ptr(), None), L.Bf(dctx.data_ptr(), None), L.Bf(dqkv.data_ptr(), None)
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3
+
+
+fwd_bytes, bwd_bytes = R * Ls * D * 2 * 4, R * Ls * D * 2 * 7
+for path in (3, 2):
+    lib.clipdlm_attn_force_simt(path)
+    for p in (0.0, 0.1):
+        f = timeit(lambda: L.check(lib.clipdlm_attn_fwd(C.byref(bq), km.data_ptr(), R, Ls, D, H, C.byref(bc), 1, 1, p, st)))
+        b = timeit(lambda: L.check(lib.clipdlm_attn_bwd(C.byref(bq), km.data_ptr(), C.byref(bd), R, Ls, D, H, C.byref(bg), 1, 1, p, st)))
+        print(f"path {path} p={p}: fwd {f:7.1f} us ({fwd_bytes / f / 1e3:6.0f} GB/s)   bwd {b:7.1f} us ({bwd_bytes / b / 1e3:6.0f} GB/s)", flush=True)
+lib.clipdlm_attn_force_simt(0)
