@@ -14,6 +14,8 @@ int num_sms();
 int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st);
 int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
                          int* argmax, double* loss_acc, double scale, cudaStream_t st);
+int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, const float* lse, const int* targets, int tgt_period, float scale,
+                                  cudaStream_t st);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
 int embed_bwd_dispatch(const clipdlm_bf_t* dz, int R, int B, int Ltxt, int L, int D, int fusion, int guided, float* d_pos, float* d_seg,
                        float* d_img, float* d_txt, cudaStream_t st);
@@ -357,7 +359,7 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
 
 // LSE-fused lm_head over x_out[:, :Ltxt]: partials -> combine.  targets may be NULL (argmax only).
 static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period, int32_t* argmax, double* loss_acc, double scale,
-                       cudaStream_t st) {
+                       cudaStream_t st, void* keep_logits = nullptr) {
   const clipdlm_config_t& c = e->cfg;
   const int M = e->last.R * e->Ltxt;
   Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
@@ -366,6 +368,7 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   g.epilogue = CLIPDLM_EPI_LSE;
   g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = argmax ? e->part_arg : nullptr; g.tgt_logit = e->tgt_logit;
   g.targets = targets; g.tgt_period = tgt_period;
+  if (keep_logits != nullptr) { g.out_hi = keep_logits; g.ldo = e->ldl; }   // bf16 logits for the in-place softmax gradient
   RUNG(g);
   RUNP(CLIPDLM_PROF_LOSS, 0, 6.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, argmax ? e->part_arg : nullptr, 2 * e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
                            scale, st));
@@ -395,17 +398,27 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
                             lc->use_embed_loss ? 1.f : 0.f, lc->use_embed_loss ? &losses[0] : nullptr, bwd ? &e->g0 : nullptr, st));
   // 2. rounding cross-entropy through the frozen lm_head
   if (lc->use_prob_loss) {
-    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st);
+    // plain bf16 + backward: the LSE pass keeps its logits (bf16, in the d(logits) buffer) and an HBM-bound pass turns them into the
+    // softmax-CE gradient in place - 8 GB of traffic instead of recomputing the 3 TFLOP lm_head GEMM.  Split precision (parity
+    // mode) recomputes the vocabulary tiles with fp32 accumulators instead (SMGRAD epilogue).
+    const bool store_logits = bwd && !e->pair;
+    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st, store_logits ? e->dlog.hi : nullptr);
     if (rc) return rc;
     if (bwd) {
       Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
-      clipdlm_gemm_t g = gemm_desc(e->xo, D, 0, emb, D, 0, M16, c.vocab, D);
-      g.gather_len = Ltxt; g.gather_stride = L;
-      g.epilogue = CLIPDLM_EPI_SMGRAD;
-      g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
-      g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
-      g.grad_scale = (float)(lc->rounding_weight * ce_scale);
-      RUNG(g);
+      clipdlm_gemm_t g;
+      if (store_logits) {
+        RUNP(CLIPDLM_PROF_GEMM_SMGRAD, 0, 4.0 * M16 * (double)e->ldl,
+             softmax_grad_inplace_dispatch(e->dlog.hi, e->ldl, M16, c.vocab, e->lse, p.ids, B * Ltxt, (float)(lc->rounding_weight * ce_scale), st));
+      } else {
+        g = gemm_desc(e->xo, D, 0, emb, D, 0, M16, c.vocab, D);
+        g.gather_len = Ltxt; g.gather_stride = L;
+        g.epilogue = CLIPDLM_EPI_SMGRAD;
+        g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
+        g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
+        g.grad_scale = (float)(lc->rounding_weight * ce_scale);
+        RUNG(g);
+      }
       // d x_out[:, :Ltxt] += dlogits[M16, V] E[V, D]
       g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
       g.out_hi = e->g0.hi; g.out_lo = e->g0.lo; g.ldo = D;

@@ -60,6 +60,7 @@ struct GemmArgs {
   int scatter_len, scatter_stride;
   int al32;  // every bf16 epilogue operand is 32-byte aligned with a pitch that is a multiple of 16 elements
   uint32_t dbg;  // clipdlm_gemm_debug_flags
+  int fast_mode; // >= 0: specialised STORE epilogue (bit 0 bias, bits 1-2 aux 0 none / 1 residual / 2 gelu'(u), bit 3 gelu dual store, bit 4 dropout)
   DropoutCfg drop;
   float* part_max;
   float* part_sum;
@@ -165,6 +166,89 @@ __device__ __forceinline__ void tile_store_f32(const GemmArgs& g, float* base, l
       }
     }
     __syncwarp();
+  }
+}
+
+// ---- specialised STORE epilogue ------------------------------------------------------------------------------------
+// The generic epilogue below decides everything per 32-column chunk at run time (which outputs exist, pair or plain storage,
+// alignment, tails): ~11 bookkeeping instructions per element next to ~12 useful ones in the GELU epilogues, and the K = 768
+// GEMMs are epilogue-issue bound.  The engine's hot launches all fall into a handful of shapes (plain bf16, 32-byte aligned
+// rows, N a multiple of 256), so those get straight-line code: the four chunks of a warp are fully unrolled, the auxiliary
+// operand (residual or gelu' input) is double-buffered in registers one chunk ahead, no per-chunk branches remain.
+template <bool BIAS, int AUX, bool DUAL, bool DROP>
+__device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr, int col0, int m, bool valid, long long mr, uint32_t sbias_u32,
+                                               uint64_t* tfull, uint32_t tphase) {
+  const __nv_bfloat16* aux = AUX == 2 ? g.u_hi : g.res_hi;
+  const long long ld_aux = AUX == 2 ? g.ldu : g.ldr;
+  const __nv_bfloat16* aux_row = AUX != 0 ? aux + mr * ld_aux + col0 : nullptr;
+  __nv_bfloat16* out_row = g.out_hi != nullptr ? g.out_hi + mr * g.ldo + col0 : nullptr;
+  __nv_bfloat16* out2_row = DUAL ? g.out2_hi + mr * g.ldo + col0 : nullptr;
+  uint32_t aux0[16], aux1[16];
+  if (AUX != 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { aux0[i] = 0u; aux1[i] = 0u; }
+    if (valid) ld_row64(aux_row, true, aux0);      // first chunk: in flight while the MMAs of this tile still run
+  }
+  mbar_wait(tfull, tphase);
+  tc_fence_after();
+  // one 32-column chunk; cur holds its auxiliary operand, nxt receives the next chunk's
+  auto chunk = [&](int cc, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
+    float v[32];
+    tmem_ld32(taddr + cc * 32, v);
+    if (AUX != 0 && cc + 1 < 4 && valid) ld_row64(aux_row + (cc + 1) * 32, true, nxt);
+    if (BIAS) {
+      const uint32_t sb = sbias_u32 + cc * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+      }
+    }
+    if (DROP) {
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        const unsigned long long idx = (unsigned long long)m * (unsigned long long)g.N + (unsigned long long)(col0 + cc * 32 + j8 * 8);
+        const uint32_t keep = dropout_keep8(g.drop, idx >> 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = ((keep >> i) & 1u) ? v[j8 * 8 + i] * g.drop.scale : 0.f;
+      }
+    }
+    if (AUX == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_bf16x2(cur[j]);
+        v[2 * j] *= dgelu_f(f.x);
+        v[2 * j + 1] *= dgelu_f(f.y);
+      }
+    } else if (AUX == 1) {
+      row_unpack<true>(cur, v);
+    }
+    if (valid) {
+      if ((!DUAL || out_row != nullptr) && !(g.dbg & 256u)) row_store_pair(out_row + cc * 32, nullptr, true, v);
+      if (DUAL) {
+        if (!(g.dbg & 128u)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+        }
+        row_store_pair(out2_row + cc * 32, nullptr, true, v);
+      }
+    }
+  };
+  // Math-heavy bodies (GELU, gelu', Philox) stay rolled: four unrolled copies (~25 KB of SASS per mode) thrash the instruction
+  // cache and measured slower than the generic loop; the light ones are fully unrolled.
+  constexpr bool HEAVY = DUAL || DROP || AUX == 2;
+  if (HEAVY) {
+#pragma unroll 1
+    for (int c2 = 0; c2 < 4; c2 += 2) {
+      chunk(c2, aux0, aux1);
+      chunk(c2 + 1, aux1, aux0);
+    }
+  } else {
+    chunk(0, aux0, aux1);
+    chunk(1, aux1, aux0);
+    chunk(2, aux0, aux1);
+    chunk(3, aux1, aux0);
   }
 }
 
@@ -335,9 +419,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
 
-      // plain-bf16 residual / gelu'(u) operand: prefetch its first 32-column chunk while the MMAs of this tile are still running
       const bool valid = m < g.M;
       const long long mr = valid ? map_row(g, m) : 0;
+      if (EPI == CLIPDLM_EPI_STORE && g.fast_mode >= 0) {
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_lo * 32;
+        const int col0 = n_blk * BN + c_lo * 32;
+        const uint32_t sb = smem_u32(sbias) + c_lo * 128;
+#define FAST_CASE(MODE, BIAS, AUX, DUAL, DROP) \
+  case MODE: epi_store_fast<BIAS, AUX, DUAL, DROP>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase); break;
+        switch (g.fast_mode) {
+          FAST_CASE(0, false, 0, false, false)    // dgrad
+          FAST_CASE(1, true, 0, false, false)     // q/k/v projection
+          FAST_CASE(2, false, 1, false, false)    // dgrad + residual branch (also the scattered lm_head dgrad)
+          FAST_CASE(3, true, 1, false, false)     // out projection / lin2 (eval) + residual
+          FAST_CASE(4, false, 2, false, false)    // lin2 dgrad * gelu'(u)
+          FAST_CASE(9, true, 0, true, false)      // lin1 / vocab_transform: pre-activation + gelu
+          FAST_CASE(19, true, 1, false, true)     // lin2 (train): bias, dropout, residual
+          default: break;
+        }
+#undef FAST_CASE
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty0_leader + as * 8);
+          else mbar_arrive(&tempty_bar[as]);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
+      // generic path. plain-bf16 residual / gelu'(u) operand: prefetch its first 32-column chunk while the MMAs of this tile are still running
       const bool al32 = g.al32 != 0;
       const bool aux_is_u = g.u_hi != nullptr;
       const __nv_bfloat16* aux = aux_is_u ? g.u_hi : g.res_hi;
@@ -368,6 +478,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           if (n0 >= g.N) break;
           float v[32];
           tmem_ld32(taddr + c * 32, v);
+          // training, plain bf16: keep the logits (bf16) so the backward turns them into d(logits) in place instead of recomputing this GEMM
+          if (g.out_hi != nullptr && m < g.M) row_store_pair(g.out_hi + (long long)m * g.ldo + n0, nullptr, g.al32 != 0, v);
           if (n0 + 32 > g.N) {   // vocabulary tail (last tile only): padding columns never win and add exp(-inf) = 0
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (n0 + j) < g.N ? v[j] : -INFINITY;
@@ -556,6 +668,52 @@ __global__ void lse_combine_kernel(const float* __restrict__ pmax, const float* 
       atomicAdd(loss_acc, t * scale);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// d(logits) in place from stored bf16 logits: x[m, n] <- (exp(x[m, n] - lse[m]) - [n == tgt[m]]) * scale  (n < N), 0 for the padding
+// columns n >= N.  One 16-byte vector (8 logits) per thread, grid-stride; HBM-bound (read + write of the [M, ld] buffer).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_grad_inplace_kernel(__nv_bfloat16* __restrict__ x, long long ld, int M, int N,
+                                                                   const float* __restrict__ lse, const int* __restrict__ targets, int tgt_period,
+                                                                   float scale, float log2_scale) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  const long long vec_per_row = ld >> 3;
+  const long long total = (long long)M * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int n0 = (int)(i - (long long)m * vec_per_row) << 3;
+    uint4* ptr = reinterpret_cast<uint4*>(x + (long long)m * ld + n0);
+    if (n0 >= N) { *ptr = make_uint4(0u, 0u, 0u, 0u); continue; }
+    const uint4 raw = *ptr;
+    const float nb = fmaf(-lse[m], LOG2E, log2_scale);
+    const int tgt = targets[m % tgt_period];
+    float v[8];
+    { float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = ex2_ftz(fmaf(v[j], LOG2E, nb));
+      if (n0 + j == tgt) p -= scale;
+      v[j] = (n0 + j) < N ? p : 0.f;
+    }
+    *ptr = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, const float* lse, const int* targets, int tgt_period, float scale,
+                                  cudaStream_t st) {
+  CLIPDLM_CHECK(logits && lse && targets && M > 0 && N > 0 && ld >= N && ld % 8 == 0 && tgt_period > 0, "softmax_grad_inplace: bad arguments");
+  CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "softmax_grad_inplace: buffer must be 16-byte aligned");
+  int sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const long long total = (long long)M * (ld >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * sms) blocks = 16LL * sms;
+  softmax_grad_inplace_kernel<<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)logits, ld, M, N, lse, targets, tgt_period, scale,
+                                                                scale > 0.f ? log2f(scale) : -INFINITY);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -770,6 +928,18 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   ga.targets = g->targets; ga.tgt_period = g->tgt_period > 0 ? g->tgt_period : 1;
   ga.lse = g->lse; ga.grad_scale = g->grad_scale;
   ga.dbg = g_dbg_flags;
+  ga.fast_mode = -1;
+  if (g->epilogue == CLIPDLM_EPI_STORE && ga.al32 && g->N % BN == 0 && !g->out_lo && !g->out2_lo && !g->res_lo && !g->u_lo && !g->out_f32 &&
+      !(g->res_hi && g->u_hi) && (g->out_hi || g->out2_hi) && !(g_dbg_flags & 7u)) {  // (bits 7, 8: triage of the dual-store mode)
+    const int aux = g->u_hi ? 2 : (g->res_hi ? 1 : 0);
+    const int mode = (g->bias ? 1 : 0) | (aux << 1) | (g->out2_hi ? 8 : 0) | (ga.drop.thresh16 ? 16 : 0);
+    switch (mode) {
+      case 0: case 1: case 2: case 3: case 4: case 9: case 19: ga.fast_mode = mode; break;
+      default: break;
+    }
+    if (!(g_dbg_flags & 64u) && ga.fast_mode >= 0 && mode != 9 && !g->out_hi) ga.fast_mode = -1;   // only the dual-store mode may omit out
+    if (g_dbg_flags & 64u) ga.fast_mode = -1;   // triage: force the generic epilogue
+  }
 
   const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
   const int grid = total < units_max ? total : units_max;   // work units: CTAs (cg = 1) or CTA pairs (cg = 2)
@@ -788,6 +958,9 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
     case CLIPDLM_EPI_LSE:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE epilogue expects K-major operands");
       CLIPDLM_CHECK(g->part_max && g->part_sum && (!g->targets || g->tgt_logit), "LSE epilogue buffers missing");
+      CLIPDLM_CHECK(!g->out_hi || (!g->out_lo && g->ldo >= (long long)ga.num_n_tiles * BN && g->ldo % 8 == 0 &&
+                                   (reinterpret_cast<uintptr_t>(g->out_hi) & 15) == 0),
+                    "LSE epilogue: the optional bf16 logits output needs a 16-byte aligned plain-bf16 buffer with pitch >= %d", ga.num_n_tiles * BN);
       return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(cg, a0, a1, b0, b1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
