@@ -378,6 +378,158 @@ __global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a
   }
 }
 
+// Plain-bf16 specialisation of the kernel above: same row ring, the per-element arithmetic in packed fp32 pairs (FFMA2 / FADD2 /
+// FMUL2), the optional features as template flags (no per-row branches), reciprocal-multiplies instead of divisions.  The generic
+// kernel spends 742 warp instructions per 768-wide row (357 of them scalar fp32 math) and is issue-bound at 12 warps per SM.
+template <int NV, bool DROP_OUT, bool DZ_DROP, bool GELU, bool DBIAS>
+__global__ void __launch_bounds__(128, 3) layernorm_bwd_fast_kernel(const LnBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t lnb_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = 4;
+  const int D = a.D;
+  const uint32_t row_bytes = (uint32_t)D * 2;
+  float* red = reinterpret_cast<float*>(lnb_smem);
+  uint8_t* ring = lnb_smem + (size_t)nwarps * D * sizeof(float) + (size_t)warp * LNB_STAGES * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnb_smem + (size_t)nwarps * D * sizeof(float) + (size_t)nwarps * LNB_STAGES * 2 * row_bytes) +
+                   warp * LNB_STAGES;
+  const long long row0 = (long long)blockIdx.x * nwarps + warp, row_step = (long long)gridDim.x * nwarps;
+  if (lane == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto issue = [&](int s, long long row) {   // lane 0 only
+    uint8_t* dst = ring + (size_t)s * 2 * row_bytes;
+    mbar_arrive_expect_tx(&bars[s], 2 * row_bytes);
+    bulk_load_1d(dst, a.z.hi + (size_t)row * D, row_bytes, &bars[s]);
+    bulk_load_1d(dst + row_bytes, a.dy.hi + (size_t)row * D, row_bytes, &bars[s]);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s)
+      if (row0 + s * row_step < a.rows) issue(s, row0 + s * row_step);
+  }
+  // LayerNorm weight of this lane's columns, packed (the same 24 columns for every row)
+  f32x2 W[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float wv[8];
+    load8_f32(a.w + (v * 32 + lane) * 8, wv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) W[v][i] = pk2(wv[2 * i], wv[2 * i + 1]);
+  }
+  f32x2 pdw[NV][4], pdb[NV][4], pbias[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pdw[v][i] = 0ull; pdb[v][i] = 0ull; pbias[v][i] = 0ull; }
+  const float inv_d = 1.0f / (float)D;
+  int stage = 0; uint32_t phase = 0;
+  for (long long row = row0; row < a.rows; row += row_step) {
+    f32x2 X[NV][4], G[NV][4];
+    mbar_wait(&bars[stage], phase);
+    {
+      const uint8_t* sz = ring + (size_t)stage * 2 * row_bytes;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint4 xr = *reinterpret_cast<const uint4*>(sz + (v * 32 + lane) * 16);
+        const uint4 gr = *reinterpret_cast<const uint4*>(sz + row_bytes + (v * 32 + lane) * 16);
+        X[v][0] = bf2_to_f2(xr.x); X[v][1] = bf2_to_f2(xr.y); X[v][2] = bf2_to_f2(xr.z); X[v][3] = bf2_to_f2(xr.w);
+        G[v][0] = bf2_to_f2(gr.x); G[v][1] = bf2_to_f2(gr.y); G[v][2] = bf2_to_f2(gr.z); G[v][3] = bf2_to_f2(gr.w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && row + LNB_STAGES * row_step < a.rows) issue(stage, row + LNB_STAGES * row_step);
+    if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
+    if (DROP_OUT) {   // the dropout that followed this LN's output masks dy
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint32_t keep = dropout_keep8(a.drop_out, ((unsigned long long)row * D + (v * 32 + lane) * 8) >> 3);
+        const float sc = a.drop_out.scale;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G[v][i] = mul2(G[v][i], pk2(((keep >> (2 * i)) & 1u) ? sc : 0.f, ((keep >> (2 * i + 1)) & 1u) ? sc : 0.f));
+      }
+    }
+    // two-pass statistics (as the forward): mean, then centred second moment; X becomes x - mean
+    f32x2 acc = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc = add2(acc, X[v][i]);
+    const float mean = warp_sum(hsum2(acc)) * inv_d;
+    const f32x2 nmean = pk2(-mean, -mean);
+    acc = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { X[v][i] = add2(X[v][i], nmean); acc = fma2(X[v][i], X[v][i], acc); }
+    const float rstd = rsqrtf(warp_sum(hsum2(acc)) * inv_d + a.eps);
+    const f32x2 rstd2 = pk2(rstd, rstd);
+    f32x2 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const f32x2 xh = mul2(X[v][i], rstd2);
+        const f32x2 gw = mul2(G[v][i], W[v][i]);
+        pdw[v][i] = fma2(G[v][i], xh, pdw[v][i]);
+        pdb[v][i] = add2(pdb[v][i], G[v][i]);
+        s1 = add2(s1, gw);
+        s2 = fma2(gw, xh, s2);
+        X[v][i] = xh; G[v][i] = gw;
+      }
+    const float s1r = warp_sum(hsum2(s1)) * inv_d * rstd, s2r = warp_sum(hsum2(s2)) * inv_d * rstd;
+    const f32x2 ns1 = pk2(-s1r, -s1r), ns2 = pk2(-s2r, -s2r);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = (size_t)row * D + (v * 32 + lane) * 8;
+      f32x2 d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = fma2(X[v][i], ns2, fma2(G[v][i], rstd2, ns1));   // (gw - s1 - xh s2) rstd
+      if (GELU) {
+        const uint4 ur = *reinterpret_cast<const uint4*>(a.gelu_u.hi + off);
+        const uint32_t uw[4] = {ur.x, ur.y, ur.z, ur.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 u = unpack_bf16x2(uw[i]);
+          d[i] = mul2(d[i], pk2(dgelu_f(u.x), dgelu_f(u.y)));
+        }
+      }
+      *reinterpret_cast<uint4*>(a.dz.hi + off) = make_uint4(f2_to_bf2(d[0]), f2_to_bf2(d[1]), f2_to_bf2(d[2]), f2_to_bf2(d[3]));
+      if (DZ_DROP) {
+        const uint32_t keep = dropout_keep8(a.drop_in, (unsigned long long)off >> 3);
+        const float sc = a.drop_in.scale;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = mul2(d[i], pk2(((keep >> (2 * i)) & 1u) ? sc : 0.f, ((keep >> (2 * i + 1)) & 1u) ? sc : 0.f));
+        *reinterpret_cast<uint4*>(a.dz_drop.hi + off) = make_uint4(f2_to_bf2(d[0]), f2_to_bf2(d[1]), f2_to_bf2(d[2]), f2_to_bf2(d[3]));
+      }
+      if (DBIAS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pbias[v][i] = add2(pbias[v][i], d[i]);
+      }
+    }
+  }
+  // block reduction: three passes through the same [nwarps][D] shared buffer
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? a.dw : (which == 1 ? a.db : (DBIAS ? a.dbias : nullptr));
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        upk2(which == 0 ? pdw[v][i] : (which == 1 ? pdb[v][i] : pbias[v][i]), lo, hi);
+        *reinterpret_cast<float2*>(&red[warp * D + (v * 32 + lane) * 8 + 2 * i]) = make_float2(lo, hi);
+      }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += red[w * D + c];
+      atomicAdd(dst + c, s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // colsum
 // ------------------------------------------------------------------------------------------------------------------
@@ -747,6 +899,34 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
       CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
       smem_set = 120 * 1024;
     }
+  }
+  // plain bf16, D = 768 (the reference model): packed-math specialisations for the four feature combinations the engine uses
+  if (a.z.lo == nullptr && a.dz.lo == nullptr && D == 768 && a.dw != nullptr && a.db != nullptr) {
+    const bool f_do = a.drop_out.thresh16 != 0, f_dd = a.dz_drop.hi != nullptr, f_g = a.gelu_u.hi != nullptr, f_b = a.dbias != nullptr;
+    const int combo = (f_do ? 1 : 0) | (f_dd ? 2 : 0) | (f_g ? 4 : 0) | (f_b ? 8 : 0);
+    const bool plain_aux = (!f_dd || a.dz_drop.lo == nullptr) && (!f_g || a.gelu_u.lo == nullptr);
+#define LNB_FAST(DO, DD, GE, DB)                                                                                              \
+  {                                                                                                                           \
+    static bool set = false;                                                                                                  \
+    if (!set) {                                                                                                               \
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_fast_kernel<3, DO, DD, GE, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); \
+      set = true;                                                                                                             \
+    }                                                                                                                         \
+    layernorm_bwd_fast_kernel<3, DO, DD, GE, DB><<<grid, 128, smem, st>>>(a);                                                 \
+    CLIPDLM_CUDA_OK(cudaGetLastError());                                                                                      \
+    return 0;                                                                                                                 \
+  }
+    if (plain_aux) {
+      switch (combo) {
+        case 8: LNB_FAST(false, false, false, true)     // sa_layer_norm: + out_lin bias gradient
+        case 10: LNB_FAST(false, true, false, true)     // output_layer_norm (train): dropped copy + lin2 bias gradient
+        case 12: LNB_FAST(false, false, true, true)     // vocab_layer_norm: * gelu'(u) + vocab_transform bias gradient
+        case 1: LNB_FAST(true, false, false, false)     // embedding LayerNorm (train)
+        case 0: LNB_FAST(false, false, false, false)    // embedding LayerNorm (eval / p = 0)
+        default: break;
+      }
+    }
+#undef LNB_FAST
   }
   DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 128, smem, st>>>(a));
   CLIPDLM_CUDA_OK(cudaGetLastError());
