@@ -238,6 +238,89 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(CBfPtr z, const floa
   }
 }
 
+// Plain-bf16, D = 768 specialisation of the forward: persistent warps, rows streamed through a per-warp bulk-copy ring, packed
+// fp32 math, w / b held in registers.  (The generic kernel: one row per warp, 319 instructions per row, latency-exposed loads.)
+constexpr int LNF_STAGES = 4;
+template <bool F32OUT>
+__global__ void __launch_bounds__(256, 2) layernorm_fwd_fast_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w,
+                                                                    const float* __restrict__ b, float eps, long long rows,
+                                                                    __nv_bfloat16* __restrict__ y, float* __restrict__ y_f32) {
+  constexpr int D = 768, NV = 3, NW = 8;
+  constexpr uint32_t row_bytes = D * 2;
+  extern __shared__ __align__(16) uint8_t lnf_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = lnf_smem + (size_t)warp * LNF_STAGES * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnf_smem + (size_t)NW * LNF_STAGES * row_bytes) + warp * LNF_STAGES;
+  const long long row0 = (long long)blockIdx.x * NW + warp, row_step = (long long)gridDim.x * NW;
+  if (lane == 0) {
+    for (int s = 0; s < LNF_STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    for (int s = 0; s < LNF_STAGES; ++s)
+      if (row0 + s * row_step < rows) {
+        mbar_arrive_expect_tx(&bars[s], row_bytes);
+        bulk_load_1d(ring + (size_t)s * row_bytes, z + (size_t)(row0 + s * row_step) * D, row_bytes, &bars[s]);
+      }
+  }
+  __syncwarp();
+  f32x2 W[NV][4], B[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float wv[8], bv[8];
+    load8_f32(w + (v * 32 + lane) * 8, wv);
+    load8_f32(b + (v * 32 + lane) * 8, bv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { W[v][i] = pk2(wv[2 * i], wv[2 * i + 1]); B[v][i] = pk2(bv[2 * i], bv[2 * i + 1]); }
+  }
+  constexpr float inv_d = 1.0f / (float)D;
+  int stage = 0; uint32_t phase = 0;
+  for (long long row = row0; row < rows; row += row_step) {
+    f32x2 X[NV][4];
+    mbar_wait(&bars[stage], phase);
+    {
+      const uint8_t* sz = ring + (size_t)stage * row_bytes;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint4 xr = *reinterpret_cast<const uint4*>(sz + (v * 32 + lane) * 16);
+        X[v][0] = bf2_to_f2(xr.x); X[v][1] = bf2_to_f2(xr.y); X[v][2] = bf2_to_f2(xr.z); X[v][3] = bf2_to_f2(xr.w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && row + LNF_STAGES * row_step < rows) {
+      mbar_arrive_expect_tx(&bars[stage], row_bytes);
+      bulk_load_1d(ring + (size_t)stage * row_bytes, z + (size_t)(row + LNF_STAGES * row_step) * D, row_bytes, &bars[stage]);
+    }
+    if (++stage == LNF_STAGES) { stage = 0; phase ^= 1; }
+    f32x2 acc = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc = add2(acc, X[v][i]);
+    const float mean = warp_sum(hsum2(acc)) * inv_d;
+    const f32x2 nmean = pk2(-mean, -mean);
+    acc = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { X[v][i] = add2(X[v][i], nmean); acc = fma2(X[v][i], X[v][i], acc); }
+    const float rstd = rsqrtf(warp_sum(hsum2(acc)) * inv_d + eps);
+    const f32x2 rstd2 = pk2(rstd, rstd);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = (size_t)row * D + (v * 32 + lane) * 8;
+      f32x2 o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = fma2(mul2(X[v][i], rstd2), W[v][i], B[v][i]);   // same rounding order as the generic kernel
+      if (y != nullptr) *reinterpret_cast<uint4*>(y + off) = make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3]));
+      if (F32OUT) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) upk2(o[i], f[2 * i], f[2 * i + 1]);
+        store8_f32(y_f32 + off, f);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm backward (+ fused dropout masks, gelu', bias column sums)
 // ------------------------------------------------------------------------------------------------------------------
@@ -865,8 +948,24 @@ int embed_bwd_dispatch(const clipdlm_bf_t* dz, int R, int B, int Ltxt, int L, in
 int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b, float eps, long long rows, int D, const clipdlm_bf_t* y,
                            float* y_f32, unsigned long long seed, uint32_t site, float p, cudaStream_t st) {
   CLIPDLM_CHECK(z && z->hi && w && b && rows > 0 && ((y && y->hi) || y_f32), "layernorm_fwd: bad arguments");
-  const int grid = (int)((rows + 7) / 8);
   const DropoutCfg d = make_drop(seed, site, p);
+  if (z->lo == nullptr && (!y || y->lo == nullptr) && D == 768 && d.thresh16 == 0 && rows >= 64) {
+    const size_t smem = (size_t)8 * LNF_STAGES * 768 * 2 + 8 * LNF_STAGES * sizeof(uint64_t);
+    static bool set = false;
+    if (!set) {
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_fwd_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_fwd_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set = true;
+    }
+    const long long want = (rows + 7) / 8;
+    const int fgrid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
+    __nv_bfloat16* yh = y ? (__nv_bfloat16*)y->hi : nullptr;
+    if (y_f32 != nullptr) layernorm_fwd_fast_kernel<true><<<fgrid, 256, smem, st>>>((const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, y_f32);
+    else layernorm_fwd_fast_kernel<false><<<fgrid, 256, smem, st>>>((const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, nullptr);
+    CLIPDLM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  const int grid = (int)((rows + 7) / 8);
   DISPATCH_NV(D, layernorm_fwd_kernel<NV><<<grid, 256, 0, st>>>(cbf(z), w, b, eps, rows, D, mbf(y), y_f32, d));
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
