@@ -101,7 +101,7 @@ __device__ __forceinline__ void st_row64(__nv_bfloat16* p, bool al32, const uint
   if (al32) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + h * 16), "r"(r[h * 8 + 0]), "r"(r[h * 8 + 1]),
+      asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + h * 16), "r"(r[h * 8 + 0]), "r"(r[h * 8 + 1]),
                    "r"(r[h * 8 + 2]), "r"(r[h * 8 + 3]), "r"(r[h * 8 + 4]), "r"(r[h * 8 + 5]), "r"(r[h * 8 + 6]), "r"(r[h * 8 + 7])
                    : "memory");
   } else {
@@ -678,26 +678,41 @@ __global__ void __launch_bounds__(256) softmax_grad_inplace_kernel(__nv_bfloat16
                                                                    const float* __restrict__ lse, const int* __restrict__ targets, int tgt_period,
                                                                    float scale, float log2_scale) {
   constexpr float LOG2E = 1.4426950408889634f;
-  const long long vec_per_row = ld >> 3;
-  const long long total = (long long)M * vec_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / vec_per_row);
-    const int n0 = (int)(i - (long long)m * vec_per_row) << 3;
-    uint4* ptr = reinterpret_cast<uint4*>(x + (long long)m * ld + n0);
-    if (n0 >= N) { *ptr = make_uint4(0u, 0u, 0u, 0u); continue; }
-    const uint4 raw = *ptr;
+  constexpr int U = 5;   // 16-byte vectors in flight per thread (5 x 2048 threads x 16 B = 160 KB per SM outstanding)
+  const int vec_per_row = (int)(ld >> 3);
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {   // one row per block iteration: no index divisions, lse / target read once
+    uint4* row = reinterpret_cast<uint4*>(x + (long long)m * ld);
     const float nb = fmaf(-lse[m], LOG2E, log2_scale);
     const int tgt = targets[m % tgt_period];
-    float v[8];
-    { float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
-      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
+    for (int v0 = threadIdx.x; v0 < vec_per_row; v0 += 256 * U) {
+      uint4 raw[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float p = ex2_ftz(fmaf(v[j], LOG2E, nb));
-      if (n0 + j == tgt) p -= scale;
-      v[j] = (n0 + j) < N ? p : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int vi = v0 + u * 256;
+        raw[u] = (vi < vec_per_row && vi * 8 < N) ? row[vi] : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int vi = v0 + u * 256;
+        if (vi >= vec_per_row) continue;
+        const int n0 = vi * 8;
+        if (n0 >= N) { row[vi] = make_uint4(0u, 0u, 0u, 0u); continue; }
+        float v[8];
+        { float2 a = unpack_bf16x2(raw[u].x), b = unpack_bf16x2(raw[u].y), c = unpack_bf16x2(raw[u].z), d = unpack_bf16x2(raw[u].w);
+          v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = ex2_ftz(fmaf(v[j], LOG2E, nb));
+        if ((unsigned)(tgt - n0) < 8u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (n0 + j == tgt) v[j] -= scale;
+        }
+        if (n0 + 8 > N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (n0 + j) < N ? v[j] : 0.f;
+        }
+        row[vi] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
     }
-    *ptr = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -707,9 +722,8 @@ int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, cons
   CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "softmax_grad_inplace: buffer must be 16-byte aligned");
   int sms = 148;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const long long total = (long long)M * (ld >> 3);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 16LL * sms) blocks = 16LL * sms;
+  long long blocks = M;
+  if (blocks > 8LL * sms) blocks = 8LL * sms;
   softmax_grad_inplace_kernel<<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)logits, ld, M, N, lse, targets, tgt_period, scale,
                                                                 scale > 0.f ? log2f(scale) : -INFINITY);
   CLIPDLM_CUDA_OK(cudaGetLastError());

@@ -99,7 +99,7 @@ class DistilBertModel:
     """
 
     def __init__(self, embedding=None, projection=None, config=None, hp: Optional[dict] = None, precision: str = "bf16",
-                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 4096):
+                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192):
         lib = L.load()
         if not torch.cuda.is_available():
             raise L.ClipdlmError("clipdlm needs a CUDA device (sm_100a); there is no CPU fallback")
