@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(BWD ? 384 : 512, 1) attn_ring_kernel(const __g
   for (uint32_t off = threadIdx.x * 16; off < (uint32_t)a.stages * stage_bytes + 1024; off += blockDim.x * 16)
     *reinterpret_cast<uint4*>(ring + off) = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();
     for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(BWD ? 384 : 512, 1) attn_ring_kernel(const __g
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA) writes
   __syncthreads();
+  pdl_wait();
 
   if (warp == a.consumers) {
     // ===================================== TMA producer =====================================
@@ -691,8 +693,7 @@ static int launch_ring(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, cons
   }
   const long long tasks = (long long)R * H;
   const int grid = (int)(tasks < num_sms() ? tasks : num_sms());
-  attn_ring_kernel<BWD><<<grid, (a.consumers + 1) * 32, smem, st>>>(tm_qkv, tm_do, a);
-  CLIPDLM_CUDA_OK(cudaGetLastError());
+  CLIPDLM_CUDA_OK(launch_pdl(attn_ring_kernel<BWD>, dim3(grid), dim3((a.consumers + 1) * 32), smem, st, tm_qkv, tm_do, a));
   return 0;
 }
 

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
     for (uint32_t off = threadIdx.x * 16; off < zbytes; off += AU_THREADS * 16) *reinterpret_cast<uint4*>(z0 + off) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();
     mbar_init(in_full, 1); mbar_init(in_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(t_empty, 4);
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const long long my_groups = a.groups > blockIdx.x ? (a.groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
@@ -343,8 +345,7 @@ int launch_attn_umma(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const 
   }
   const long long want = (BWD ? 2LL : 4LL) * num_sms();
   const int grid = (int)(a.groups < want ? a.groups : want);
-  attn_umma_kernel<BWD><<<grid, AU_THREADS, smem, st>>>(tm_qkv, tm_do, a);
-  CLIPDLM_CUDA_OK(cudaGetLastError());
+  CLIPDLM_CUDA_OK(launch_pdl(attn_umma_kernel<BWD>, dim3(grid), dim3(AU_THREADS), smem, st, tm_qkv, tm_do, a));
   return 0;
 }
 template int launch_attn_umma<false>(const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int, int, __nv_bfloat16*, const DropoutCfg&,

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace clipdlm {
 
@@ -172,6 +173,28 @@ __device__ __forceinline__ float dgelu_f(float x) {
   const float cdf = x >= 0.f ? 1.0f - h : h;
   return fmaf(x, pdf, cdf);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the persistent kernels of the step are launched with the programmatic-stream-serialization
+// attribute, announce at their very start that their successor may be scheduled (its CTAs become resident as ours retire and
+// run their prologue - barrier init, TMEM allocation, descriptor prefetch - under our tail), and wait for their predecessor's
+// memory to be complete and visible before the first global access.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction, a 64-bit register pair per operand)

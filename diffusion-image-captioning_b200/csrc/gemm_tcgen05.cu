@@ -279,6 +279,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const int unit_stride = CG == 2 ? (int)num_clusters_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
+    pdl_launch_dependents();
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB0);
     if (g.nparts > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
   }
@@ -295,6 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits + TMEM allocation visible (pair-wide for CG = 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch global memory
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -845,11 +847,13 @@ static int launch_gemm_cg(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Geo<CG>::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_dbg_flags & 512u ? 1 : 2;   // debug bit 9: no programmatic dependent launch
   CLIPDLM_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, ga));
   return 0;
 }

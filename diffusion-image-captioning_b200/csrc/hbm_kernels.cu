@@ -252,9 +252,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_fwd_fast_kernel(const __nv_b
   uint8_t* ring = lnf_smem + (size_t)warp * LNF_STAGES * row_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(lnf_smem + (size_t)NW * LNF_STAGES * row_bytes) + warp * LNF_STAGES;
   const long long row0 = (long long)blockIdx.x * NW + warp, row_step = (long long)gridDim.x * NW;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (lane == 0) {
     for (int s = 0; s < LNF_STAGES; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
+  }
+  pdl_wait();
+  if (lane == 0) {
     for (int s = 0; s < LNF_STAGES; ++s)
       if (row0 + s * row_step < rows) {
         mbar_arrive_expect_tx(&bars[s], row_bytes);
@@ -468,6 +472,7 @@ template <int NV, bool DROP_OUT, bool DZ_DROP, bool GELU, bool DBIAS>
 __global__ void __launch_bounds__(128, 3) layernorm_bwd_fast_kernel(const LnBwdArgs a) {
   extern __shared__ __align__(16) uint8_t lnb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   constexpr int nwarps = 4;
   const int D = a.D;
   const uint32_t row_bytes = (uint32_t)D * 2;
@@ -487,6 +492,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_bwd_fast_kernel(const LnBwdA
     bulk_load_1d(dst, a.z.hi + (size_t)row * D, row_bytes, &bars[s]);
     bulk_load_1d(dst + row_bytes, a.dy.hi + (size_t)row * D, row_bytes, &bars[s]);
   };
+  pdl_wait();
   if (lane == 0) {
     for (int s = 0; s < LNB_STAGES; ++s)
       if (row0 + s * row_step < a.rows) issue(s, row0 + s * row_step);
@@ -960,9 +966,8 @@ int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b
     const long long want = (rows + 7) / 8;
     const int fgrid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
     __nv_bfloat16* yh = y ? (__nv_bfloat16*)y->hi : nullptr;
-    if (y_f32 != nullptr) layernorm_fwd_fast_kernel<true><<<fgrid, 256, smem, st>>>((const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, y_f32);
-    else layernorm_fwd_fast_kernel<false><<<fgrid, 256, smem, st>>>((const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, nullptr);
-    CLIPDLM_CUDA_OK(cudaGetLastError());
+    if (y_f32 != nullptr) CLIPDLM_CUDA_OK(launch_pdl(layernorm_fwd_fast_kernel<true>, dim3(fgrid), dim3(256), smem, st, (const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, y_f32));
+    else CLIPDLM_CUDA_OK(launch_pdl(layernorm_fwd_fast_kernel<false>, dim3(fgrid), dim3(256), smem, st, (const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, (float*)nullptr));
     return 0;
   }
   const int grid = (int)((rows + 7) / 8);
@@ -1011,8 +1016,7 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
       CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_fast_kernel<3, DO, DD, GE, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); \
       set = true;                                                                                                             \
     }                                                                                                                         \
-    layernorm_bwd_fast_kernel<3, DO, DD, GE, DB><<<grid, 128, smem, st>>>(a);                                                 \
-    CLIPDLM_CUDA_OK(cudaGetLastError());                                                                                      \
+    CLIPDLM_CUDA_OK(launch_pdl(layernorm_bwd_fast_kernel<3, DO, DD, GE, DB>, dim3(grid), dim3(128), smem, st, a));            \
     return 0;                                                                                                                 \
   }
     if (plain_aux) {
