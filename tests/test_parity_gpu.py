@@ -231,6 +231,33 @@ def test_validate_and_state_dict_roundtrip(pkg):
     assert torch.equal(model2.flat, model.flat) and torch.equal(model2.shadow_hi, model.shadow_hi)
 
 
+@pytest.mark.parametrize("shape", ["bert-large-shaped", "bert-base-depth"])
+def test_other_model_shapes_vs_oracle(pkg, shape):
+    """BASELINE.json configs 2 / 5: the 12-layer ('bert-base') depth and the bert-large geometry (d = 1024, 16 heads, FFN 4096,
+    MAX_LENGTH = 64 -> L = 66: generic LayerNorm, fp32 SIMT attention, 64-row lm_head gather) against the oracle, parity mode."""
+    if shape == "bert-large-shaped":
+        hp = golden_hp(N_LAYERS=2, DIM=1024, N_HEADS=16, HIDDEN_DIM=4096, IN_CHANNEL=1024, MAX_LENGTH=64, BATCH_SIZE=2, SAMPLE_SIZE=3)
+    else:
+        hp = golden_hp(N_LAYERS=12, BATCH_SIZE=2, SAMPLE_SIZE=2)
+    P = O.init_params(hp, seed=7, closed_form=False)
+    ML, D, B, S = hp["MAX_LENGTH"], hp["DIM"], hp["BATCH_SIZE"], hp["SAMPLE_SIZE"]
+    batch = O.synthetic_batch(hp, seed=8, ragged=True)
+    gen = torch.Generator().manual_seed(9)
+    t = torch.randint(0, 1000, (S, 1, 1), generator=gen)
+    n_t = torch.randn(B, ML, D, generator=gen); n_1 = torch.randn(B, ML, D, generator=gen)
+    ref = O.train_func({k: v.clone() for k, v in P.items()}, None, batch, hp, O.alpha_cumprod(hp), False, t=t, noise_t=n_t, noise_1=n_1)
+    for precision, tol in (("bf16x3", 1e-3), ("bf16", 2e-2)):
+        model = make_model(pkg, hp, precision=precision, P={k: v.clone() for k, v in P.items()}).train()
+        tr = pkg.AdamW(model.parameters(), lr=1e-4)
+        got = pkg.train_func(model, tr, to_dev(batch), t=t, noise_t=n_t, noise_1=n_1)
+        for x, y in zip(got, ref):
+            assert abs(x.item() - y.item()) < tol * abs(y.item()), (precision, x.item(), y.item())
+        assert bool(torch.isfinite(model.flat).all())
+        model.eval()
+        ids, _ = pkg.sample(model, batch["image_clip"].to(DEV), n_steps=2)
+        assert tuple(ids.shape) == (B, ML)
+
+
 # --------------------------------------------------------------------------------------------------- full size (BASELINE cfg 2 / 4)
 def test_full_size_properties(pkg):
     hp = pkg.default_hparams(BATCH_SIZE=512, SAMPLE_SIZE=100)

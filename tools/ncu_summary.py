@@ -19,8 +19,9 @@ def category(name: str) -> str:
     if m:
         amaj, bmaj, epi = (int(x) for x in m.groups())
         return {1: "gemm_wgrad", 2: "gemm_lse", 3: "gemm_smgrad"}.get(epi, "gemm_dgrad" if bmaj else "gemm_fwd")
-    for key, cat in (("softmax_grad_inplace", "gemm_smgrad"), ("attn_umma_kernel<(bool)0", "attn_fwd"), ("attn_umma_kernel<(bool)1", "attn_bwd"),
-                     ("attn_ring_kernel<(bool)0", "attn_fwd"), ("attn_ring_kernel<(bool)1", "attn_bwd"), ("attn_fwd", "attn_fwd"),
+    name = name.replace("(bool)", "")
+    for key, cat in (("softmax_grad_inplace", "gemm_smgrad"), ("attn_umma_kernel<0", "attn_fwd"), ("attn_umma_kernel<1", "attn_bwd"),
+                     ("attn_ring_kernel<0", "attn_fwd"), ("attn_ring_kernel<1", "attn_bwd"), ("attn_fwd", "attn_fwd"),
                      ("attn_bwd", "attn_bwd"), ("layernorm_fwd", "ln_fwd"), ("layernorm_bwd", "ln_bwd"), ("embed_fwd", "embed"),
                      ("embed_loss", "loss"), ("lse_combine", "loss"), ("colsum", "colsum"), ("adamw", "adamw")):
         if key in name:
