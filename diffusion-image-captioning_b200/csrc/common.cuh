@@ -164,7 +164,7 @@ __device__ __forceinline__ float phi_tail(float a) {   // a >= 0
   return ex2_ftz(p);
 }
 __device__ __forceinline__ float gelu_f(float x) {
-  const float a = fabsf(x);
+  const float a = fminf(fabsf(x), 5.6f);   // clamped in the product too (|error| < 7e-8 beyond 5.6): bit-identical to gelu2 below
   return fmaf(-a, phi_tail(a), fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float dgelu_f(float x) {
@@ -209,6 +209,42 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 __device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 __device__ __forceinline__ uint32_t f2_to_bf2(f32x2 v) { float a, b; upk2(v, a, b); return pack_bf16x2(a, b); }
 __device__ __forceinline__ float hsum2(f32x2 v) { float a, b; upk2(v, a, b); return a + b; }
+
+// Packed-pair versions of gelu_f / dgelu_f above (same polynomial, evaluated in -a so the final product needs no negation):
+// 6.5 / 10 instructions per element instead of 10 / 16 - the GELU epilogues of the K = 768 GEMMs are issue-bound.
+__device__ __forceinline__ f32x2 phi_tail2(float x0, float x1, f32x2& an) {   // returns (Phi(-|x0|), Phi(-|x1|)); an = -min(|x|, 5.6)
+  an = pk2(fmaxf(-fabsf(x0), -5.6f), fmaxf(-fabsf(x1), -5.6f));
+  f32x2 p = fma2(an, pk2(1.775593238e-05f, 1.775593238e-05f), pk2(6.477629528e-04f, 6.477629528e-04f));
+  p = fma2(an, p, pk2(7.724055995e-03f, 7.724055995e-03f));
+  p = fma2(an, p, pk2(5.292675105e-02f, 5.292675105e-02f));
+  p = fma2(an, p, pk2(-4.590827311e-01f, -4.590827311e-01f));
+  p = fma2(an, p, pk2(1.151116857e+00f, 1.151116857e+00f));
+  p = fma2(an, p, pk2(-1.0f, -1.0f));
+  float p0, p1;
+  upk2(p, p0, p1);
+  return pk2(ex2_ftz(p0), ex2_ftz(p1));
+}
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1) {
+  f32x2 an;
+  const f32x2 h = phi_tail2(x0, x1, an);
+  return fma2(an, h, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));   // max(x, 0) - |x| Phi(-|x|)
+}
+__device__ __forceinline__ f32x2 dgelu2(float x0, float x1) {
+  f32x2 an;
+  const f32x2 h = phi_tail2(x0, x1, an);
+  const f32x2 x = pk2(x0, x1);
+  const f32x2 arg = fma2(mul2(x, x), pk2(-0.72134752044448170f, -0.72134752044448170f), pk2(-1.32574806473616470f, -1.32574806473616470f));
+  float a0, a1;
+  upk2(arg, a0, a1);
+  const f32x2 pdf = pk2(ex2_ftz(a0), ex2_ftz(a1));
+  // Phi(x) = 0.5 + copysign(0.5 - h, x)   (h = Phi(-|x|) <= 0.5)
+  float t0, t1;
+  upk2(fma2(h, pk2(-1.f, -1.f), pk2(0.5f, 0.5f)), t0, t1);
+  t0 = __uint_as_float(__float_as_uint(t0) | (__float_as_uint(x0) & 0x80000000u));
+  t1 = __uint_as_float(__float_as_uint(t1) | (__float_as_uint(x1) & 0x80000000u));
+  const f32x2 cdf = add2(pk2(t0, t1), pk2(0.5f, 0.5f));
+  return fma2(x, pdf, cdf);
+}
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier (shared::cta) with a bounded spin: a protocol bug traps instead of hanging the GPU.

@@ -202,7 +202,8 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       for (int j = 0; j < 8; ++j) {
         float4 b4;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
-        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        upk2(add2(pk2(v[4 * j], v[4 * j + 1]), pk2(b4.x, b4.y)), v[4 * j], v[4 * j + 1]);
+        upk2(add2(pk2(v[4 * j + 2], v[4 * j + 3]), pk2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
       }
     }
     if (DROP) {
@@ -217,9 +218,8 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
     if (AUX == 2) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack_bf16x2(cur[j]);
-        v[2 * j] *= dgelu_f(f.x);
-        v[2 * j + 1] *= dgelu_f(f.y);
+        const f32x2 r = mul2(pk2(v[2 * j], v[2 * j + 1]), dgelu2(__uint_as_float(cur[j] << 16), __uint_as_float(cur[j] & 0xffff0000u)));
+        upk2(r, v[2 * j], v[2 * j + 1]);
       }
     } else if (AUX == 1) {
       row_unpack<true>(cur, v);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       if (DUAL) {
         if (!(g.dbg & 128u)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          for (int j = 0; j < 16; ++j) upk2(gelu2(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
         }
         row_store_pair(out2_row + cc * 32, nullptr, true, v);
       }
