@@ -89,6 +89,7 @@ class LossCfg(C.Structure):
         ("R_total", i64),
         ("rounding_weight", f32), ("backward", i32),
         ("target", c_p), ("target_rows", i32),
+        ("row_scale_self", c_p), ("row_scale_export", c_p), ("export_engine", c_p),
     ]
 
 
@@ -143,6 +144,8 @@ _SIGS = {
     "clipdlm_engine_forward": (C.c_int, [c_p, C.POINTER(Pass), c_p]),
     "clipdlm_engine_lm_head": (C.c_int, [c_p, c_p, i64, c_p, c_p]),
     "clipdlm_engine_loss_backward": (C.c_int, [c_p, C.POINTER(LossCfg), c_p, c_p]),
+    "clipdlm_engine_cfg_mix": (C.c_int, [c_p, c_p, c_p, f32, c_p]),
+    "clipdlm_engine_backward": (C.c_int, [c_p, c_p]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
     "clipdlm_engine_profile": (C.c_int, [c_p, i32]),
     "clipdlm_engine_profile_read": (C.c_int, [c_p, c_p, i32]),

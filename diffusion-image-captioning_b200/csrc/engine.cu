@@ -14,6 +14,9 @@ int num_sms();
 int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st);
 int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
                          int* argmax, double* loss_acc, double scale, cudaStream_t st);
+int cfg_mix_dispatch(const clipdlm_bf_t* xu, const clipdlm_bf_t* xg, const int* guided, float w, int R, int L, int D, cudaStream_t st);
+int row_scale_dispatch(const clipdlm_bf_t* g, const float* s_self, const clipdlm_bf_t* ex, const float* s_ex, int R, int L, int D,
+                       cudaStream_t st);
 int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, const float* lse, const int* targets, int tgt_period, float scale,
                                   cudaStream_t st);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
@@ -375,60 +378,15 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   return 0;
 }
 
-static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, double* losses, cudaStream_t st) {
+// Backward of the last forward from the upstream gradient d(x_out) held in e->g0: transform head, blocks, embeddings.
+static int backward_from_g0(clipdlm_engine* e, cudaStream_t st) {
   const clipdlm_config_t& c = e->cfg;
-  CLIPDLM_CHECK(e->have_fwd, "loss_backward without a preceding forward");
-  CLIPDLM_CHECK(lc != nullptr && losses != nullptr, "null loss config / output");
-  CLIPDLM_CHECK(e->last.ids != nullptr || (lc->target && !lc->use_prob_loss), "loss needs the caption ids of the pass");
-  CLIPDLM_CHECK(!lc->backward || (e->last.train || e->training), "backward needs a training engine");
-  CLIPDLM_CHECK(!lc->backward || e->training, "engine was created without training buffers");
   const clipdlm_pass_t& p = e->last;
   const int R = p.R, B = p.B, L = e->L, Ltxt = e->Ltxt, D = c.dim, F = c.hidden_dim, NL = c.n_layers;
-  const int T = R * L, M16 = R * Ltxt;
-  const bool bwd = lc->backward != 0;
+  const int T = R * L;
   const bool train = p.train != 0;
   const float pdrop = train ? c.dropout : 0.f, padrop = train ? c.attn_dropout : 0.f;
-  const long long R_total = lc->R_total > 0 ? lc->R_total : R;
-  const bool mean_kind = lc->loss_kind == 0 || lc->loss_kind == 2;
-  const double ce_scale = mean_kind ? 1.0 / (double)R_total : 1.0 / (double)lc->batch_size;  // CLIP-DDPM.py:437 vs :439-440
-
-  // 1. embedding-space loss (+ its gradient written over every row of g0)
-  if (lc->use_embed_loss || bwd)
-    RUNP(CLIPDLM_PROF_LOSS, 0, ((double)M16 + (bwd ? T : 0)) * D * (e->pair ? 4.0 : 2.0) + (double)M16 * D * 4, embed_loss_dispatch(&e->xo, e->bufs.emb_table, p.ids, lc->target, lc->target_rows, R, B, Ltxt, L, D, lc->loss_kind, R_total, lc->batch_size,
-                            lc->use_embed_loss ? 1.f : 0.f, lc->use_embed_loss ? &losses[0] : nullptr, bwd ? &e->g0 : nullptr, st));
-  // 2. rounding cross-entropy through the frozen lm_head
-  if (lc->use_prob_loss) {
-    // plain bf16 + backward: the LSE pass keeps its logits (bf16, in the d(logits) buffer) and an HBM-bound pass turns them into the
-    // softmax-CE gradient in place - 8 GB of traffic instead of recomputing the 3 TFLOP lm_head GEMM.  Split precision (parity
-    // mode) recomputes the vocabulary tiles with fp32 accumulators instead (SMGRAD epilogue).
-    const bool store_logits = bwd && !e->pair;
-    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st, store_logits ? e->dlog.hi : nullptr);
-    if (rc) return rc;
-    if (bwd) {
-      Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
-      clipdlm_gemm_t g;
-      if (store_logits) {
-        RUNP(CLIPDLM_PROF_GEMM_SMGRAD, 0, 4.0 * M16 * (double)e->ldl,
-             softmax_grad_inplace_dispatch(e->dlog.hi, e->ldl, M16, c.vocab, e->lse, p.ids, B * Ltxt, (float)(lc->rounding_weight * ce_scale), st));
-      } else {
-        g = gemm_desc(e->xo, D, 0, emb, D, 0, M16, c.vocab, D);
-        g.gather_len = Ltxt; g.gather_stride = L;
-        g.epilogue = CLIPDLM_EPI_SMGRAD;
-        g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
-        g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
-        g.grad_scale = (float)(lc->rounding_weight * ce_scale);
-        RUNG(g);
-      }
-      // d x_out[:, :Ltxt] += dlogits[M16, V] E[V, D]
-      g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
-      g.out_hi = e->g0.hi; g.out_lo = e->g0.lo; g.ldo = D;
-      g.res_hi = e->g0.hi; g.res_lo = e->g0.lo; g.ldr = D;
-      g.scatter_len = Ltxt; g.scatter_stride = L;
-      RUNG(g);
-    }
-  }
-  if (!bwd) return 0;
-
+  (void)Ltxt;
   // 3. MLM transform head: x_out = LN_v(gelu(h W_t^T + b_t))
   RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&e->gv, &e->g0, param(e, CLIPDLM_P_VLN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_VLN_W),
                              grad(e, CLIPDLM_P_VLN_B), 0, 0, 0.f, nullptr, 0, 0.f, &e->uv, grad(e, CLIPDLM_P_VT_B), st));
@@ -485,6 +443,70 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
   RUN(small_linear_bwd_dispatch(p.image_clip, e->d_img_proj, B, c.clip_dim, D, grad(e, CLIPDLM_P_IMG_W), grad(e, CLIPDLM_P_IMG_B), st));
   RUN(small_linear_bwd_dispatch(p.text_clip, e->d_txt_proj, B, c.clip_dim, D, grad(e, CLIPDLM_P_TXT_W), grad(e, CLIPDLM_P_TXT_B), st));
   return 0;
+}
+
+static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, double* losses, cudaStream_t st) {
+  const clipdlm_config_t& c = e->cfg;
+  CLIPDLM_CHECK(e->have_fwd, "loss_backward without a preceding forward");
+  CLIPDLM_CHECK(lc != nullptr && losses != nullptr, "null loss config / output");
+  CLIPDLM_CHECK(e->last.ids != nullptr || (lc->target && !lc->use_prob_loss), "loss needs the caption ids of the pass");
+  CLIPDLM_CHECK(!lc->backward || (e->last.train || e->training), "backward needs a training engine");
+  CLIPDLM_CHECK(!lc->backward || e->training, "engine was created without training buffers");
+  const clipdlm_pass_t& p = e->last;
+  const int R = p.R, B = p.B, L = e->L, Ltxt = e->Ltxt, D = c.dim, F = c.hidden_dim, NL = c.n_layers;
+  const int T = R * L, M16 = R * Ltxt;
+  const bool bwd = lc->backward != 0;
+  const bool train = p.train != 0;
+  const float pdrop = train ? c.dropout : 0.f, padrop = train ? c.attn_dropout : 0.f;
+  const long long R_total = lc->R_total > 0 ? lc->R_total : R;
+  const bool mean_kind = lc->loss_kind == 0 || lc->loss_kind == 2;
+  const double ce_scale = mean_kind ? 1.0 / (double)R_total : 1.0 / (double)lc->batch_size;  // CLIP-DDPM.py:437 vs :439-440
+
+  // 1. embedding-space loss (+ its gradient written over every row of g0)
+  if (lc->use_embed_loss || bwd)
+    RUNP(CLIPDLM_PROF_LOSS, 0, ((double)M16 + (bwd ? T : 0)) * D * (e->pair ? 4.0 : 2.0) + (double)M16 * D * 4, embed_loss_dispatch(&e->xo, e->bufs.emb_table, p.ids, lc->target, lc->target_rows, R, B, Ltxt, L, D, lc->loss_kind, R_total, lc->batch_size,
+                            lc->use_embed_loss ? 1.f : 0.f, lc->use_embed_loss ? &losses[0] : nullptr, bwd ? &e->g0 : nullptr, st));
+  // 2. rounding cross-entropy through the frozen lm_head
+  if (lc->use_prob_loss) {
+    // plain bf16 + backward: the LSE pass keeps its logits (bf16, in the d(logits) buffer) and an HBM-bound pass turns them into the
+    // softmax-CE gradient in place - 8 GB of traffic instead of recomputing the 3 TFLOP lm_head GEMM.  Split precision (parity
+    // mode) recomputes the vocabulary tiles with fp32 accumulators instead (SMGRAD epilogue).
+    const bool store_logits = bwd && !e->pair;
+    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st, store_logits ? e->dlog.hi : nullptr);
+    if (rc) return rc;
+    if (bwd) {
+      Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
+      clipdlm_gemm_t g;
+      if (store_logits) {
+        RUNP(CLIPDLM_PROF_GEMM_SMGRAD, 0, 4.0 * M16 * (double)e->ldl,
+             softmax_grad_inplace_dispatch(e->dlog.hi, e->ldl, M16, c.vocab, e->lse, p.ids, B * Ltxt, (float)(lc->rounding_weight * ce_scale), st));
+      } else {
+        g = gemm_desc(e->xo, D, 0, emb, D, 0, M16, c.vocab, D);
+        g.gather_len = Ltxt; g.gather_stride = L;
+        g.epilogue = CLIPDLM_EPI_SMGRAD;
+        g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
+        g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
+        g.grad_scale = (float)(lc->rounding_weight * ce_scale);
+        RUNG(g);
+      }
+      // d x_out[:, :Ltxt] += dlogits[M16, V] E[V, D]
+      g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
+      g.out_hi = e->g0.hi; g.out_lo = e->g0.lo; g.ldo = D;
+      g.res_hi = e->g0.hi; g.res_lo = e->g0.lo; g.ldr = D;
+      g.scatter_len = Ltxt; g.scatter_stride = L;
+      RUNG(g);
+    }
+  }
+  if (!bwd) return 0;
+  // classifier-free guidance: d(x_out) belongs to the MIX of two passes - scale our share, hand the other engine its share
+  if (lc->row_scale_self != nullptr || lc->export_engine != nullptr) {
+    CLIPDLM_CHECK(lc->export_engine == nullptr || (lc->export_engine->training && lc->export_engine->have_fwd && lc->export_engine->last.R == R &&
+                                                   lc->export_engine->pair == e->pair && lc->export_engine->L == L),
+                  "loss_backward: export engine must hold a training forward of the same shape");
+    RUNP(CLIPDLM_PROF_OTHER, 0, (double)T * D * (e->pair ? 4.0 : 2.0) * 3,
+         row_scale_dispatch(&e->g0, lc->row_scale_self, lc->export_engine ? &lc->export_engine->g0 : nullptr, lc->row_scale_export, R, L, D, st));
+  }
+  return backward_from_g0(e, st);
 }
 
 static int lm_head_impl(clipdlm_engine* e, float* logits, int64_t ld_logits, int32_t* argmax, cudaStream_t st) {
@@ -576,6 +598,19 @@ int clipdlm_engine_lm_head(clipdlm_engine_t* e, float* logits, int64_t ld_logits
 int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* lc, double* losses, clipdlm_stream stream) {
   CLIPDLM_CHECK(e != nullptr, "null engine");
   return loss_backward_impl(e, lc, losses, (cudaStream_t)stream);
+}
+int clipdlm_engine_cfg_mix(clipdlm_engine_t* eu, clipdlm_engine_t* eg, const int32_t* guided, float w, clipdlm_stream stream) {
+  CLIPDLM_CHECK(eu != nullptr && eg != nullptr && guided != nullptr, "cfg_mix: null argument");
+  CLIPDLM_CHECK(eu->have_fwd && eg->have_fwd && eu->last.R == eg->last.R && eu->L == eg->L && eu->cfg.dim == eg->cfg.dim && eu->pair == eg->pair,
+                "cfg_mix: the two engines must hold forward passes of the same shape");
+  clipdlm_engine* e = eu;
+  cudaStream_t st = (cudaStream_t)stream;
+  RUNP(CLIPDLM_PROF_OTHER, 0, 0, cfg_mix_dispatch(&eu->xo, &eg->xo, guided, w, eu->last.R, eu->L, eu->cfg.dim, st));
+  return 0;
+}
+int clipdlm_engine_backward(clipdlm_engine_t* e, clipdlm_stream stream) {
+  CLIPDLM_CHECK(e != nullptr && e->have_fwd && e->training, "engine_backward: needs a training engine with a forward pass");
+  return backward_from_g0(e, (cudaStream_t)stream);
 }
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e) { return e ? e->launches : -1; }
 

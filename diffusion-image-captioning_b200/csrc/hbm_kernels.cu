@@ -886,6 +886,44 @@ __global__ void keymask_kernel(const int* __restrict__ attn_mask, int R, int B, 
   km[idx] = bits;
 }
 
+// classifier-free guidance: mix of the guided / unguided encoder outputs, and per-row scaling of the upstream gradient
+__global__ void __launch_bounds__(256) cfg_mix_kernel(BfPtr xu, CBfPtr xg, const int* __restrict__ guided, float w, int L, int D, long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int vec_per_row = L * (D >> 3);
+  const int r = (int)(i / vec_per_row);
+  if (!guided[r]) return;
+  float a[8], b[8];
+  CBfPtr cu; cu.hi = xu.hi; cu.lo = xu.lo;
+  load8(cu, (size_t)i * 8, a);
+  load8(xg, (size_t)i * 8, b);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = (1.f + w) * b[k] - w * a[k];
+  store8(xu, (size_t)i * 8, a);
+}
+__global__ void __launch_bounds__(256) row_scale_kernel(BfPtr g, const float* __restrict__ s_self, BfPtr ex, const float* __restrict__ s_ex,
+                                                        int L, int D, long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int vec_per_row = L * (D >> 3);
+  const int r = (int)(i / vec_per_row);
+  float a[8], b[8];
+  CBfPtr cg; cg.hi = g.hi; cg.lo = g.lo;
+  load8(cg, (size_t)i * 8, a);
+  if (ex.hi != nullptr) {
+    const float se = s_ex != nullptr ? s_ex[r] : 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = a[k] * se;
+    store8(ex, (size_t)i * 8, b);
+  }
+  if (s_self != nullptr) {
+    const float ss = s_self[r];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= ss;
+    store8(g, (size_t)i * 8, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------------------------------------------
@@ -910,6 +948,22 @@ static inline int grid_1d(long long n, int threads, int max_blocks) {
     case 4: { constexpr int NV = 4; __VA_ARGS__; break; }                                         \
     default: CLIPDLM_CHECK(false, "unsupported model dim %d (need a multiple of 256, <= 1024)", (D)); \
   }
+
+int cfg_mix_dispatch(const clipdlm_bf_t* xu, const clipdlm_bf_t* xg, const int* guided, float w, int R, int L, int D, cudaStream_t st) {
+  CLIPDLM_CHECK(xu && xu->hi && xg && xg->hi && guided && R > 0 && D % 8 == 0, "cfg_mix: bad arguments");
+  const long long nvec = (long long)R * L * (D / 8);
+  cfg_mix_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(mbf(xu), cbf(xg), guided, w, L, D, nvec);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int row_scale_dispatch(const clipdlm_bf_t* g, const float* s_self, const clipdlm_bf_t* ex, const float* s_ex, int R, int L, int D,
+                       cudaStream_t st) {
+  CLIPDLM_CHECK(g && g->hi && R > 0 && D % 8 == 0, "row_scale: bad arguments");
+  const long long nvec = (long long)R * L * (D / 8);
+  row_scale_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(mbf(g), s_self, ex ? mbf(ex) : mbf(nullptr), s_ex, L, D, nvec);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st) {
   CLIPDLM_CHECK(e != nullptr && e->D % 256 == 0, "embed_fwd: bad descriptor / dim");

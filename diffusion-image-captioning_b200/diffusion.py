@@ -70,14 +70,32 @@ def _next_seed() -> int:
 
 def _loss_pass(model: DistilBertModel, eng, losses: torch.Tensor, slot: int, *, R: int, B: int, R_total: int, mode: int, ids32, mask32,
                image_clip, text_clip, backward: bool, seed: int, use_embed: bool, x_in=None, noise=None, coef_a=None, coef_b=None,
-               target=None, target_rows: int = 0, guided: bool = False):
+               target=None, target_rows: int = 0, guided: bool = False, cfg_rows: Optional[torch.Tensor] = None, eng_guided=None):
+    """One encoder pass + its loss terms (+ backward). cfg_rows (int32 [R], 1 = classifier-free-guided row) switches on the
+    guidance mix of CLIP-DDPM.py:313-317: a second, guided pass over the same rows in `eng_guided`, x_out mixed row-wise, the
+    gradient of the mixed output split between the two passes ((1 + w) to the guided one, -w / 1 to the unguided one)."""
     hp = model.hp
-    model._run_forward(eng, R=R, B=B, mode=mode, guided=guided, train=model.training, image_clip=image_clip, text_clip=text_clip,
-                       attn_mask=mask32, x_in=x_in, ids=ids32, noise=noise, coef_a=coef_a, coef_b=coef_b, drop_seed=seed)
+    lib = L.load()
+    fw = dict(R=R, B=B, mode=mode, train=model.training, image_clip=image_clip, text_clip=text_clip, attn_mask=mask32, x_in=x_in,
+              ids=ids32, noise=noise, coef_a=coef_a, coef_b=coef_b)
+    model._run_forward(eng, guided=guided, drop_seed=seed, **fw)
+    s_self = s_exp = None
+    if cfg_rows is not None:
+        w = float(hp["CLASSIFIER_FREE_WEIGHT"])
+        model._run_forward(eng_guided, guided=True, drop_seed=seed + 104729, **fw)   # the reference's second self.model(...) call draws its own dropout
+        with torch.cuda.device(model.device):
+            L.check(lib.clipdlm_engine_cfg_mix(eng, eng_guided, L.ptr(cfg_rows), w, model._stream()))
+        if backward:
+            gm = cfg_rows.to(torch.float32)
+            s_self = (1.0 - (1.0 + w) * gm).contiguous()   # unguided pass: 1 on plain rows, -w on guided rows
+            s_exp = ((1.0 + w) * gm).contiguous()          # guided pass: (1 + w) on guided rows, 0 elsewhere
     lc = L.LossCfg(LOSS_KIND[hp["LOSS_FUNC"]], 1 if use_embed else 0, 1 if hp["USE_PROB_LOSS"] else 0, hp["BATCH_SIZE"], R_total,
-                   float(hp["ROUNDING_WEIGHT"]), 1 if backward else 0, L.ptr(target), target_rows)
+                   float(hp["ROUNDING_WEIGHT"]), 1 if backward else 0, L.ptr(target), target_rows,
+                   L.ptr(s_self), L.ptr(s_exp), eng_guided if (cfg_rows is not None and backward) else None)
     with torch.cuda.device(model.device):
-        L.check(L.load().clipdlm_engine_loss_backward(eng, C.byref(lc), losses.data_ptr() + 8 * slot, model._stream()))
+        L.check(lib.clipdlm_engine_loss_backward(eng, C.byref(lc), losses.data_ptr() + 8 * slot, model._stream()))
+        if cfg_rows is not None and backward:
+            L.check(lib.clipdlm_engine_backward(eng_guided, model._stream()))
     if backward:
         model._grads_dirty = True
 
@@ -97,7 +115,7 @@ def _prep_batch(model, image_clip, text_clip, mask, idx):
 
 
 def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, loss_func=None, *, backward: Optional[bool] = None,
-         dropout_seed: Optional[int] = None):
+         dropout_seed: Optional[int] = None, classifier_mask: Optional[torch.Tensor] = None):
     """CLIP-DDPM.py:382-445. Same inputs / outputs: returns (x_t_loss, x_1_loss, ROUNDING_WEIGHT * (x_t_prob_loss + x_1_prob_loss))
     as 0-dim device tensors. `loss_func` is accepted for signature compatibility; the objective is `model.hp['LOSS_FUNC']`
     (a name) because the kernels implement the reference's four LOSS_FUNCs natively. backward=None => model.training and grad
@@ -110,9 +128,15 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
     assert tuple(mask.shape) == (B, ML) and tuple(idx.shape) == (B, ML)
     if loss_func is not None and getattr(loss_func, "__name__", loss_func) != hp["LOSS_FUNC"]:
         raise ValueError(f"loss_func {getattr(loss_func, '__name__', loss_func)} differs from hp['LOSS_FUNC'] = {hp['LOSS_FUNC']}")
-    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:
-        raise NotImplementedError("classifier-free guidance training (CLIP-DDPM.py:406-410) is not built yet (SURVEY 8f N1)")
     _need_cuda(x_t)
+    cfg = None
+    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:  # :406-410: per-row guidance draw; rows 0 / 1 pinned so that both kinds always occur
+        if classifier_mask is None:
+            classifier_mask = (torch.rand((S * B, 1)) > hp["CLASSIFIER_FREE_PROB"]).to(torch.float32)
+            classifier_mask[0] = 0
+            classifier_mask[1] = 1
+        cfg = (classifier_mask.reshape(-1) != 0).to(model.device, torch.int32).contiguous()
+        assert cfg.numel() == S * B
     if backward is None:
         backward = model.training and torch.is_grad_enabled()
     img, txt, mask32, ids32 = _prep_batch(model, image_clip, text_clip, mask, idx)
@@ -122,9 +146,9 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
         assert tuple(x_tgt.shape) == tuple(x_t.shape)  # :420
     spc = max(1, model.chunk_rows // B)
     eng = model._engine(min(S, spc) * B, B, backward or model.training)
+    eng_g = model._engine(min(S, spc) * B, B, backward or model.training, tag="g") if cfg is not None else None
     losses = torch.zeros(4, dtype=torch.float64, device=model.device)
     seed = _next_seed() if dropout_seed is None else int(dropout_seed)
-    row_elems = ML * D
     for ci, s0 in enumerate(range(0, S, spc)):
         s1 = min(S, s0 + spc)
         R = (s1 - s0) * B
@@ -134,14 +158,16 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
         else:
             target, trows = tgt_t[s0 * B:s1 * B], R
         _loss_pass(model, eng, losses, 0, R=R, B=B, R_total=S * B, mode=0, ids32=ids32, mask32=mask32, image_clip=img, text_clip=txt,
-                   backward=backward, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], x_in=xin, target=target, target_rows=trows)
+                   backward=backward, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], x_in=xin, target=target, target_rows=trows,
+                   cfg_rows=cfg[s0 * B:s1 * B].contiguous() if cfg is not None else None, eng_guided=eng_g)
     _loss_pass(model, eng, losses, 2, R=B, B=B, R_total=B, mode=0, ids32=ids32, mask32=mask32, image_clip=img, text_clip=txt,
                backward=backward, seed=seed + 7919, use_embed=hp["USE_X_1_LOSS"], x_in=x_132, target=x_032, target_rows=B)
     return _finish(model, losses)
 
 
 def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train: bool = True, *, t: Optional[torch.Tensor] = None,
-               noise_t: Optional[torch.Tensor] = None, noise_1: Optional[torch.Tensor] = None, dropout_seed: Optional[int] = None):
+               noise_t: Optional[torch.Tensor] = None, noise_1: Optional[torch.Tensor] = None, dropout_seed: Optional[int] = None,
+               noise_tgt: Optional[torch.Tensor] = None, classifier_mask: Optional[torch.Tensor] = None):
     """CLIP-DDPM.py:458-486: embed -> draw t -> q_sample x2 -> zero_grad -> loss -> backward -> AdamW step.
     Returns (l, x_t_loss, x_1_loss, prob_loss) as 0-dim device tensors (no host sync, like the reference's loop :530-533).
 
@@ -166,10 +192,10 @@ def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train:
         x_0 = model.embedding(ids)
         t_next = torch.max(t - hp["X_T_STEP_INTERVAL"], torch.zeros_like(t))
         x_t = diffuse_t(x_0, t, hp, noise_t)
-        x_tgt = diffuse_t(x_0, t_next, hp)
+        x_tgt = diffuse_t(x_0, t_next, hp, noise_tgt)
         x_1 = diffuse_t(x_0, torch.ones(1, dtype=torch.int64, device=dev), hp, noise_1)
         x_t_loss, x_1_loss, prob_loss = loss(model, x_t, x_1, x_tgt, x_0, x["image_clip"], x["text_clip"], x["attention_mask"], ids,
-                                             backward=backward, dropout_seed=dropout_seed)
+                                             backward=backward, dropout_seed=dropout_seed, classifier_mask=classifier_mask)
     else:
         img, txt, mask32, ids32 = _prep_batch(model, x["image_clip"], x["text_clip"], x["attention_mask"], ids)
         if noise_t is None:

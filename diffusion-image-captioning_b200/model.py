@@ -258,10 +258,10 @@ class DistilBertModel:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _engine(self, rows: int, batch: int, training: bool):
+    def _engine(self, rows: int, batch: int, training: bool, tag: str = ""):
         """Engine (+ its workspace) able to run passes of up to `rows` rows over `batch` captions. One engine is kept per
-        (training) flavour and regrown on demand."""
-        key = bool(training)
+        (training, tag) flavour and regrown on demand (tag "g" = the guided pass of classifier-free-guidance training)."""
+        key = (bool(training), tag)
         cur = self._engines.get(key)
         if cur is not None and cur[1] >= rows and cur[2] >= batch:
             return cur[0]

@@ -254,8 +254,23 @@ typedef struct clipdlm_loss_cfg {
   int32_t backward;       /* 0 = losses only (validate, CLIP-DDPM.py:488-501) */
   const float* target;    /* optional explicit embedding-loss target, see clipdlm_embed_loss */
   int32_t target_rows;
+  /* Classifier-free-guidance training (CLIP-DDPM.py:313-317,406-410): x_out of this engine is the MIX of an unguided pass (this
+   * engine) and a guided pass (another engine, see clipdlm_engine_cfg_mix). After the loss gradient d(x_out) is formed, row r of
+   * it is multiplied by row_scale_self[r] before this engine's backward continues, and - if export_engine is set - d(x_out) *
+   * row_scale_export[r] is written into that engine's upstream-gradient buffer for clipdlm_engine_backward. NULL = plain path. */
+  const float* row_scale_self;    /* [R] device, or NULL */
+  const float* row_scale_export;  /* [R] device, or NULL */
+  clipdlm_engine_t* export_engine;
 } clipdlm_loss_cfg_t;
 int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* lc, double* losses, clipdlm_stream stream);
+/* x_out(e_unguided)[r] <- guided[r] ? (1 + w) * x_out(e_guided)[r] - w * x_out(e_unguided)[r] : unchanged, over the R rows of the two
+ * engines' last forward passes (same R, B). Replaces the guidance mix of DistilBertModel.forward (CLIP-DDPM.py:313-317); the
+ * mixed x_out is what clipdlm_engine_loss_backward / clipdlm_engine_lm_head of e_unguided then see. */
+int clipdlm_engine_cfg_mix(clipdlm_engine_t* e_unguided, clipdlm_engine_t* e_guided, const int32_t* guided /* [R] device */, float w,
+                           clipdlm_stream stream);
+/* Backward of the last forward of `e` from the upstream gradient d(x_out) another engine exported into it (row_scale_export
+ * above): transform head, blocks, embeddings; gradients accumulate into bufs.grads. */
+int clipdlm_engine_backward(clipdlm_engine_t* e, clipdlm_stream stream);
 
 /* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e);

@@ -128,6 +128,40 @@ def main() -> int:
             check(f"train_func[{fusion},{lf}] text_linear grad is exactly zero (key 17 masked)",
                   (not zero_txt) or (float(gref["text_linear.weight"].abs().max()) == 0.0 and float(Po["text_linear.weight"].grad.abs().max()) == 0.0))
 
+    # 7. classifier-free-guidance training (CLIP-DDPM.py:313-317,406-410): losses + gradients with the reference's own guidance draw
+    for fusion in ("concat", "add"):
+        hp = small_hp(CLIP_ADDING_METHOD=fusion, CLASSIFIER_FREE_WEIGHT=0.3, CLASSIFIER_FREE_PROB=0.4)
+        ns = H.build_namespace(hp)
+        model = H.build_model(ns, hp, seed=2)
+        P = H.export_params(model)
+        batch = O.synthetic_batch(hp, seed=4, ragged=True)
+        S, B = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"]
+        x_0 = P["embedding.weight"][batch["input_ids"]]
+        tt = torch.tensor([3, 200, 600, 950]).reshape(S, 1, 1)
+        acp = O.alpha_cumprod(hp)
+        g = torch.Generator().manual_seed(31)
+        x_t = O.diffuse_t(x_0, tt, acp, torch.randn(x_0.shape, generator=g))
+        x_1 = O.diffuse_t(x_0, torch.ones(1, dtype=torch.int64), acp, torch.randn(x_0.shape, generator=g))
+        torch.manual_seed(77)
+        lr = ns["loss"](model, x_t, x_1, None, x_0, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"],
+                        ns["LOSS_FUNC"])
+        sum(lr).backward()
+        torch.manual_seed(77)
+        cmask = (torch.rand((S * B, 1)) > hp["CLASSIFIER_FREE_PROB"]).type(torch.float32)
+        cmask[0] = 0; cmask[1] = 1
+        Po = {k: v.clone() for k, v in P.items()}
+        O.make_trainable(Po, hp)
+        lo = O.loss(Po, x_t, x_1, None, x_0, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], hp,
+                    train=True, classifier_mask=cmask)
+        sum(lo).backward()
+        ok = max(rel(a.detach(), b.detach()) for a, b in zip(lo, lr)) < 1e-5
+        check(f"CFG loss[{fusion}]", ok, f"ref={[round(float(v), 5) for v in lr]} oracle={[round(float(v), 5) for v in lo]}")
+        gref = {n: p.grad.detach() for n, p in model.named_parameters() if p.grad is not None}
+        gscale = max(float(v.double().norm()) for v in gref.values())
+        names = [k for k in O.trainable_names(hp) if not (Po[k].grad is None and k not in gref)]
+        worst = max(float((Po[k].grad.double() - gref[k].double()).norm()) / max(float(gref[k].double().norm()), 1e-4 * gscale) for k in names)
+        check(f"CFG gradients[{fusion}]", worst < 2e-4, f"worst rel={worst:.2e}")
+
     # AdamW restatement vs torch.optim.AdamW on identical synthetic gradients (3 steps, incl. an all-zero gradient tensor)
     torch.manual_seed(0)
     ps = [torch.randn(7, 5), torch.randn(11), torch.randn(3, 3)]

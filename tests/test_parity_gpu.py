@@ -231,6 +231,49 @@ def test_validate_and_state_dict_roundtrip(pkg):
     assert torch.equal(model2.flat, model.flat) and torch.equal(model2.shadow_hi, model.shadow_hi)
 
 
+@pytest.mark.parametrize("fusion", ["concat", "add"])
+def test_classifier_free_guidance_training_vs_oracle(pkg, fusion):
+    """CLASSIFIER_FREE_WEIGHT > 0 (CLIP-DDPM.py:313-317,406-410): per-row guidance draw, guided second pass, mixed x_out, gradient
+    split between the two passes. Losses and every gradient against the oracle (itself pinned against the real reference with the
+    reference's own guidance draw, oracle/validate_against_reference.py check 7), parity mode, chunked (2 chunks)."""
+    hp = golden_hp(CLIP_ADDING_METHOD=fusion, CLASSIFIER_FREE_WEIGHT=0.3, CLASSIFIER_FREE_PROB=0.4, BATCH_SIZE=3, SAMPLE_SIZE=4)
+    P = O.init_params(hp, seed=11, closed_form=False)
+    S, B, ML, D = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["DIM"]
+    batch = O.synthetic_batch(hp, seed=12, ragged=True)
+    gen = torch.Generator().manual_seed(13)
+    acp = O.alpha_cumprod(hp)
+    x_0 = P["embedding.weight"][batch["input_ids"]]
+    t = torch.tensor([5, 300, 700, 990]).reshape(S, 1, 1)
+    x_t = O.diffuse_t(x_0, t, acp, torch.randn(x_0.shape, generator=gen))
+    x_1 = O.diffuse_t(x_0, torch.ones(1, dtype=torch.int64), acp, torch.randn(x_0.shape, generator=gen))
+    cmask = (torch.rand((S * B, 1), generator=gen) > 0.4).float()
+    cmask[0] = 0; cmask[1] = 1
+    Po = {k: v.clone() for k, v in P.items()}
+    O.make_trainable(Po, hp)
+    ref = O.loss(Po, x_t, x_1, None, x_0, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], hp,
+                 train=True, classifier_mask=cmask)
+    sum(ref).backward()
+    model = make_model(pkg, hp, P={k: v.clone() for k, v in P.items()}, chunk_rows=2 * B).train()
+    got = pkg.loss(model, x_t.to(DEV), x_1.to(DEV), None, x_0.to(DEV), batch["image_clip"].to(DEV), batch["text_clip"].to(DEV),
+                   batch["attention_mask"].to(DEV), batch["input_ids"].to(DEV), backward=True, classifier_mask=cmask)
+    for x, y in zip(got, ref):
+        assert abs(x.item() - y.item()) < 1e-3 * abs(y.item()), (x.item(), y.item())
+    grads = model.named_grads()
+    gscale = max(float(Po[n].grad.double().norm()) for n in O.trainable_names(hp) if Po[n].grad is not None)
+    for n in O.trainable_names(hp):
+        if Po[n].grad is None:
+            continue
+        r = Po[n].grad.double()
+        mine = grads[n].reshape(-1)[:r.numel()].reshape(r.shape).cpu().double()
+        assert float((mine - r).norm()) <= 5e-3 * max(float(r.norm()), 1e-3 * gscale), n
+    # eval: the mixed forward only (validate path)
+    model.eval()
+    got_e = pkg.loss(model, x_t.to(DEV), x_1.to(DEV), None, x_0.to(DEV), batch["image_clip"].to(DEV), batch["text_clip"].to(DEV),
+                     batch["attention_mask"].to(DEV), batch["input_ids"].to(DEV), backward=False, classifier_mask=cmask)
+    for x, y in zip(got_e, ref):
+        assert abs(x.item() - y.item()) < 1e-3 * abs(y.item())
+
+
 @pytest.mark.parametrize("shape", ["bert-large-shaped", "bert-base-depth"])
 def test_other_model_shapes_vs_oracle(pkg, shape):
     """BASELINE.json configs 2 / 5: the 12-layer ('bert-base') depth and the bert-large geometry (d = 1024, 16 heads, FFN 4096,
