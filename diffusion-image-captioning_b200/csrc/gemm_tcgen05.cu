@@ -85,7 +85,7 @@ __device__ __forceinline__ void ld_row64(const __nv_bfloat16* p, bool al32, uint
   if (al32) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=r"(r[h * 8 + 0]), "=r"(r[h * 8 + 1]), "=r"(r[h * 8 + 2]), "=r"(r[h * 8 + 3]), "=r"(r[h * 8 + 4]), "=r"(r[h * 8 + 5]),
                      "=r"(r[h * 8 + 6]), "=r"(r[h * 8 + 7])
                    : "l"(p + h * 16));
