@@ -22,6 +22,12 @@ def __getattr__(name):  # torch-dependent modules load lazily so that `build` wo
     if name in ("diffuse_t", "generate_diffuse_pair", "loss", "train_func", "validate", "train", "sample"):
         from . import diffusion as _d
         return getattr(_d, name)
+    if name in ("DeviceCaptionDataset", "CaptionSubset", "CaptionLoader", "synthetic_dataset"):
+        from . import data as _da
+        return getattr(_da, name)
+    if name in ("postprocess", "decode", "bleu_score"):
+        from . import metrics as _me
+        return getattr(_me, name)
     if name in ("enable_data_parallel", "init_process_group_from_env", "shard_range"):
         from . import parallel as _p
         return getattr(_p, name)

@@ -104,3 +104,51 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_device_caption_dataset_and_loader():
+    """pre-tokenised dataset + loader with the reference's split / drop_last / batch-dict semantics."""
+    import torch
+    import clipdlm
+    ds = clipdlm.synthetic_dataset(103, seed=1)
+    tr, va = ds.random_split(0.8, torch.Generator().manual_seed(0))
+    assert len(tr) == int(103 * 0.8) and len(tr) + len(va) == 103
+    assert set(tr.indices.tolist()).isdisjoint(va.indices.tolist())
+    loader = tr.loader(8, shuffle=True, generator=torch.Generator().manual_seed(3))
+    batches = list(loader)
+    assert len(batches) == len(loader) == len(tr) // 8  # drop_last
+    b = batches[0]
+    assert set(b) >= {"image_clip", "text_clip", "input_ids", "attention_mask", "image"}
+    assert tuple(b["input_ids"].shape) == (8, 16) and b["input_ids"].dtype == torch.int64 and tuple(b["image_clip"].shape) == (8, 512)
+    seen = torch.cat([x["input_ids"] for x in batches])
+    assert seen.shape[0] == len(batches) * 8
+    # data-parallel sharding: two ranks see disjoint batches of the same permutation, same count
+    r0 = list(tr.loader(8, shuffle=True, generator=torch.Generator().manual_seed(5), rank=0, world=2))
+    r1 = list(tr.loader(8, shuffle=True, generator=torch.Generator().manual_seed(5), rank=1, world=2))
+    assert len(r0) == len(r1) == (len(tr) // 8) // 2
+    a = {tuple(x.tolist()) for bb in r0 for x in bb["input_ids"]}
+    c = {tuple(x.tolist()) for bb in r1 for x in bb["input_ids"]}
+    assert a.isdisjoint(c)
+
+
+def test_postprocess_and_bleu():
+    """unique_consecutive quirk + BLEU-4 known answers (hand-computed / sacrebleu-style definitions)."""
+    import torch
+    import clipdlm
+    ids = torch.tensor([[5, 5, 7, 7, 9], [1, 1, 2, 3, 3]])
+    # batch semantics of the reference: a column goes only if it repeats for EVERY row -> columns 1 (5|1) and 3 (7|3)... col 3 = (7,3) vs col 2 = (7,2): kept
+    cols = clipdlm.postprocess(ids)
+    assert [r.tolist() for r in cols] == [[5, 7, 7, 9], [1, 2, 3, 3]]
+    assert [r.tolist() for r in clipdlm.postprocess(ids, per_sequence=True)] == [[5, 7, 9], [1, 2, 3]]
+    assert clipdlm.decode([torch.tensor([3, 4])], lambda i: f"w{i}") == ["w3 w4"]
+    cand = ["the cat sat on the mat"]
+    assert abs(clipdlm.bleu_score(cand, [["the cat sat on the mat"]]) - 1.0) < 1e-12
+    assert clipdlm.bleu_score(["a b c d"], [["e f g h"]]) == 0.0
+    # 5 of 6 unigrams, 3 of 5 bigrams, 1 of 4 trigrams, 0 of 3 4-grams -> 0 (no smoothing)
+    assert clipdlm.bleu_score(["the cat the cat on mat"], [["the cat sat on the mat"]]) == 0.0
+    # brevity penalty: candidate = first 5 tokens of a 6-token reference, all n-grams match: BLEU = exp(1 - 6/5)
+    import math
+    assert abs(clipdlm.bleu_score(["the cat sat on the"], [["the cat sat on the mat"]]) - math.exp(1 - 6 / 5)) < 1e-12
+    # two references: clipping takes the max count over references, length = closest reference
+    s = clipdlm.bleu_score(["a a b c d e"], [["a b c d e f", "a a b c d e"]])
+    assert abs(s - 1.0) < 1e-12
