@@ -23,8 +23,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output ("NCCL version ...", NCCL_DEBUG=INFO lines) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line. Libraries print there too (the image sets NCCL_DEBUG=VERSION: "NCCL version ..." comes from
+# NCCL's C code), so file descriptor 1 is pointed at stderr for the whole run and the result line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import torch  # noqa: E402
 
@@ -165,7 +172,7 @@ def run_reference(args):
             "data": "synthetic", "config": workload_config(args, B_override=None),
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, B_override=None):
@@ -318,7 +325,7 @@ def run_ours(args):
                 v = rows * len(times) / sum(times) * (10 / 100.0)
                 sample = "2 denoise loops of 8 captions x 10 steps, scaled to 100 steps"
             line["cpu_baseline"] = {"value": v, "unit": line["unit"], "cores": threads, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
