@@ -296,7 +296,7 @@ def run_ours(args):
                        "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
                        "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
                    for k, v in prof.items() if v["launches"]}
-        roofline = {"bound": "tensor", "kernel": f"gemm_kernel ({dom}: tcgen05.mma 128x256x16, TMA-fed, fused epilogue)", "achieved": ach,
+        roofline = {"bound": "tensor", "kernel": f"gemm_kernel ({dom}: tcgen05.mma.cta_group::2 256x256x16 CTA pairs, TMA-fed 5-stage ring, fused epilogue with TMA stores)", "achieved": ach,
                     "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "peak_kind": f"{pk['source']} sustained bf16 (burst {pk['tf_burst']})",
                     "avg_launch_ms": d["ms"] / max(d["launches"], 1), "flops_per_launch": d["flops"] / max(d["launches"], 1),
                     "traffic": ncu_traffic(dom), "ms_per_step_with_event_brackets": ms_prof / args.steps,

@@ -353,6 +353,16 @@ __device__ __forceinline__ void lds8(const __nv_bfloat16* hi, const __nv_bfloat1
     v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
   }
 }
+// TMA store of a shared-memory tile (written with generic-proxy stores + fence.proxy.async) into a 2-D tensor; bulk async-group
+// bookkeeping: commit after the store(s), wait_group.read N before the source buffer is overwritten again.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // CTA-pair variants: the data lands in THIS CTA's shared memory, the transaction bytes are signalled on the mbarrier at
 // shared::cluster address `bar_cluster` (the leader CTA's barrier, which the MMA-issuing thread waits on).
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {

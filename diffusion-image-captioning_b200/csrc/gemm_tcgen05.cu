@@ -23,8 +23,8 @@ namespace clipdlm {
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16384
 constexpr int EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quadrant, each owning 128 of the 256 tile columns
-constexpr int STG_PITCH = 80;                       // bytes per staged row (64 B payload = 32 bf16 or 16 fp32, + 16 B pad)
-constexpr int STG_WARP_BYTES = 32 * STG_PITCH;      // 2560
+constexpr int STG_PITCH = 80;                       // fp32 staging (WGRAD): bytes per staged row (64 B payload = 16 fp32, + 16 B pad)
+constexpr int STG_WARP_BYTES = 8192;                // per epilogue warp: two [32 rows][128 B] swizzled tiles feeding TMA stores (or the fp32 staging)
 constexpr int TMEM_COLS = 512;
 // Geometry per CTA-group size.  CG = 1: one CTA computes a 128 x 256 tile (tcgen05.mma.cta_group::1, M = 128).
 // CG = 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256): each CTA
@@ -36,7 +36,7 @@ struct Geo {
   static constexpr int BN_CTA = BN / CG;
   static constexpr int B_STAGE_BYTES = BN_CTA * BK * 2;   // 32768 / 16384
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int STAGES = CG == 2 ? 5 : 3;   // + 64 KB of epilogue staging = 227 KB
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES + BN * 4 /*bias*/ + 256 /*barriers*/;
 };
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
@@ -60,6 +60,7 @@ struct GemmArgs {
   int scatter_len, scatter_stride;
   int al32;  // every bf16 epilogue operand is 32-byte aligned with a pitch that is a multiple of 16 elements
   uint32_t dbg;  // clipdlm_gemm_debug_flags
+  int tma_out;   // the bf16 outputs of the specialised STORE epilogue / the LSE logits go out through TMA stores (tmO / tmO2)
   int fast_mode; // >= 0: specialised STORE epilogue (bit 0 bias, bits 1-2 aux 0 none / 1 residual / 2 gelu'(u), bit 3 gelu dual store, bit 4 dropout)
   DropoutCfg drop;
   float* part_max;
@@ -175,9 +176,22 @@ __device__ __forceinline__ void tile_store_f32(const GemmArgs& g, float* base, l
 // GEMMs are epilogue-issue bound.  The engine's hot launches all fall into a handful of shapes (plain bf16, 32-byte aligned
 // rows, N a multiple of 256), so those get straight-line code: the four chunks of a warp are fully unrolled, the auxiliary
 // operand (residual or gelu' input) is double-buffered in registers one chunk ahead, no per-chunk branches remain.
+// 32 bf16 (one chunk of this thread's row) into the warp's [32 rows][128 B] swizzled staging tile, half `half` of the 64-column pair
+__device__ __forceinline__ void stage_row32(uint32_t buf, int row, int half, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t addr = buf + (uint32_t)row * 128u + ((uint32_t)((half * 4 + q) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[8 * q], v[8 * q + 1])),
+                 "r"(pack_bf16x2(v[8 * q + 2], v[8 * q + 3])), "r"(pack_bf16x2(v[8 * q + 4], v[8 * q + 5])),
+                 "r"(pack_bf16x2(v[8 * q + 6], v[8 * q + 7]))
+                 : "memory");
+  }
+}
+
 template <bool BIAS, int AUX, bool DUAL, bool DROP>
 __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr, int col0, int m, bool valid, long long mr, uint32_t sbias_u32,
-                                               uint64_t* tfull, uint32_t tphase) {
+                                               uint64_t* tfull, uint32_t tphase, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint32_t stg,
+                                               int row_base) {
   const __nv_bfloat16* aux = AUX == 2 ? g.u_hi : g.res_hi;
   const long long ld_aux = AUX == 2 ? g.ldu : g.ldr;
   const __nv_bfloat16* aux_row = AUX != 0 ? aux + mr * ld_aux + col0 : nullptr;
@@ -224,7 +238,33 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
     } else if (AUX == 1) {
       row_unpack<true>(cur, v);
     }
-    if (valid) {
+    if (g.tma_out) {
+      // Outputs leave through shared memory + TMA: the row-wise 32-byte stores cost one L1 transaction per sector (2 K per
+      // 128 x 256 output tile, twice that for the dual store) and made the GELU GEMMs store-bound. Buffers alternate (single
+      // output: pair 0 -> A, pair 1 -> B; dual: u -> A, gelu(u) -> B), a buffer is rewritten only after wait_group.read.
+      const int lane = m - row_base;
+      const bool single = !DUAL || out_row == nullptr;   // one output stream (also: gelu-only inference variant of the dual mode)
+      const uint32_t bufU = stg + (single ? (uint32_t)((cc >> 1) * 4096) : 0u), bufG = stg + (single ? (uint32_t)((cc >> 1) * 4096) : 4096u);
+      if ((cc & 1) == 0) {
+        if (lane == 0) { if (single) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        __syncwarp();
+      }
+      if (!DUAL || out_row != nullptr) stage_row32(bufU, lane, cc & 1, v);
+      if (DUAL) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) upk2(gelu2(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
+        stage_row32(bufG, lane, cc & 1, v);
+      }
+      if (cc & 1) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = col0 + (cc >> 1) * 64;
+          if (!DUAL || out_row != nullptr) { tma_store_2d(tmO, bufU, c0, row_base); bulk_commit(); }
+          if (DUAL) { tma_store_2d(tmO2, bufG, c0, row_base); bulk_commit(); }
+        }
+      }
+    } else if (valid) {
       if ((!DUAL || out_row != nullptr) && !(g.dbg & 256u)) row_store_pair(out_row + cc * 32, nullptr, true, v);
       if (DUAL) {
         if (!(g.dbg & 128u)) {
@@ -255,7 +295,8 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
 template <int AMAJ, int BMAJ, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-            const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs g) {
+            const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmArgs g) {
   using G = Geo<CG>;
   constexpr int STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -428,7 +469,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         const int col0 = n_blk * BN + c_lo * 32;
         const uint32_t sb = smem_u32(sbias) + c_lo * 128;
 #define FAST_CASE(MODE, BIAS, AUX, DUAL, DROP) \
-  case MODE: epi_store_fast<BIAS, AUX, DUAL, DROP>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase); break;
+  case MODE: epi_store_fast<BIAS, AUX, DUAL, DROP>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg), row_base); break;
         switch (g.fast_mode) {
           FAST_CASE(0, false, 0, false, false)    // dgrad
           FAST_CASE(1, true, 0, false, false)     // q/k/v projection
@@ -630,6 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   }
 
+  if (warp >= 4 && lane == 0) bulk_wait_read<0>();   // outstanding TMA stores still read this CTA's staging tiles
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: nobody leaves while the peer may still read its smem / signal its barriers
   if (warp == 2) {
@@ -813,8 +855,8 @@ static uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_flags = 0;
 static int g_num_sms = 0;
 
 template <int AMAJ, int BMAJ, int EPI, int CG>
-static int launch_gemm_cg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
-                          int units, cudaStream_t st) {
+static int launch_gemm_cg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& o0,
+                          const CUtensorMap& o1, const GemmArgs& ga, int units, cudaStream_t st) {
   static bool attr_set = false;
   static int max_units = 0;   // co-resident work units (CTAs / CTA pairs) of this instantiation: the kernel is persistent
   auto kfn = gemm_kernel<AMAJ, BMAJ, EPI, CG>;
@@ -854,14 +896,14 @@ static int launch_gemm_cg(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_dbg_flags & 512u ? 1 : 2;   // debug bit 9: no programmatic dependent launch
-  CLIPDLM_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, ga));
+  CLIPDLM_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, o0, o1, ga));
   return 0;
 }
 template <int AMAJ, int BMAJ, int EPI>
-static int launch_gemm(int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const GemmArgs& ga,
-                       int units, cudaStream_t st) {
-  if (cg == 2) return launch_gemm_cg<AMAJ, BMAJ, EPI, 2>(a0, a1, b0, b1, ga, units, st);
-  return launch_gemm_cg<AMAJ, BMAJ, EPI, 1>(a0, a1, b0, b1, ga, units, st);
+static int launch_gemm(int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& o0,
+                       const CUtensorMap& o1, const GemmArgs& ga, int units, cudaStream_t st) {
+  if (cg == 2) return launch_gemm_cg<AMAJ, BMAJ, EPI, 2>(a0, a1, b0, b1, o0, o1, ga, units, st);
+  return launch_gemm_cg<AMAJ, BMAJ, EPI, 1>(a0, a1, b0, b1, o0, o1, ga, units, st);
 }
 
 int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
@@ -958,6 +1000,17 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
     if (!(g_dbg_flags & 64u) && ga.fast_mode >= 0 && mode != 9 && !g->out_hi) ga.fast_mode = -1;   // only the dual-store mode may omit out
     if (g_dbg_flags & 64u) ga.fast_mode = -1;   // triage: force the generic epilogue
   }
+  // bf16 outputs through TMA stores (box 64 columns x 32 rows out of the epilogue warps' swizzled staging tiles)
+  CUtensorMap o0 = a0, o1 = a0;
+  ga.tma_out = 0;
+  if (ga.fast_mode >= 0 && g->scatter_len == 0 && !(g_dbg_flags & 1024u)) {
+    uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+    uint64_t str[1] = {(uint64_t)g->ldo * 2};
+    uint32_t box[2] = {64, 32};
+    if (g->out_hi && (rc = encode_map(&o0, g->out_hi, 2, dims, str, box))) return rc;
+    if (g->out2_hi && (rc = encode_map(&o1, g->out2_hi, 2, dims, str, box))) return rc;
+    ga.tma_out = 1;
+  }
 
   const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
   const int grid = total < units_max ? total : units_max;   // work units: CTAs (cg = 1) or CTA pairs (cg = 2)
@@ -967,24 +1020,24 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
       CLIPDLM_CHECK(g->N % 32 == 0, "STORE epilogue needs N %% 32 == 0 (N = %d)", g->N);
       CLIPDLM_CHECK(g->out_hi || g->out_f32 || g->out2_hi, "STORE epilogue without output");
       CLIPDLM_CHECK(g->a_major == 0, "STORE epilogue expects K-major A");
-      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, ga, grid, st);
-      return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, ga, grid, st);
+      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+      return launch_gemm<0, 1, CLIPDLM_EPI_STORE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     case CLIPDLM_EPI_WGRAD:
       CLIPDLM_CHECK(g->a_major == 1 && g->b_major == 1, "WGRAD epilogue expects MN-major A and B");
       CLIPDLM_CHECK(g->N % 32 == 0 && g->acc_f32, "WGRAD needs N %% 32 == 0 and an fp32 accumulator");
-      return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(cg, a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<1, 1, CLIPDLM_EPI_WGRAD>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     case CLIPDLM_EPI_LSE:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE epilogue expects K-major operands");
       CLIPDLM_CHECK(g->part_max && g->part_sum && (!g->targets || g->tgt_logit), "LSE epilogue buffers missing");
       CLIPDLM_CHECK(!g->out_hi || (!g->out_lo && g->ldo >= (long long)ga.num_n_tiles * BN && g->ldo % 8 == 0 &&
                                    (reinterpret_cast<uintptr_t>(g->out_hi) & 15) == 0),
                     "LSE epilogue: the optional bf16 logits output needs a 16-byte aligned plain-bf16 buffer with pitch >= %d", ga.num_n_tiles * BN);
-      return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(cg, a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
       CLIPDLM_CHECK(g->out_hi && g->lse && g->targets, "SMGRAD epilogue buffers missing");
       CLIPDLM_CHECK(g->ldo >= (long long)ga.num_n_tiles * BN, "SMGRAD output pitch %lld < %d", (long long)g->ldo, ga.num_n_tiles * BN);
-      return launch_gemm<0, 0, CLIPDLM_EPI_SMGRAD>(cg, a0, a1, b0, b1, ga, grid, st);
+      return launch_gemm<0, 0, CLIPDLM_EPI_SMGRAD>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     default:
       CLIPDLM_CHECK(false, "unknown epilogue %d", g->epilogue);
   }
