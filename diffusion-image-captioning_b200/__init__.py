@@ -28,6 +28,9 @@ def __getattr__(name):  # torch-dependent modules load lazily so that `build` wo
     if name in ("postprocess", "decode", "bleu_score"):
         from . import metrics as _me
         return getattr(_me, name)
+    if name in ("load_reference_checkpoint", "save_reference_pickle", "to_reference_module", "save_checkpoint", "load_checkpoint"):
+        from . import checkpoint as _c
+        return getattr(_c, name)
     if name in ("enable_data_parallel", "init_process_group_from_env", "shard_range"):
         from . import parallel as _p
         return getattr(_p, name)
