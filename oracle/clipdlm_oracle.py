@@ -114,6 +114,11 @@ def param_names(hp: dict) -> List[Tuple[str, Tuple[int, ...]]]:
             ("model.vocab_layer_norm.weight", (d,)), ("model.vocab_layer_norm.bias", (d,)),
             ("image_linear.weight", (d, c)), ("image_linear.bias", (d,)),
             ("text_linear.weight", (d, c)), ("text_linear.bias", (d,))]
+    if hp["TRAIN_EMBEDDING"]:  # :238-243,260-262: learned IN_CHANNEL-wide embedding, lm_head and in/out projections, all trainable
+        ch, V = hp["IN_CHANNEL"], hp["VOCAB_SIZE"]
+        out += [("embedding.weight", (V, ch)), ("lm_head.weight", (V, ch)),
+                ("input_projection.weight", (d, ch)), ("input_projection.bias", (d,)),
+                ("output_projection.weight", (ch, d)), ("output_projection.bias", (ch,))]
     if hp["CLIP_ADDING_METHOD"] == "concat":
         out += [("segment_embedding.weight", (2, d))]
     return out
@@ -128,7 +133,7 @@ def init_params(hp: dict, seed: int = 0, closed_form: bool = False) -> Dict[str,
     """
     g = torch.Generator().manual_seed(seed)
     params: Dict[str, Tensor] = {}
-    names = param_names(hp) + [("embedding.weight", (hp["VOCAB_SIZE"], hp["DIM"]))]
+    names = param_names(hp) + ([] if hp["TRAIN_EMBEDDING"] else [("embedding.weight", (hp["VOCAB_SIZE"], hp["DIM"]))])
     for k, (name, shape) in enumerate(names):
         n = int(math.prod(shape))
         if closed_form:
@@ -141,6 +146,10 @@ def init_params(hp: dict, seed: int = 0, closed_form: bool = False) -> Dict[str,
                 v = 0.7 * base
             elif name.startswith(("image_linear", "text_linear")):
                 v = base / math.sqrt(hp["CLIP_DIM"])
+            elif hp["TRAIN_EMBEDDING"] and name == "embedding.weight":
+                v = base  # nn.Embedding default N(0, 1) (:238)
+            elif hp["TRAIN_EMBEDDING"] and name.startswith(("lm_head", "input_projection", "output_projection")):
+                v = 0.5 * base / math.sqrt(shape[-1])  # nn.Linear-like scale (fan-in = last dim)
             else:
                 v = 0.03 * base
             params[name] = v.float()
@@ -150,9 +159,12 @@ def init_params(hp: dict, seed: int = 0, closed_form: bool = False) -> Dict[str,
             elif name.startswith(("image_linear", "text_linear")):
                 bound = 1.0 / math.sqrt(hp["CLIP_DIM"])
                 params[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            elif hp["TRAIN_EMBEDDING"] and name.startswith(("lm_head", "input_projection", "output_projection")):
+                bound = 1.0 / math.sqrt(shape[-1] if name.endswith("weight") else (hp["IN_CHANNEL"] if name.startswith("input") else hp["DIM"]))
+                params[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound  # nn.Linear default init
             elif name.endswith(".bias"):
                 params[name] = torch.zeros(shape)
-            elif name == "segment_embedding.weight":
+            elif name == "segment_embedding.weight" or (hp["TRAIN_EMBEDDING"] and name == "embedding.weight"):
                 params[name] = torch.randn(shape, generator=g)
             else:
                 params[name] = torch.randn(shape, generator=g) * 0.02
@@ -208,7 +220,7 @@ def encoder(P: Dict[str, Tensor], x: Tensor, key_mask: Tensor, hp: dict, train: 
 
 def model_forward(P: Dict[str, Tensor], x: Tensor, image_clip: Tensor, text_clip: Tensor, mask: Tensor, concat_mask: Tensor,
                   hp: dict, train: bool = False) -> Tuple[Tensor, Tensor]:
-    """DistilBertModel.forward, CLIP-DDPM.py:271-323 (TRAIN_EMBEDDING=False branch). Returns (vocab_out, feature_out)."""
+    """DistilBertModel.forward, CLIP-DDPM.py:271-323. Returns (vocab_out, feature_out)."""
     R = x.shape[0]
     ML = hp["MAX_LENGTH"]
     assert x.shape == (R, ML, hp["IN_CHANNEL"])  # :284-287
@@ -216,6 +228,8 @@ def model_forward(P: Dict[str, Tensor], x: Tensor, image_clip: Tensor, text_clip
     assert mask.shape == (R, ML)
     assert concat_mask.shape == (R, 2)
     guidance = concat_mask[:, 1] == 1  # :290
+    if hp["TRAIN_EMBEDDING"]:  # :292-293
+        x = F.linear(x, P["input_projection.weight"], P["input_projection.bias"])
     img = F.linear(image_clip, P["image_linear.weight"], P["image_linear.bias"])
     txt = F.linear(text_clip, P["text_linear.weight"], P["text_linear.bias"])
     if hp["CLIP_ADDING_METHOD"] == "concat":  # :295-302
@@ -237,7 +251,11 @@ def model_forward(P: Dict[str, Tensor], x: Tensor, image_clip: Tensor, text_clip
     if w > 0 and not guidance.sum() == 0:  # :313-317
         x_out = x_out.clone()
         x_out[guidance] = (1 + w) * encoder(P, guided_x[guidance], guided_mask[guidance], hp, train) - w * x_out[guidance]
+    if hp["TRAIN_EMBEDDING"]:  # :319-320
+        x_out = F.linear(x_out, P["output_projection.weight"], P["output_projection.bias"])
     assert x_out.shape == (R, non_mask.shape[-1], hp["IN_CHANNEL"])  # :322
+    if hp["TRAIN_EMBEDDING"]:
+        return F.linear(x_out[:, :ML, :], P["lm_head.weight"]), x_out  # trainable nn.Linear(IN_CHANNEL, VOCAB_SIZE, bias=False) (:239)
     return F.linear(x_out[:, :ML, :], P["embedding.weight"]), x_out  # lm_head: frozen, weight == embedding, bias 0 (:246-247,323)
 
 
@@ -352,7 +370,8 @@ def make_trainable(P: Dict[str, Tensor], hp: dict) -> List[Tensor]:
     for n in trainable_names(hp):
         P[n].requires_grad_(True)
         out.append(P[n])
-    P["embedding.weight"].requires_grad_(False)
+    if not hp["TRAIN_EMBEDDING"]:
+        P["embedding.weight"].requires_grad_(False)
     return out
 
 

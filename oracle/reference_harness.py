@@ -56,6 +56,8 @@ def build_model(ns: dict, hp: dict, seed: int = 0):
     torch.manual_seed(seed)
     cfg = DistilBertConfig(n_layers=hp["N_LAYERS"], dim=hp["DIM"], n_heads=hp["N_HEADS"], hidden_dim=hp["HIDDEN_DIM"],
                            dropout=hp["DROPOUT"], attention_dropout=hp["ATTENTION_DROPOUT"], vocab_size=hp["VOCAB_SIZE"])
+    if hp["TRAIN_EMBEDDING"]:  # CLIP-DDPM.py:325-327
+        return ns["DistilBertModel"](config=cfg)
     origin = DistilBertForMaskedLM(cfg)
     model = ns["DistilBertModel"](origin.get_input_embeddings(), origin.get_output_embeddings(), cfg)
     return model
@@ -65,9 +67,11 @@ def export_params(model) -> dict:
     """Reference parameters under the names oracle/clipdlm_oracle.py uses."""
     P = {}
     for n, p in model.named_parameters():
-        if n.startswith(("model.", "image_linear", "text_linear", "segment_embedding")) and "vocab_projector" not in n:
+        if n.startswith(("model.", "image_linear", "text_linear", "segment_embedding", "input_projection", "output_projection")) and "vocab_projector" not in n:
             P[n] = p.detach().clone()
     P["embedding.weight"] = model.embedding.weight.detach().clone()
+    if hasattr(model, "input_projection"):  # TRAIN_EMBEDDING: the lm_head is its own trainable tensor (:239)
+        P["lm_head.weight"] = model.lm_head.weight.detach().clone()
     return P
 
 
@@ -77,4 +81,4 @@ def load_params(model, P: dict):
             if n in P:
                 p.copy_(P[n])
         model.embedding.weight.copy_(P["embedding.weight"])
-        model.lm_head.weight.copy_(P["embedding.weight"])
+        model.lm_head.weight.copy_(P.get("lm_head.weight", P["embedding.weight"]))

@@ -162,6 +162,54 @@ def main() -> int:
         worst = max(float((Po[k].grad.double() - gref[k].double()).norm()) / max(float(gref[k].double().norm()), 1e-4 * gscale) for k in names)
         check(f"CFG gradients[{fusion}]", worst < 2e-4, f"worst rel={worst:.2e}")
 
+    # 8. TRAIN_EMBEDDING=True (CLIP-DDPM.py:238-243,292-293,319-320): 16-channel learned embedding, trainable lm_head and in/out
+    #    projections; the gradient reaches embedding.weight through x_t, x_1 AND the loss target x_0
+    for lf, x0pred in (("series_sum_sample_mean", True), ("mse_series_mean", True), ("series_sum_sample_mean", False)):
+        hp = small_hp(TRAIN_EMBEDDING=True, IN_CHANNEL=16, LOSS_FUNC=lf, X_0_PREDICTION=x0pred, X_T_STEP_INTERVAL=100)
+        ns = H.build_namespace(hp)
+        model = H.build_model(ns, hp, seed=5)
+        P = H.export_params(model)
+        acp = O.alpha_cumprod(hp)
+        batch = O.synthetic_batch(hp, seed=6, ragged=True)
+        S, B = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"]
+        model.eval()
+        R = 4
+        xin = torch.randn(R, 16, 16)
+        img, txt = torch.randn(R, 1, 512), torch.randn(R, 1, 512)
+        mask = (torch.rand(R, 16) > 0.3).long(); mask[:, 0] = 1
+        cm = torch.tensor([1, 0]).repeat(R, 1)
+        with torch.no_grad():
+            lo_r, xo_r = model(xin, img, txt, mask, cm)
+            lo_o, xo_o = O.model_forward(P, xin, img, txt, mask, cm, hp, False)
+        check(f"TRAIN_EMBEDDING forward[{lf}]", (xo_r - xo_o).abs().max() < 1e-5 and (lo_r - lo_o).abs().max() < 1e-4 and tuple(xo_r.shape) == (R, 18, 16),
+              f"max_abs x_out={(xo_r - xo_o).abs().max():.2e} logits={(lo_r - lo_o).abs().max():.2e}")
+        model.train()
+        x_0r = model.embedding(batch["input_ids"])
+        tt = torch.tensor([3, 200, 600, 950]).reshape(S, 1, 1)
+        g = torch.Generator().manual_seed(41)
+        n_t, n_1, n_g = (torch.randn(B, 16, 16, generator=g) for _ in range(3))
+        one = torch.ones(1, dtype=torch.int64)
+        t_next = torch.max(tt - hp["X_T_STEP_INTERVAL"], torch.zeros_like(tt))
+        x_t = O.diffuse_t(x_0r, tt, acp, n_t); x_1 = O.diffuse_t(x_0r, one, acp, n_1)
+        x_tgt = None if x0pred else O.diffuse_t(x_0r, t_next, acp, n_g)
+        lr = ns["loss"](model, x_t, x_1, x_tgt, x_0r, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], ns["LOSS_FUNC"])
+        sum(lr).backward()
+        Po = {k: v.clone() for k, v in P.items()}
+        O.make_trainable(Po, hp)
+        x_0o = torch.nn.functional.embedding(batch["input_ids"], Po["embedding.weight"])
+        x_to = O.diffuse_t(x_0o, tt, acp, n_t); x_1o = O.diffuse_t(x_0o, one, acp, n_1)
+        x_tgto = None if x0pred else O.diffuse_t(x_0o, t_next, acp, n_g)
+        lo = O.loss(Po, x_to, x_1o, x_tgto, x_0o, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], hp, train=True)
+        sum(lo).backward()
+        ok = max(rel(a.detach(), b.detach()) for a, b in zip(lo, lr)) < 1e-5
+        check(f"TRAIN_EMBEDDING loss[{lf},x0={x0pred}]", ok, f"ref={[round(float(v), 5) for v in lr]} oracle={[round(float(v), 5) for v in lo]}")
+        gref = {n: p.grad.detach() for n, p in model.named_parameters() if p.grad is not None}
+        gscale = max(float(v.double().norm()) for v in gref.values())
+        names = [k for k in O.trainable_names(hp) if not (Po[k].grad is None and k not in gref)]
+        worst = max(float((Po[k].grad.double() - gref[k].double()).norm()) / max(float(gref[k].double().norm()), 1e-4 * gscale) for k in names)
+        check(f"TRAIN_EMBEDDING gradients[{lf},x0={x0pred}]", worst < 2e-4 and {"embedding.weight", "lm_head.weight", "input_projection.weight", "output_projection.bias"} <= set(names),
+              f"worst rel={worst:.2e} over {len(names)} tensors")
+
     # AdamW restatement vs torch.optim.AdamW on identical synthetic gradients (3 steps, incl. an all-zero gradient tensor)
     torch.manual_seed(0)
     ps = [torch.randn(7, 5), torch.randn(11), torch.randn(3, 3)]

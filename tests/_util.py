@@ -28,8 +28,11 @@ GOLDEN_CASES = {
     "concat_mse_mean": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_mean"),
     "concat_series_sum": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum"),
     "concat_mse_sum": dict(CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_sum"),
+    # TRAIN_EMBEDDING=True (CLIP-DDPM.py:238-243): 16-channel learned embedding, trainable lm_head and in/out projections
+    "te_concat_l1": dict(TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean"),
+    "te_add_mse_mean": dict(TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="add", LOSS_FUNC="mse_series_mean"),
 }
-FULL_CASES = ("concat_l1", "add_l1")
+FULL_CASES = ("concat_l1", "add_l1", "te_concat_l1")
 
 
 def load_golden(name):
@@ -38,7 +41,7 @@ def load_golden(name):
 
 def golden_inputs(hp):
     """The closed-form inputs tests/golden/make_golden.py fed to the reference."""
-    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["DIM"]
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]  # == DIM unless TRAIN_EMBEDDING
     R = 2
     mask = torch.ones(R, ML, dtype=torch.int64)
     mask[1, 9:] = 0

@@ -55,7 +55,7 @@ def make_case(name: str, full: bool = True, **kw):
     P = O.init_params(hp, seed=0, closed_form=True)
     H.load_params(model, P)
     batch = O.closed_form_batch(hp, k=1, ragged=True)
-    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["DIM"]
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]  # == DIM unless TRAIN_EMBEDDING
     out = {}
     # forward (eval) on explicit rows
     model.eval()
@@ -112,8 +112,14 @@ if __name__ == "__main__":
     if not H.available():
         sys.exit("reference unavailable")
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "te":  # only the TRAIN_EMBEDDING cases (added later; the others are unchanged)
+        make_case("te_concat_l1", TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean")
+        make_case("te_add_mse_mean", full=False, TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="add", LOSS_FUNC="mse_series_mean")
+        sys.exit(0)
     make_case("concat_l1", CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean")
     make_case("add_l1", CLIP_ADDING_METHOD="add", LOSS_FUNC="series_sum_sample_mean")
     make_case("concat_mse_mean", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_mean")
     make_case("concat_series_sum", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum")
     make_case("concat_mse_sum", full=False, CLIP_ADDING_METHOD="concat", LOSS_FUNC="mse_series_sum")
+    make_case("te_concat_l1", TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean")
+    make_case("te_add_mse_mean", full=False, TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="add", LOSS_FUNC="mse_series_mean")
