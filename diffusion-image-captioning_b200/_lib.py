@@ -146,6 +146,10 @@ _SIGS = {
     "clipdlm_engine_loss_backward": (C.c_int, [c_p, C.POINTER(LossCfg), c_p, c_p]),
     "clipdlm_engine_cfg_mix": (C.c_int, [c_p, c_p, c_p, f32, c_p]),
     "clipdlm_engine_backward": (C.c_int, [c_p, c_p]),
+    "clipdlm_engine_backward_from": (C.c_int, [c_p, c_p, c_p, c_p]),
+    "clipdlm_feature_loss_f32": (C.c_int, [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p, c_p, i32, c_p, c_p, c_p]),
+    "clipdlm_pack_rows_bf16": (C.c_int, [c_p, i64, i32, i32, i32, i32, c_p, c_p, c_p]),
+    "clipdlm_embedding_bwd": (C.c_int, [c_p, c_p, c_p, i32, i64, i32, c_p, c_p]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
     "clipdlm_engine_profile": (C.c_int, [c_p, i32]),
     "clipdlm_engine_profile_read": (C.c_int, [c_p, c_p, i32]),

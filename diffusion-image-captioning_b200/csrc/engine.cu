@@ -35,6 +35,8 @@ int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* 
 int small_linear_fwd_dispatch(const float* x, const float* w, const float* b, int B, int K, int N, float* y, cudaStream_t st);
 int small_linear_bwd_dispatch(const float* x, const float* dy, int B, int K, int N, float* dw, float* db, cudaStream_t st);
 int keymask_dispatch(const int* attn_mask, int R, int B, int Ltxt, int L, int fusion, int guided, uint32_t* km, cudaStream_t st);
+int to_bf16_dispatch(const float* x, void* hi, void* lo, long long n, cudaStream_t st);
+int gather_rows_f32_dispatch(const clipdlm_bf_t* x, long long rows_out, int len, int stride, int D, float* y, cudaStream_t st);
 int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, int L, int D, int H, const clipdlm_bf_t* ctx,
                       unsigned long long seed, uint32_t site, float p, cudaStream_t st);
 int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int R, int L, int D, int H,
@@ -611,6 +613,18 @@ int clipdlm_engine_cfg_mix(clipdlm_engine_t* eu, clipdlm_engine_t* eg, const int
 int clipdlm_engine_backward(clipdlm_engine_t* e, clipdlm_stream stream) {
   CLIPDLM_CHECK(e != nullptr && e->have_fwd && e->training, "engine_backward: needs a training engine with a forward pass");
   return backward_from_g0(e, (cudaStream_t)stream);
+}
+int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float* dx_in, clipdlm_stream stream) {
+  CLIPDLM_CHECK(e != nullptr && e->have_fwd && e->training, "engine_backward_from: needs a training engine with a forward pass");
+  CLIPDLM_CHECK(dx_out != nullptr, "engine_backward_from: null upstream gradient");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long T = (long long)e->last.R * e->L;
+  RUN(to_bf16_dispatch(dx_out, e->g0.hi, e->pair ? e->g0.lo : nullptr, T * e->cfg.dim, st));
+  int rc = backward_from_g0(e, st);
+  if (rc) return rc;
+  // g1 now holds d(z0), the gradient of the pre-LayerNorm embedding sum; the caller's x_in enters z0 additively at the text positions
+  if (dx_in != nullptr) RUN(gather_rows_f32_dispatch(&e->g1, (long long)e->last.R * e->Ltxt, e->Ltxt, e->L, e->cfg.dim, dx_in, st));
+  return 0;
 }
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e) { return e ? e->launches : -1; }
 

@@ -49,7 +49,8 @@ def diffuse_t(x: torch.Tensor, t: torch.Tensor, hp: dict, noise: Optional[torch.
     if noise is None:
         noise = torch.randn(x.shape, device=x.device)
     ca, cb = _coefs(hp, t.to(x.device))
-    x32, n32 = x.float().contiguous(), noise.float().contiguous()
+    x32, n32 = x.float().contiguous(), noise.to(x.device, torch.float32).contiguous()
+    assert tuple(n32.shape) == tuple(x32.shape), "diffuse_t: the noise draw has x's shape (CLIP-DDPM.py:359)"
     out = torch.empty(S * B, seq, ch, device=x.device)
     with torch.cuda.device(x.device):
         L.check(L.load().clipdlm_q_sample(L.ptr(x32), L.ptr(n32), L.ptr(ca), L.ptr(cb), x32.numel(), S, L.ptr(out),
@@ -129,6 +130,10 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
     if loss_func is not None and getattr(loss_func, "__name__", loss_func) != hp["LOSS_FUNC"]:
         raise ValueError(f"loss_func {getattr(loss_func, '__name__', loss_func)} differs from hp['LOSS_FUNC'] = {hp['LOSS_FUNC']}")
     _need_cuda(x_t)
+    if hp["TRAIN_EMBEDDING"]:
+        if backward is None:
+            backward = model.training and torch.is_grad_enabled()
+        return _loss_te(model, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, backward=backward, dropout_seed=dropout_seed)
     cfg = None
     if hp["CLASSIFIER_FREE_WEIGHT"] > 0:  # :406-410: per-row guidance draw; rows 0 / 1 pinned so that both kinds always occur
         if classifier_mask is None:
@@ -165,6 +170,71 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
     return _finish(model, losses)
 
 
+def _loss_te(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, *, backward: bool, dropout_seed=None,
+             embed_coefs=None):
+    """loss() for TRAIN_EMBEDDING=True (train_embedding.py). The inputs x_t / x_1 / x_tgt / x_0 are functions of the trainable
+    embedding; `embed_coefs = (ca_t [S], ca_1 [1], ca_tgt [S] or None)` (the sqrt(alpha_bar) factors of q_sample, CLIP-DDPM.py:360) lets
+    the gradients that reach them be folded into d(embedding.weight) chunk by chunk. Called without it (a direct loss() call on
+    explicit tensors) every other parameter gradient is still produced, exactly as autograd would treat detached inputs."""
+    from . import train_embedding as TE
+    hp = model.hp
+    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:
+        raise NotImplementedError("TRAIN_EMBEDDING=True with classifier-free-guidance TRAINING is not built (forward()/sample() support the mix)")
+    S, B, ML, ch = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    img, txt, mask32, ids32 = _prep_batch(model, image_clip, text_clip, mask, idx)
+    x_t32, x_132, x_032 = x_t.float().contiguous(), x_1.float().contiguous(), x_0.float().contiguous()
+    x0pred = bool(hp["X_0_PREDICTION"])
+    tgt_t = x_032 if x0pred else x_tgt.float().contiguous()
+    if not x0pred:
+        assert tuple(x_tgt.shape) == tuple(x_t.shape)  # :420
+    spc = max(1, model.chunk_rows // B)
+    eng = model._engine(min(S, spc) * B, B, backward or model.training)
+    losses = torch.zeros(4, dtype=torch.float64, device=model.device)
+    seed = _next_seed() if dropout_seed is None else int(dropout_seed)
+    d_x0 = torch.zeros_like(x_032) if backward else None
+    for ci, s0 in enumerate(range(0, S, spc)):
+        s1 = min(S, s0 + spc)
+        R = (s1 - s0) * B
+        if x0pred:
+            target, trows, d_tgt = tgt_t, B, d_x0
+        else:
+            target, trows = tgt_t[s0 * B:s1 * B], R
+            d_tgt = torch.zeros(R, ML, ch, device=model.device) if backward else None
+        dx = TE.loss_pass(model, eng, losses, 0, x16=x_t32[s0 * B:s1 * B], R=R, B=B, R_total=S * B, target=target, target_rows=trows, img=img,
+                          txt=txt, mask32=mask32, ids32=ids32, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], backward=backward, d_target=d_tgt)
+        if backward and embed_coefs is not None:
+            TE.embedding_bwd(model, dx, embed_coefs[0][s0:s1].contiguous(), ids32, s1 - s0)
+            if not x0pred and hp["USE_X_T_LOSS"]:
+                TE.embedding_bwd(model, d_tgt, embed_coefs[2][s0:s1].contiguous(), ids32, s1 - s0)
+    dx = TE.loss_pass(model, eng, losses, 2, x16=x_132, R=B, B=B, R_total=B, target=x_032, target_rows=B, img=img, txt=txt, mask32=mask32,
+                      ids32=ids32, seed=seed + 7919, use_embed=hp["USE_X_1_LOSS"], backward=backward, d_target=d_x0)
+    if backward and embed_coefs is not None:
+        TE.embedding_bwd(model, dx, embed_coefs[1].contiguous(), ids32, 1)
+        TE.embedding_bwd(model, d_x0, None, ids32, 1)  # the loss targets x_0.repeat(...) / x_0 (:418,428) are the embedding rows themselves
+    return _finish(model, losses)
+
+
+def _train_func_te(model: DistilBertModel, trainer, x: dict, train: bool, t, noise_t, noise_1, noise_tgt, dropout_seed):
+    """train_func (CLIP-DDPM.py:458-486) for TRAIN_EMBEDDING=True: x_0 = model.embedding(ids) carries gradient."""
+    hp = model.hp
+    dev = model.device
+    S, B, ML = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"]
+    ids = x["input_ids"].to(dev)
+    x_0 = model.embedding(ids).contiguous()  # :459
+    ca, _ = _coefs(hp, t)
+    one = torch.ones(1, dtype=torch.int64, device=dev)
+    ca1, _ = _coefs(hp, one)
+    x_t = diffuse_t(x_0, t, hp, noise_t)  # :464
+    x_tgt, ca_n = None, None
+    if not hp["X_0_PREDICTION"]:  # :466-467
+        t_next = torch.max(t - hp["X_T_STEP_INTERVAL"], torch.zeros_like(t))
+        x_tgt = diffuse_t(x_0, t_next, hp, noise_tgt)
+        ca_n, _ = _coefs(hp, t_next)
+    x_1 = diffuse_t(x_0, one, hp, noise_1)  # :468
+    return _loss_te(model, x_t, x_1, x_tgt, x_0, x["image_clip"], x["text_clip"], x["attention_mask"], ids, backward=bool(train),
+                    dropout_seed=dropout_seed, embed_coefs=(ca, ca1, ca_n))
+
+
 def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train: bool = True, *, t: Optional[torch.Tensor] = None,
                noise_t: Optional[torch.Tensor] = None, noise_1: Optional[torch.Tensor] = None, dropout_seed: Optional[int] = None,
                noise_tgt: Optional[torch.Tensor] = None, classifier_mask: Optional[torch.Tensor] = None):
@@ -187,7 +257,9 @@ def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train:
     backward = bool(train)
     if train:
         trainer.zero_grad()  # :471
-    if not hp["X_0_PREDICTION"] or hp["CLASSIFIER_FREE_WEIGHT"] > 0:
+    if hp["TRAIN_EMBEDDING"]:
+        x_t_loss, x_1_loss, prob_loss = _train_func_te(model, trainer, x, train, t, noise_t, noise_1, noise_tgt, dropout_seed)
+    elif not hp["X_0_PREDICTION"] or hp["CLASSIFIER_FREE_WEIGHT"] > 0:
         # x_{t-1}-prediction objective (:466-467): explicit tensors through loss()
         x_0 = model.embedding(ids)
         t_next = torch.max(t - hp["X_T_STEP_INTERVAL"], torch.zeros_like(t))
@@ -308,6 +380,21 @@ def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, r
     eng = model._engine(B, B, False)
     model._last_eng = eng
     outs = []
+    if hp["TRAIN_EMBEDDING"]:  # the loop runs in the IN_CHANNEL-wide space: input_projection -> encoder -> output_projection per step
+        from . import train_embedding as TE
+        xo = torch.empty(B, Lfull, hp["DIM"], device=dev)
+        for i in range(n_steps):
+            u = TE.in_proj(model, cur[:, :ML].contiguous())
+            model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=u,
+                               x_out=xo, reuse_proj=i > 0)
+            cur = TE.out_proj(model, xo)
+            if return_all:
+                outs.append(TE.argmax(model, cur))
+        indexes = outs[-1] if return_all and outs else TE.argmax(model, cur)
+        if unique_consecutive:
+            indexes = indexes.unique_consecutive(dim=-1)
+        cur = cur.clone()
+        return (indexes, cur, outs) if return_all else (indexes, cur)
     for i in range(n_steps):
         model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=cur,
                            x_in_stride=Lfull * D, x_out=nxt, reuse_proj=i > 0)  # the CLIP projections do not change across steps

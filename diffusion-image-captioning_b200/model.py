@@ -55,9 +55,13 @@ class _LmHead:
     def __init__(self, owner: "DistilBertModel"):
         self._owner = owner
         self.weight = owner.lm_head_weight
-        self.bias = torch.zeros(owner.hp["VOCAB_SIZE"], device=owner.device)
+        # TRAIN_EMBEDDING: nn.Linear(IN_CHANNEL, VOCAB_SIZE, bias=False), trainable (CLIP-DDPM.py:239)
+        self.bias = None if owner.hp["TRAIN_EMBEDDING"] else torch.zeros(owner.hp["VOCAB_SIZE"], device=owner.device)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if self._owner.hp["TRAIN_EMBEDDING"]:
+            from . import train_embedding as TE
+            return TE.logits_dense(self._owner, x)
         return self._owner._lm_head_dense(x)
 
 
@@ -87,6 +91,10 @@ def _slot_names(hp: dict) -> List[Tuple[str, int, Tuple[int, ...], int]]:
     return out
 
 
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
 class DistilBertModel:
     """Drop-in for the reference's `class DistilBertModel(nn.Module)` (CLIP-DDPM.py:227-323).
 
@@ -114,8 +122,8 @@ class DistilBertModel:
                       MAX_POSITION=config.max_position_embeddings)
             if not hp["TRAIN_EMBEDDING"]:
                 hp["IN_CHANNEL"] = config.dim
-        if hp["TRAIN_EMBEDDING"]:
-            raise NotImplementedError("TRAIN_EMBEDDING=True (IN_CHANNEL=16 learned embedding, CLIP-DDPM.py:238-243) is outside the built path")
+        if hp["TRAIN_EMBEDDING"] and hp["IN_CHANNEL"] == hp["DIM"]:
+            hp["IN_CHANNEL"] = 16  # CLIP-DDPM.py:99-100
         if hp["CLIP_ADDING_METHOD"] not in ("concat", "add"):
             raise NotImplementedError(hp["CLIP_ADDING_METHOD"])  # CLIP-DDPM.py:269
         if precision not in ("bf16", "bf16x3"):
@@ -132,7 +140,18 @@ class DistilBertModel:
         n = lib.clipdlm_param_count(C.byref(self._cfg))
         if n <= 0:
             raise L.ClipdlmError("bad model configuration: " + lib.clipdlm_last_error().decode())
-        self.n_params = int(n)
+        self.n_engine = int(n)  # the encoder's slots (laid out by libclipdlm)
+        # TRAIN_EMBEDDING: the extra trainable tensors follow in the same flat buffer, so the one fused AdamW / all-reduce covers them
+        self._te_off: Dict[str, int] = {}
+        te_extra = []
+        off = _round_up(self.n_engine, 64)
+        if hp["TRAIN_EMBEDDING"]:
+            from . import train_embedding as TE
+            te_extra = TE.extra_params(hp)
+            for name, stored, _ in te_extra:
+                self._te_off[name] = off
+                off += _round_up(int(math.prod(stored)), 64)
+        self.n_params = off if te_extra else self.n_engine
         dev = self.device
         self.flat = torch.zeros(self.n_params, device=dev)
         self.grad = torch.zeros(self.n_params, device=dev)
@@ -140,15 +159,37 @@ class DistilBertModel:
         self.shadow_lo = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16) if precision == "bf16x3" else None
         self._views: Dict[str, torch.Tensor] = {}
         self._gviews: Dict[str, torch.Tensor] = {}
+        self._scr: Dict[str, torch.Tensor] = {}
         for name, slot, shape, rel in _slot_names(hp):
             off = int(lib.clipdlm_param_offset(C.byref(self._cfg), slot)) + rel
             cnt = int(math.prod(shape))
             self._views[name] = self.flat[off:off + cnt].view(shape)
             self._gviews[name] = self.grad[off:off + cnt].view(shape)
-        if sum(v.numel() for v in self._views.values()) != self.n_params:
+        if sum(v.numel() for v in self._views.values()) != self.n_engine:
             raise L.ClipdlmError("parameter name map does not cover the flat buffer")
+        if te_extra:  # the reference lists them before segment_embedding (CLIP-DDPM.py:259-265)
+            seg = [(k, self._views.pop(k), self._gviews.pop(k)) for k in ("segment_embedding.weight",) if k in self._views]
+            for name, stored, logical in te_extra:
+                o, cnt = self._te_off[name], int(math.prod(stored))
+                sl = tuple(slice(0, n) for n in logical)
+                self._views[name] = self.flat[o:o + cnt].view(stored)[sl]    # lm_head.weight: strided view into its zero-padded slot
+                self._gviews[name] = self.grad[o:o + cnt].view(stored)[sl]
+            for k, v, g in seg:
+                self._views[k], self._gviews[k] = v, g
         self._init_parameters(seed)
+        self._engines: Dict[tuple, tuple] = {}
+        self._launches_retired = 0
+        self._grads_dirty = False
         V, D = hp["VOCAB_SIZE"], hp["DIM"]
+        if hp["TRAIN_EMBEDDING"]:  # CLIP-DDPM.py:238-239: both live in the trainable flat buffer; `embedding` / `projection` are ignored
+            self.embedding_weight = self._views["embedding.weight"]
+            self.lm_head_weight = self._views["lm_head.weight"]
+            self._vpad = (V + 255) // 256 * 256
+            self.emb_hi = self.emb_lo = None
+            self.embedding = _Embedding(self.embedding_weight)
+            self.lm_head = _LmHead(self)
+            self.sync_shadow()
+            return
         if embedding is None:
             g = torch.Generator(device="cpu")
             g.manual_seed(0 if seed is None else seed + 1)
@@ -167,9 +208,6 @@ class DistilBertModel:
         self.emb_lo = torch.zeros(self._vpad, D, device=dev, dtype=torch.bfloat16) if precision == "bf16x3" else None
         self.embedding = _Embedding(self.embedding_weight)
         self.lm_head = _LmHead(self)
-        self._engines: Dict[tuple, tuple] = {}
-        self._launches_retired = 0
-        self._grads_dirty = False
         self.sync_shadow()
 
     # ---------------------------------------------------------------------------------------------------------- params
@@ -180,7 +218,13 @@ class DistilBertModel:
         g.manual_seed(torch.initial_seed() if seed is None else seed)
         c = self.hp["CLIP_DIM"]
         for name, v in self._views.items():
-            if "LayerNorm.weight" in name or "layer_norm.weight" in name:
+            if self.hp["TRAIN_EMBEDDING"] and name.startswith(("embedding.", "lm_head.", "input_projection.", "output_projection.")):
+                if name == "embedding.weight":  # nn.Embedding default N(0, 1)
+                    v.copy_(torch.randn(v.shape, generator=g))
+                else:  # nn.Linear default: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
+                    fan_in = self.hp["DIM"] if name.startswith("output_projection") else self.hp["IN_CHANNEL"]
+                    v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) / math.sqrt(fan_in))
+            elif "LayerNorm.weight" in name or "layer_norm.weight" in name:
                 v.fill_(1.0)
             elif name.startswith(("image_linear", "text_linear")):
                 bound = 1.0 / math.sqrt(c)
@@ -206,6 +250,8 @@ class DistilBertModel:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Reference-compatible names: trainable tensors + embedding.weight + lm_head.{weight,bias}."""
         sd = {k: v.detach().clone() for k, v in self._views.items()}
+        if self.hp["TRAIN_EMBEDDING"]:  # embedding.weight / lm_head.weight are trainable views already; no lm_head bias (:239)
+            return sd
         sd["embedding.weight"] = self.embedding_weight.clone()
         sd["lm_head.weight"] = self.lm_head_weight.clone()
         sd["lm_head.bias"] = torch.zeros(self.hp["VOCAB_SIZE"], device=self.device)
@@ -218,6 +264,9 @@ class DistilBertModel:
         for k, v in self._views.items():
             if k in sd:
                 v.copy_(sd[k].to(self.device, torch.float32))
+        if self.hp["TRAIN_EMBEDDING"]:
+            self.sync_shadow()
+            return
         if "embedding.weight" in sd:
             self.embedding_weight.copy_(sd["embedding.weight"].to(self.device, torch.float32))
         if "lm_head.weight" in sd:
@@ -231,6 +280,8 @@ class DistilBertModel:
         lib, st = L.load(), self._stream()
         with torch.cuda.device(self.device):
             L.check(lib.clipdlm_to_bf16(L.ptr(self.flat), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), self.n_params, st))
+            if self.hp["TRAIN_EMBEDDING"]:
+                return  # the lm_head operand is part of the flat shadow
             n = self.hp["VOCAB_SIZE"] * self.hp["DIM"]
             L.check(lib.clipdlm_to_bf16(L.ptr(self.lm_head_weight), L.ptr(self.emb_hi), L.ptr(self.emb_lo), n, st))
 
@@ -276,8 +327,14 @@ class DistilBertModel:
         if need == 0:
             raise L.ClipdlmError("workspace query failed: " + lib.clipdlm_last_error().decode())
         ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        bufs = L.Buffers(L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), L.ptr(self.embedding_weight),
-                         L.ptr(self.emb_hi), L.ptr(self.emb_lo), L.ptr(ws), need)
+        if self.hp["TRAIN_EMBEDDING"]:
+            # the engine's own embedding gather / frozen lm_head stay unused in this mode (x enters through input_projection, the
+            # lm_head is composed in train_embedding.py); its non-null checks get the flat buffers as placeholders
+            bufs = L.Buffers(L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), L.ptr(self.flat),
+                             L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), L.ptr(ws), need)
+        else:
+            bufs = L.Buffers(L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), L.ptr(self.embedding_weight),
+                             L.ptr(self.emb_hi), L.ptr(self.emb_lo), L.ptr(ws), need)
         h = lib.clipdlm_engine_create(C.byref(self._cfg), C.byref(bufs), rows, batch, 1 if training else 0)
         if not h:
             raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
@@ -285,6 +342,15 @@ class DistilBertModel:
         if getattr(self, "_profiling", False):
             L.check(lib.clipdlm_engine_profile(h, 1))
         return h
+
+    def _scratch(self, name: str, shape, dtype) -> torch.Tensor:
+        """Named reusable device buffer (host-composed paths allocate nothing per step once shapes have been seen)."""
+        n = int(math.prod(shape))
+        t = self._scr.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._scr[name] = t
+        return t[:n].view(shape)
 
     def launch_count(self) -> int:
         """Kernel launches issued by this model's engines so far (bench `gpu_launches`)."""
@@ -342,11 +408,20 @@ class DistilBertModel:
         guidance = concat_mask[:, 1] == 1  # :290
         n_guided = int(guidance.sum().item())
         w = hp["CLASSIFIER_FREE_WEIGHT"]
+        te = hp["TRAIN_EMBEDDING"]
+        if te:  # :292-293
+            from . import train_embedding as TE
+            x = TE.in_proj(self, self._f32(x)).clone()
         x_out = self._encode(x, image_clip[:, 0], text_clip[:, 0], mask, guided=False)
-        if w > 0 and n_guided > 0:  # :313-317
+        mixed = w > 0 and n_guided > 0
+        if mixed:  # :313-317
             idx = guidance.nonzero().flatten()
             guided_out = self._encode(x[idx], image_clip[idx, 0], text_clip[idx, 0], mask[idx], guided=True)
             x_out[idx] = (1 + w) * guided_out - w * x_out[idx]
+        if te:  # :319-320,323
+            y = TE.out_proj(self, x_out).clone()
+            return TE.logits(self, y), y
+        if mixed:
             return self.lm_head(x_out[:, :ML, :]), x_out
         return self._lm_head_last(R), x_out
 

@@ -59,8 +59,9 @@ def enable_data_parallel(model, group=None):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return model
     broadcast_flat(model.flat, group)
-    broadcast_flat(model.embedding_weight, group)
-    broadcast_flat(model.lm_head_weight, group)
+    if not model.hp["TRAIN_EMBEDDING"]:  # (there, embedding / lm_head are trainable slots of the flat buffer)
+        broadcast_flat(model.embedding_weight, group)
+        broadcast_flat(model.lm_head_weight, group)
     model.sync_shadow()
     model.dp_group = group if group is not None else dist.group.WORLD
     model.dp_world = dist.get_world_size(group)

@@ -180,6 +180,25 @@ int clipdlm_keymask(const int32_t* attn_mask, int32_t R, int32_t B, int32_t Ltxt
                     uint32_t* keymask, clipdlm_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * TRAIN_EMBEDDING=True glue (CLIP-DDPM.py:238-243,292-293,319-320): the learned embedding is IN_CHANNEL (16) wide, features are fp32.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* LOSS_FUNC (CLIP-DDPM.py:77-89) between y[:, :Ltxt] (y fp32 [R, L, ch], model feature_out) and target[r % target_rows] (fp32
+ * [target_rows, Ltxt, ch]; x_0.repeat(...) :418,428 or x_tgt :421). kind / R_total / batch_size / weight / loss_acc as clipdlm_embed_loss.
+ * dy (optional, fp32 [R, L, ch]) is WRITTEN: text positions = loss gradient + dce[(r * Ltxt + p) * ld_dce + c] (optional gradient coming
+ * from the rounding cross-entropy), other positions = 0. d_target (optional, fp32 like target) -= loss gradient (atomic): with a learned
+ * embedding the target x_0 / x_tgt carries gradient too. */
+int clipdlm_feature_loss_f32(const float* y, const float* target, int32_t target_rows, int32_t R, int32_t Ltxt, int32_t L, int32_t ch,
+                             int32_t kind, int64_t R_total, int32_t batch_size, float weight, double* loss_acc, const float* dce,
+                             int32_t ld_dce, float* dy, float* d_target, clipdlm_stream stream);
+/* Compact zero-padded GEMM operand: out[m, c] = c < ch ? y[(m / Ltxt) * L + m % Ltxt, c] : 0 for m < rows_out, c < ld; bf16 (pair). */
+int clipdlm_pack_rows_bf16(const float* y, int64_t rows_out, int32_t Ltxt, int32_t L, int32_t ch, int32_t ld, void* hi, void* lo,
+                           clipdlm_stream stream);
+/* Gradient of nn.Embedding through q_sample: d_table[ids[j], c] += sum_s scale[s] * dx[s, j, c]; dx fp32 [S, tokens, ch], ids int32
+ * [tokens], scale [S] (sqrt(alpha_bar[t_s]), CLIP-DDPM.py:360) or NULL (= 1). Replaces autograd through :459 and :347-362. */
+int clipdlm_embedding_bwd(const float* dx, const float* scale, const int32_t* ids, int32_t S, int64_t tokens, int32_t ch, float* d_table,
+                          clipdlm_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Engine: the composite hot path (model forward / loss+backward / denoise step) orchestrated natively.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct clipdlm_config {
@@ -271,6 +290,11 @@ int clipdlm_engine_cfg_mix(clipdlm_engine_t* e_unguided, clipdlm_engine_t* e_gui
 /* Backward of the last forward of `e` from the upstream gradient d(x_out) another engine exported into it (row_scale_export
  * above): transform head, blocks, embeddings; gradients accumulate into bufs.grads. */
 int clipdlm_engine_backward(clipdlm_engine_t* e, clipdlm_stream stream);
+
+/* Backward of the last forward of `e` from an explicit upstream gradient dx_out (fp32 [R, L, dim], the gradient of the fp32 x_out the
+ * forward returned) and, optionally, the gradient of the mode-0 input x_in (fp32 [R, max_len, dim]) written to dx_in. Used when the
+ * encoder sits between caller-side layers (TRAIN_EMBEDDING=True: input_projection / output_projection, CLIP-DDPM.py:292-293,319-320). */
+int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float* dx_in /* may be NULL */, clipdlm_stream stream);
 
 /* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e);

@@ -428,3 +428,81 @@ def test_adamw_matches_torch(G):
         assert float(gg.abs().max()) == 0.0  # zero_grad fused
         assert rel(p, ref_p.detach()) < 2e-6
         assert rel(hi.float() + lo.float(), p) < 1e-5 and torch.equal(hi, p.bfloat16())
+
+
+# ------------------------------------------------------------------------------------------------------------ TRAIN_EMBEDDING glue
+@pytest.mark.parametrize("pair", [False, True])
+def test_gemm_narrow_operands(G, pair):
+    """The 64-channel-padded lm_head GEMMs of the TRAIN_EMBEDDING path: K = 64 forward, N = 64 dgrad (MN-major B, ragged K = V),
+    N = 64 wgrad with a ragged M = V."""
+    M, V, C64 = 200, 997, 64
+    Vp = (V + 255) // 256 * 256
+    a = torch.zeros(M, C64, device=G.DEV); a[:, :16] = torch.randn(M, 16, device=G.DEV)
+    w = torch.zeros(Vp, C64, device=G.DEV); w[:V, :16] = torch.randn(V, 16, device=G.DEV) * 0.2
+    ah, al = G.split(a, pair); wh, wl = G.split(w, pair)
+    ar, wr = G.join(ah, al).double(), G.join(wh, wl).double()
+    n32 = (V + 31) // 32 * 32
+    out = torch.zeros(M, n32, device=G.DEV)
+    G.gemm(a_hi=ah, a_lo=al, b_hi=wh, b_lo=wl, lda=C64, ldb=C64, M=M, N=n32, K=C64, epilogue=0, out_f32=out, ldo=n32)
+    assert rel(out[:, :V], ar @ wr[:V].t()) < (3e-5 if pair else 4e-3)
+    assert float(out[:, V:].abs().max()) == 0.0
+    ldl = Vp
+    dl = torch.zeros(M, ldl, device=G.DEV); dl[:, :V] = torch.randn(M, V, device=G.DEV) * 0.1
+    dh, dll = G.split(dl, pair)
+    dr = G.join(dh, dll).double()
+    dce = torch.full((M, C64), 7.0, device=G.DEV)
+    G.gemm(a_hi=dh, a_lo=dll, b_hi=wh, b_lo=wl, lda=ldl, ldb=C64, M=M, N=C64, K=V, a_major=0, b_major=1, epilogue=0, out_f32=dce, ldo=C64)
+    assert rel(dce, dr[:, :V] @ wr[:V]) < (3e-5 if pair else 4e-3)
+    assert float(dce[:, 16:].abs().max()) == 0.0
+    acc = torch.zeros(Vp, C64, device=G.DEV); acc[:V] = 0.25
+    G.gemm(a_hi=dh, a_lo=dll, b_hi=ah, b_lo=al, lda=ldl, ldb=C64, M=V, N=C64, K=M, a_major=1, b_major=1, epilogue=1, acc_f32=acc, ldo=C64)
+    assert rel(acc[:V], dr[:, :V].t() @ ar + 0.25) < (3e-5 if pair else 4e-3)
+    assert float(acc[V:].abs().max()) == 0.0 and float((acc[:V, 16:] - 0.25).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind,name", [(0, "series_sum_sample_mean"), (1, "series_sum"), (2, "mse_series_mean"), (3, "mse_series_sum")])
+def test_feature_loss_f32(G, kind, name):
+    R, B, Ltxt, Lf, ch = 13, 4, 16, 18, 16
+    hp = O.default_hparams(); hp.update(BATCH_SIZE=B)
+    y = torch.randn(R, Lf, ch, device=G.DEV).requires_grad_(True)
+    for trows in (B, R):
+        tgt = torch.randn(trows, Ltxt, ch, device=G.DEV).requires_grad_(True)
+        rep = tgt.repeat((R + trows - 1) // trows, 1, 1)[:R] if trows != R else tgt
+        ref = O.LOSS_FUNCS[name](y[:, :Ltxt], rep, hp)
+        if kind == 0:
+            ref = ref  # mean over [R, ch]
+        gy, gt = torch.autograd.grad(ref * 0.5, [y, tgt])
+        dce = torch.randn(R * Ltxt, 64, device=G.DEV)
+        dy = torch.full((R, Lf, ch), 9.0, device=G.DEV); dt = torch.zeros(trows, Ltxt, ch, device=G.DEV)
+        acc = torch.zeros(1, device=G.DEV, dtype=torch.float64)
+        G.L.check(G.lib().clipdlm_feature_loss_f32(y.data_ptr(), tgt.data_ptr(), trows, R, Ltxt, Lf, ch, kind, R, B, 0.5, acc.data_ptr(),
+                                                   dce.data_ptr(), 64, dy.data_ptr(), dt.data_ptr(), G.st()))
+        torch.cuda.synchronize()
+        assert abs(acc.item() - ref.item()) < 1e-5 * abs(ref.item())   # value is unweighted, gradient carries the weight
+        want = gy.clone(); want[:, :Ltxt] += dce.view(R, Ltxt, 64)[:, :, :ch]
+        assert rel(dy, want) < 1e-5 and float(dy[:, Ltxt:].abs().max()) == 0.0
+        assert rel(dt, gt) < 1e-5
+
+
+def test_pack_rows_and_embedding_bwd(G):
+    R, Ltxt, Lf, ch = 7, 16, 18, 16
+    y = torch.randn(R, Lf, ch, device=G.DEV)
+    for pair in (False, True):
+        hi, lo = G.empty_pair((R * Ltxt, 64), pair)
+        hi.fill_(3.0)
+        G.L.check(G.lib().clipdlm_pack_rows_bf16(y.data_ptr(), R * Ltxt, Ltxt, Lf, ch, 64, hi.data_ptr(), G.L.ptr(lo), G.st()))
+        got = G.join(hi, lo)
+        assert rel(got[:, :ch], y[:, :Ltxt].reshape(-1, ch)) < (1e-5 if pair else 4e-3) and float(got[:, ch:].abs().max()) == 0.0
+    S, B, V = 5, 3, 50
+    ids = torch.randint(0, V, (B * Ltxt,), device=G.DEV, dtype=torch.int32)
+    ids[:4] = 7  # collisions
+    dx = torch.randn(S, B * Ltxt, ch, device=G.DEV); scale = torch.rand(S, device=G.DEV)
+    dE = torch.full((V, ch), 0.5, device=G.DEV)
+    G.L.check(G.lib().clipdlm_embedding_bwd(dx.data_ptr(), scale.data_ptr(), ids.data_ptr(), S, B * Ltxt, ch, dE.data_ptr(), G.st()))
+    ref = torch.full((V, ch), 0.5, device=G.DEV, dtype=torch.float64)
+    ref.index_add_(0, ids.long(), (dx.double() * scale.double()[:, None, None]).sum(0))
+    assert rel(dE, ref) < 1e-6
+    dE2 = torch.zeros(V, ch, device=G.DEV)
+    G.L.check(G.lib().clipdlm_embedding_bwd(dx.data_ptr(), None, ids.data_ptr(), 1, B * Ltxt, ch, dE2.data_ptr(), G.st()))
+    ref2 = torch.zeros(V, ch, device=G.DEV, dtype=torch.float64).index_add_(0, ids.long(), dx[0].double())
+    assert rel(dE2, ref2) < 1e-6

@@ -26,7 +26,8 @@ def make_model(pkg, hp, precision="bf16x3", P=None, chunk_rows=4096):
                                dropout=hp["DROPOUT"], attention_dropout=hp["ATTENTION_DROPOUT"])
     if P is None:
         P = O.init_params(hp, seed=0, closed_form=True)
-    model = pkg.DistilBertModel(P["embedding.weight"], P["embedding.weight"], cfg, hp=hp, precision=precision, chunk_rows=chunk_rows)
+    emb = None if hp["TRAIN_EMBEDDING"] else P["embedding.weight"]  # TRAIN_EMBEDDING: the reference ignores both arguments (:237-243)
+    model = pkg.DistilBertModel(emb, emb, cfg, hp=hp, precision=precision, chunk_rows=chunk_rows)
     model.load_state_dict({k: v.detach() for k, v in P.items()})
     return model
 
@@ -347,3 +348,72 @@ def test_full_size_properties(pkg):
     ids_p, _ = pkg.sample(model, img[perm], n_steps=4, restored=restored[perm])
     assert torch.equal(ids[perm], ids_p)
     assert tuple(ids.shape) == (1024, 16) and int(ids.min()) >= 0 and int(ids.max()) < 30522
+
+
+# --------------------------------------------------------------------------------------------------- TRAIN_EMBEDDING=True
+@pytest.mark.parametrize("x0pred", [True, False])
+def test_train_embedding_trajectory_vs_oracle(pkg, x0pred):
+    """TRAIN_EMBEDDING=True (CLIP-DDPM.py:238-243): 16-channel learned embedding, trainable lm_head and in/out projections. Three
+    optimizer steps in 3 row chunks against the oracle; the gradient reaches embedding.weight through x_t, x_1, x_tgt and x_0."""
+    hp = golden_hp(TRAIN_EMBEDDING=True, IN_CHANNEL=16, BATCH_SIZE=4, SAMPLE_SIZE=5, X_0_PREDICTION=x0pred, X_T_STEP_INTERVAL=150,
+                   LOSS_FUNC="mse_series_mean")  # smooth objective: no sign() flips between the two implementations
+    P = O.init_params(hp, seed=3, closed_form=False)
+    model = make_model(pkg, hp, P={k: v.clone() for k, v in P.items()}, chunk_rows=8).train()
+    assert sum(p.numel() for p in model.parameters()) == sum(v.numel() for v in P.values())
+    trainer = pkg.AdamW(model.parameters(), lr=2e-4)
+    Po = {k: v.clone() for k, v in P.items()}
+    oopt = O.AdamW(O.make_trainable(Po, hp), lr=2e-4)
+    acp = O.alpha_cumprod(hp)
+    torch.set_num_threads(8)
+    S, B = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"]
+    for step in range(3):
+        batch = O.synthetic_batch(hp, seed=20 + step, ragged=True)
+        gen = torch.Generator().manual_seed(200 + step)
+        t = torch.randint(0, 1000, (S, 1, 1), generator=gen)
+        n_t, n_1, n_g = (torch.randn(B, 16, 16, generator=gen) for _ in range(3))
+        # oracle step with every draw pinned (its train_func draws x_tgt's noise itself, so drive loss() directly)
+        oopt.zero_grad()
+        x_0 = torch.nn.functional.embedding(batch["input_ids"], Po["embedding.weight"])
+        t_next = torch.max(t - hp["X_T_STEP_INTERVAL"], torch.zeros_like(t))
+        x_t, x_1 = O.diffuse_t(x_0, t, acp, n_t), O.diffuse_t(x_0, torch.ones(1, dtype=torch.int64), acp, n_1)
+        x_tgt = None if x0pred else O.diffuse_t(x_0, t_next, acp, n_g)
+        lo = O.loss(Po, x_t, x_1, x_tgt, x_0, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], hp, train=True)
+        sum(lo).backward()
+        oopt.step()
+        lm = pkg.train_func(model, trainer, to_dev(batch), t=t, noise_t=n_t.to(DEV), noise_1=n_1.to(DEV), noise_tgt=n_g.to(DEV))
+        for x, y in zip(lm[1:], lo):
+            assert abs(x.item() - y.item()) < 1e-3 * abs(y.item()), (step, x.item(), y.item())
+    after = dict(model.named_parameters())
+    for n in ("embedding.weight", "lm_head.weight", "input_projection.weight", "input_projection.bias", "output_projection.weight",
+              "output_projection.bias", "model.vocab_transform.weight", "model.distilbert.transformer.layer.0.attention.q_lin.weight"):
+        assert rel(after[n], Po[n].detach()) < 1e-3, n
+    # rows of the embedding that no caption used only decay (AdamW weight decay), rows that were used moved
+    used = torch.zeros(hp["VOCAB_SIZE"], dtype=torch.bool)
+    for step in range(3):
+        used[O.synthetic_batch(hp, seed=20 + step, ragged=True)["input_ids"].reshape(-1)] = True
+    moved = (after["embedding.weight"].cpu() - P["embedding.weight"]).abs().amax(-1) > 1e-4
+    assert bool(moved[used].all()) and not bool(moved[~used].any())
+    # the zero padding of the lm_head slot stays exactly zero through AdamW (it is a GEMM operand)
+    o = model._te_off["lm_head.weight"]
+    slot = model.flat[o:o + model._vpad * 64].view(model._vpad, 64)
+    assert float(slot[:, 16:].abs().max()) == 0.0 and float(slot[hp["VOCAB_SIZE"]:].abs().max()) == 0.0
+
+
+def test_train_embedding_speed_mode_and_state_dict(pkg):
+    """bf16 speed mode of the TRAIN_EMBEDDING path: losses within 1e-2 of the oracle; state_dict round trip; sample() shape."""
+    hp = golden_hp(TRAIN_EMBEDDING=True, IN_CHANNEL=16)
+    P = O.init_params(hp, seed=0, closed_form=True)
+    inp = golden_inputs(hp)
+    model = make_model(pkg, hp, precision="bf16").train()
+    l, a, b, c = pkg.train_func(model, None, to_dev(inp["batch"]), train=False, t=inp["t"], noise_t=inp["noise_t"], noise_1=inp["noise_1"])
+    g = load_golden("te_concat_l1")
+    np.testing.assert_allclose([l.item(), a.item(), b.item(), c.item()], g["train_losses"], rtol=1e-2)
+    sd = model.state_dict()
+    assert "lm_head.bias" not in sd and tuple(sd["lm_head.weight"].shape) == (hp["VOCAB_SIZE"], 16) and sd["lm_head.weight"].is_contiguous()
+    model2 = make_model(pkg, hp, precision="bf16", P=O.init_params(hp, seed=5, closed_form=False))
+    model2.load_state_dict(sd)
+    assert torch.equal(model2.flat, model.flat) and torch.equal(model2.shadow_hi, model.shadow_hi)
+    ids, restored = pkg.sample(model.eval(), inp["batch"]["image_clip"].to(DEV), n_steps=3)
+    assert tuple(ids.shape) == (hp["BATCH_SIZE"], 16) and tuple(restored.shape) == (hp["BATCH_SIZE"], 18, 16)
+    lg = model.lm_head(restored[:, :16])
+    assert torch.equal(lg.argmax(-1), ids)
