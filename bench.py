@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import contextlib
 import os
 import statistics
 import subprocess
@@ -35,7 +36,7 @@ def emit(line: dict):
 
 import torch  # noqa: E402
 
-TRAIN_GFLOP_PER_ROW = {6: 6.1730, 12: 10.7774}  # algorithmic 2*MAC, fwd+dgrad+wgrad, frozen lm_head x2, no recompute
+TRAIN_GFLOP_PER_ROW = {6: 6.1730, 12: 10.7774, "bert-large": 129.2953}  # algorithmic 2*MAC, fwd+dgrad+wgrad, frozen lm_head x2, no recompute
 FWD_GFLOP_PER_ROW_NO_HEAD = {6: 1.5576, 12: 3.0924}
 LM_HEAD_GFLOP_PER_ROW = 0.7501
 
@@ -107,16 +108,17 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_host_batch(B: int, seed: int):
+def synthetic_host_batch(B: int, seed: int, ML: int = 16):
     g = torch.Generator().manual_seed(seed)
-    b = {"input_ids": torch.randint(0, 30522, (B, 16), generator=g), "attention_mask": torch.ones(B, 16, dtype=torch.int64),
+    b = {"input_ids": torch.randint(0, 30522, (B, ML), generator=g), "attention_mask": torch.ones(B, ML, dtype=torch.int64),
          "image_clip": torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1),
          "text_clip": torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1)}
     return {k: v.pin_memory() if torch.cuda.is_available() else v for k, v in b.items()}
 
 
 # ------------------------------------------------------------------------------------------------------------ CPU (reference) arm
-def cpu_reference_steps(layers: int, steps: int, warmup: int, B: int = 8, S: int = 24, workload: str = "train"):
+def cpu_reference_steps(layers: int, steps: int, warmup: int, B: int = 8, S: int = 24, workload: str = "train", device: str = "cpu",
+                        autocast: bool = False):
     """The reference's CPU path through the oracle port (the reference is Python + HF transformers and cannot travel to the
     GPU box; oracle/clipdlm_oracle.py restates it op for op and is pinned against it). fp32, train mode (dropout on), AdamW step
     included, all host threads. Each step is a bounded sample: B captions x S noise levels (+ the x_1 pass)."""
@@ -125,24 +127,36 @@ def cpu_reference_steps(layers: int, steps: int, warmup: int, B: int = 8, S: int
     torch.set_num_threads(threads)
     hp = O.default_hparams()
     hp.update(BATCH_SIZE=B, SAMPLE_SIZE=S, N_LAYERS=layers)
-    P = O.init_params(hp, seed=0)
-    acp = O.alpha_cumprod(hp)
-    batch = O.synthetic_batch(hp, seed=0)
+    P = {k: v.to(device) for k, v in O.init_params(hp, seed=0).items()}
+    acp = O.alpha_cumprod(hp).to(device)
+    batch = {k: v.to(device) for k, v in O.synthetic_batch(hp, seed=0).items()}
     times = []
+    on_gpu = device != "cpu"  # --ref-device cuda: the same eager PyTorch ops on the B200 itself, optionally under autocast(bf16)
+
+    def clock():
+        if on_gpu:
+            torch.cuda.synchronize()
+        return time.perf_counter()
+
+    ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if (on_gpu and autocast) else contextlib.nullcontext
     if workload == "train":
         opt = O.AdamW(O.make_trainable(P, hp), lr=1e-4)
         for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            O.train_func(P, opt, batch, hp, acp, True)
+            t0 = clock()
+            with ctx():
+                O.train_func(P, opt, batch, hp, acp, True)
+            t1 = clock()
             if i >= warmup:
-                times.append(time.perf_counter() - t0)
+                times.append(t1 - t0)
         rows = B * (S + 1)
     else:
         for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            O.sample(P, batch["image_clip"], hp, n_steps=S)
+            t0 = clock()
+            with ctx():
+                O.sample(P, batch["image_clip"], hp, n_steps=S)
+            t1 = clock()
             if i >= warmup:
-                times.append(time.perf_counter() - t0)
+                times.append(t1 - t0)
         rows = B
     return times, rows, threads
 
@@ -152,6 +166,9 @@ def run_reference(args):
     if rank != 0:
         return
     W = min(args.warmup, 1)
+    gpu_ref = args.ref_device == "cuda"
+    if gpu_ref:
+        return run_reference_on_gpu(args)
     if args.workload == "train":
         B, S = 8, 24
         times, rows, threads = cpu_reference_steps(args.layers, args.steps, W, B, S, "train")
@@ -175,8 +192,39 @@ def run_reference(args):
     emit(line)
 
 
+def run_reference_on_gpu(args):
+    """Extra comparison, not the driver's reference arm: the reference's own eager PyTorch op sequence (the oracle port) executed on
+    the B200 (`--impl reference --ref-device cuda [--ref-autocast]`), fp32 or autocast(bf16), train mode, AdamW step included.
+    The reference materialises fp32 logits [rows, 16, 30522] twice (lm_head output + softmax), so its batch is capped by memory:
+    --ref-batch captions x --ref-samples noise levels per step (default 8 x 100, CLIP-DDPM.py's own defaults)."""
+    B, S = args.ref_batch, args.ref_samples
+    W = max(1, min(args.warmup, 2))
+    if args.workload == "train":
+        times, rows, _ = cpu_reference_steps(args.layers, args.steps, W, B, S, "train", "cuda", args.ref_autocast)
+        sec = sum(times)
+        value = rows * len(times) / sec / (S + 1.0)
+        metric, unit = "training samples/sec (seq=16)", f"captions/s (1 caption = {S + 1} noised sequences)"
+        what = f"train step, {B} captions x {S}+1 noise levels = {rows} encoder rows"
+    else:
+        times, rows, _ = cpu_reference_steps(args.layers, args.steps, W, B, S, "denoise", "cuda", args.ref_autocast)
+        sec = sum(times)
+        value = rows * len(times) / sec
+        metric, unit = f"denoise-loop captions/sec ({S} steps)", "captions/s"
+        what = f"denoise loop, {B} captions x {S} steps, lm_head every step"
+    emit({"impl": "reference", "ref_device": "cuda", "ref_dtype": "autocast-bf16" if args.ref_autocast else "f32", "metric": metric, "value": value,
+          "unit": unit, "n_gpus": 1, "steps": len(times), "warmup": W, "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True,
+          "data": "synthetic", "config": {"workload": f"eager PyTorch restatement of CLIP-DDPM.py on the B200: {what}, {args.layers}L", "global_batch": B,
+                                           "sample_size": S, "layers": args.layers},
+          "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
+
+
 def workload_config(args, B_override=None):
     B = args.batch
+    if getattr(args, "model", "distilbert") == "bert-large":
+        return {"workload": f"CLIP-DDPM.py train_func on a bert-large-shaped encoder (24L/1024/16H/4096), seq_len=64 (+2 CLIP positions), bs={B} captions/GPU x "
+                            f"SAMPLE_SIZE={args.samples} (+x_1 pass) = {B * (args.samples + 1)} encoder rows/step/GPU, x_0-predict, concat fusion, L1 + rounding CE, "
+                            f"dropout 0.1, AdamW (BASELINE.json configs[4])", "global_batch": B * args.gpus, "seq_len": 64, "sample_size": args.samples,
+                "layers": 24, "parallelism": f"dp{args.gpus}", "chunk_rows": args.chunk_rows, "l2": "working set >> L2, 256 MB L2 flush between timed steps"}
     if args.workload == "train":
         return {"workload": f"CLIP-DDPM.py train_func, DistilBertConfig() {args.layers}L/768/12H/3072 ('bert-base' in BASELINE.json), seq_len=16 (+2 CLIP positions), "
                             f"bs={B} captions/GPU x SAMPLE_SIZE={args.samples} (+x_1 pass) = {B * (args.samples + 1)} encoder rows/step/GPU, x_0-predict, concat fusion, "
@@ -198,11 +246,13 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     B, S = args.batch, args.samples
     hp = clipdlm.default_hparams(BATCH_SIZE=B, SAMPLE_SIZE=S, N_LAYERS=args.layers)
+    if args.model == "bert-large":  # BASELINE.json configs[4]: bert-large-shaped 24L/1024/16H/4096, seq_len 64 (+2 CLIP positions)
+        hp = clipdlm.default_hparams(BATCH_SIZE=B, SAMPLE_SIZE=S, N_LAYERS=24, DIM=1024, N_HEADS=16, HIDDEN_DIM=4096, MAX_LENGTH=64)
     torch.manual_seed(0)
     model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=args.chunk_rows)
     parallel.enable_data_parallel(model)
     trainer = clipdlm.AdamW(model.parameters(), lr=hp["LEARNING_RATE"])
-    host = synthetic_host_batch(B if args.workload == "train" else args.denoise_batch, seed=rank)
+    host = synthetic_host_batch(B if args.workload == "train" else args.denoise_batch, seed=rank, ML=hp["MAX_LENGTH"])
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -311,7 +361,7 @@ def run_ours(args):
                 "kernels": kernels}
         if args.workload == "train":
             rows_s = value * (S + 1)
-            alg = rows_s * TRAIN_GFLOP_PER_ROW.get(args.layers, float("nan")) / 1e3
+            alg = rows_s * TRAIN_GFLOP_PER_ROW.get("bert-large" if args.model == "bert-large" else args.layers, float("nan")) / 1e3
             line["noised_sequences_per_s"] = rows_s
             line["algorithmic_tflops"] = alg
             line["algorithmic_frac_of_sustained_peak"] = alg / pk["tf_sustained"] / world
@@ -338,12 +388,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "denoise"])
     ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--model", default="distilbert", choices=["distilbert", "bert-large"],
+                    help="bert-large = BASELINE.json configs[4] (24L/1024/16H/4096, seq_len 64): use with --batch 64 --chunk-rows 1024")
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--samples", type=int, default=100)
     ap.add_argument("--chunk-rows", type=int, default=8192)
     ap.add_argument("--denoise-batch", type=int, default=1024)
     ap.add_argument("--denoise-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: 'cuda' runs the eager PyTorch port on the GPU (extra comparison)")
+    ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--ref-samples", type=int, default=100)
     ap.add_argument("--profile-mode", action="store_true", help="for runs under ncu: no forced warm-up, no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

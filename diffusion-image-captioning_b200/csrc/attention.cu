@@ -702,7 +702,7 @@ int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, i
   CLIPDLM_CHECK(qkv && qkv->hi && ctx && ctx->hi && keymask, "attn_fwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_fwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_fwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && (g_force_path == 0 || g_force_path == 3))
+  if (qkv->lo == nullptr && ctx->lo == nullptr && ((L <= 32 && (g_force_path == 0 || g_force_path == 3)) || (L > 32 && g_force_path != 1)))
     return launch_attn_umma<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && g_force_path == 2)
     return launch_ring<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
@@ -731,7 +731,8 @@ int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cl
   CLIPDLM_CHECK(qkv && qkv->hi && dctx && dctx->hi && dqkv && dqkv->hi && keymask, "attn_bwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_bwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_bwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && g_force_path == 3)
+  // 32 < L <= 128 (bert-large / seq_len 64 shapes): tcgen05 tiles with one or two sequences per tile, both directions
+  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && ((L <= 32 && g_force_path == 3) || (L > 32 && g_force_path != 1)))
     return launch_attn_umma<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
                                   make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && L <= 32 && (g_force_path == 0 || g_force_path == 2))

@@ -205,7 +205,8 @@ def _attn_ref(qkv, km_bool, R, L, D, H, mask_mult=None):
 
 
 @pytest.mark.parametrize("pair", [False, True])
-@pytest.mark.parametrize("L,R,D", [(18, 37, 768), (16, 5, 768), (66, 7, 1024), (1, 3, 768)])
+@pytest.mark.parametrize("L,R,D", [(18, 37, 768), (16, 5, 768), (66, 7, 1024), (1, 3, 768), (33, 5, 768), (40, 9, 768), (64, 4, 768),
+                                   (97, 3, 1024), (128, 2, 768)])
 def test_attention_fwd_bwd(G, L, R, D, pair):
     H = D // 64
     qkv = torch.randn(R * L, 3 * D, device=G.DEV)
@@ -289,6 +290,44 @@ def test_attention_mma_path_matches_simt_with_dropout(G):
     for path in (0, 2, 3):
         assert rel(outs[path][0], outs[1][0]) < 1e-2 and rel(outs[path][1], outs[1][1]) < 1.5e-2, path
     # a differing mask would change ~10 % of the probabilities by 100 %: far outside these bounds
+
+
+@pytest.mark.parametrize("L,R", [(40, 7), (66, 5), (128, 3)])
+def test_attention_long_rows_umma_matches_simt_with_dropout(G, L, R):
+    """32 < L <= 128, plain bf16: tcgen05 tiles with two / one sequence(s) per tile (the bert-large, seq_len 64 shape is L = 66). The
+    fp32 SIMT kernels must see the same dropout mask, forward and backward."""
+    D, H, p = 1024, 16, 0.1
+    qkv = torch.randn(R * L, 3 * D, device=G.DEV).bfloat16()
+    dctx = torch.randn(R * L, D, device=G.DEV).bfloat16()
+    km = torch.rand(R, L, device=G.DEV) > 0.2
+    km[:, 1] = True
+    kw = (L + 31) // 32
+    words = torch.zeros(R, kw, device=G.DEV, dtype=torch.int64)
+    for j in range(L):
+        words[:, j // 32] |= km[:, j].long() << (j % 32)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+    lib, Lb = G.lib(), G.L
+    outs = {}
+    for simt in (0, 1):
+        lib.clipdlm_attn_force_simt(simt)
+        ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
+        dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
+        Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx, None)), 777, 5, p, G.st()))
+        Lb.check(lib.clipdlm_attn_bwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), C.byref(G.bfp(dctx, None)), R, L, D, H, C.byref(G.bfp(dq, None)),
+                                      777, 5, p, G.st()))
+        torch.cuda.synchronize()
+        outs[simt] = (ctx.float(), dq.float())
+    lib.clipdlm_attn_force_simt(0)
+    assert rel(outs[0][0], outs[1][0]) < 1e-2 and rel(outs[0][1], outs[1][1]) < 1.5e-2
+    # repeated launches on the persistent tiles (stale P / dS blocks of earlier groups must not leak): a second, different input
+    qkv2 = torch.randn(R * L, 3 * D, device=G.DEV).bfloat16()
+    ctx_a = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16); ctx_b = torch.zeros_like(ctx_a)
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv2, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx_a, None)), 0, 0, 0.0, G.st()))
+    lib.clipdlm_attn_force_simt(1)
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv2, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx_b, None)), 0, 0, 0.0, G.st()))
+    lib.clipdlm_attn_force_simt(0)
+    torch.cuda.synchronize()
+    assert rel(ctx_a.float(), ctx_b.float()) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------------------------ embed / loss / misc

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the attention kernels at the train-chunk shape (R = 4096 sequences x L = 18, 12 heads): paths 0 (tcgen05 packed
-tiles), 2 (mma.sync TMA ring), with and without dropout. Triage tool."""
+tiles), 2 (mma.sync TMA ring), with and without dropout. Triage tool.
+SEQ / DIM / ROWS env vars select other shapes (SEQ > 32: the one- / two-sequence-per-tile tcgen05 kernels, e.g. SEQ=66 DIM=1024)."""
 import ctypes as C
 import os
 import sys
@@ -13,14 +14,18 @@ import clipdlm  # noqa: E402,F401
 from clipdlm import _lib as L  # noqa: E402
 
 DEV = "cuda:0"
-R, Ls, D, H = int(os.environ.get("ROWS", 4096)), 18, 768, 12
+R, Ls, D = int(os.environ.get("ROWS", 4096)), int(os.environ.get("SEQ", 18)), int(os.environ.get("DIM", 768))
+H = D // 64
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
 qkv = torch.randn(R * Ls, 3 * D, device=DEV).bfloat16()
 dctx = torch.randn(R * Ls, D, device=DEV).bfloat16()
 ctx = torch.empty(R * Ls, D, device=DEV, dtype=torch.bfloat16)
 dqkv = torch.empty(R * Ls, 3 * D, device=DEV, dtype=torch.bfloat16)
-km = torch.full((R,), (1 << 17) - 1, device=DEV, dtype=torch.int32)
+KW = (Ls + 31) // 32
+km = torch.full((R, KW), -1, device=DEV, dtype=torch.int32)  # every key visible (bits >= L are ignored)
+if Ls <= 32:
+    km = torch.full((R,), (1 << 17) - 1, device=DEV, dtype=torch.int32)
 bq, bc, bd, bg = L.Bf(qkv.data_ptr(), None), L.Bf(ctx.data_ptr(), None), L.Bf(dctx.data_ptr(), None), L.Bf(dqkv.data_ptr(), None)
 
 
@@ -38,7 +43,7 @@ def timeit(fn, iters=20):
 
 
 fwd_bytes, bwd_bytes = R * Ls * D * 2 * 4, R * Ls * D * 2 * 7
-for path in (3, 2):
+for path in ((3, 2) if Ls <= 32 else (0,)):
     lib.clipdlm_attn_force_simt(path)
     for p in (0.0, 0.1):
         f = timeit(lambda: L.check(lib.clipdlm_attn_fwd(C.byref(bq), km.data_ptr(), R, Ls, D, H, C.byref(bc), 1, 1, p, st)))
