@@ -225,6 +225,11 @@ def workload_config(args, B_override=None):
                             f"SAMPLE_SIZE={args.samples} (+x_1 pass) = {B * (args.samples + 1)} encoder rows/step/GPU, x_0-predict, concat fusion, L1 + rounding CE, "
                             f"dropout 0.1, AdamW (BASELINE.json configs[4])", "global_batch": B * args.gpus, "seq_len": 64, "sample_size": args.samples,
                 "layers": 24, "parallelism": f"dp{args.gpus}", "chunk_rows": args.chunk_rows, "l2": "working set >> L2, 256 MB L2 flush between timed steps"}
+    if args.workload == "train" and getattr(args, "train_embedding", False):
+        return {"workload": f"CLIP-DDPM.py train_func with TRAIN_EMBEDDING=True (IN_CHANNEL=16 learned embedding, trainable lm_head + in/out projections), "
+                            f"{args.layers}L/768, seq_len=16, bs={B} x SAMPLE_SIZE={args.samples}", "global_batch": B * args.gpus, "seq_len": 16,
+                "sample_size": args.samples, "layers": args.layers, "parallelism": f"dp{args.gpus}", "chunk_rows": args.chunk_rows,
+                "l2": "working set >> L2, 256 MB L2 flush between timed steps"}
     if args.workload == "train":
         return {"workload": f"CLIP-DDPM.py train_func, DistilBertConfig() {args.layers}L/768/12H/3072 ('bert-base' in BASELINE.json), seq_len=16 (+2 CLIP positions), "
                             f"bs={B} captions/GPU x SAMPLE_SIZE={args.samples} (+x_1 pass) = {B * (args.samples + 1)} encoder rows/step/GPU, x_0-predict, concat fusion, "
@@ -248,6 +253,8 @@ def run_ours(args):
     hp = clipdlm.default_hparams(BATCH_SIZE=B, SAMPLE_SIZE=S, N_LAYERS=args.layers)
     if args.model == "bert-large":  # BASELINE.json configs[4]: bert-large-shaped 24L/1024/16H/4096, seq_len 64 (+2 CLIP positions)
         hp = clipdlm.default_hparams(BATCH_SIZE=B, SAMPLE_SIZE=S, N_LAYERS=24, DIM=1024, N_HEADS=16, HIDDEN_DIM=4096, MAX_LENGTH=64)
+    if args.train_embedding:  # CLIP-DDPM.py:98-102: 16-channel learned embedding, trainable lm_head and in/out projections
+        hp.update(TRAIN_EMBEDDING=True, IN_CHANNEL=16)
     torch.manual_seed(0)
     model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=args.chunk_rows)
     parallel.enable_data_parallel(model)
@@ -395,6 +402,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=8192)
     ap.add_argument("--denoise-batch", type=int, default=1024)
     ap.add_argument("--denoise-steps", type=int, default=100)
+    ap.add_argument("--train-embedding", action="store_true", help="TRAIN_EMBEDDING=True variant of the train step (use with --no-cpu-baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: 'cuda' runs the eager PyTorch port on the GPU (extra comparison)")
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")

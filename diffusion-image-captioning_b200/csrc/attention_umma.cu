@@ -58,6 +58,23 @@ __device__ __forceinline__ void au_row_keep(const DropoutCfg& d, unsigned long l
   }
 }
 
+// keep bits (bit j = key 32 kc + j survives the dropout) of query row i: one Philox evaluation serves several passes over the row
+__device__ __forceinline__ uint32_t au_row_keep_bits(const DropoutCfg& d, unsigned long long rh, int i, int L, int kc) {
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 rnd = au_rand_block(d, rh, (i & 7) * 4 + c, (i >> 3) * 4 + kc);
+    const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      if (kc * 32 + jb * 8 >= L) continue;
+      bits |= ((w[jb] & 0xffffu) >= d.thresh16 ? 1u : 0u) << (jb * 8 + 2 * c);
+      bits |= ((w[jb] >> 16) >= d.thresh16 ? 1u : 0u) << (jb * 8 + 2 * c + 1);
+    }
+  }
+  return bits;
+}
+
 // x[j] *= keep-scale, in place (forward)
 __device__ __forceinline__ void au_row_drop(const DropoutCfg& d, unsigned long long rh, int i, int L, float (&x)[32], int kc = 0) {
 #pragma unroll
@@ -301,25 +318,24 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
           inv = 1.f / sum;
           out_scale = inv;
         } else {
-          float dp[32], ks[32];
+          float dp[32];
+          uint32_t kb[NC];   // dropout keep bits per key chunk, drawn once (first pass) and reused when dS is written
           const uint32_t dcol = tq + 128u + (uint32_t)(SL * slot);
           float sum = 0.f, edot = 0.f;   // sum_j e_j and sum_j e_j dP_j (through the dropout): dot = edot / sum
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
+            kb[c] = 0xffffffffu;
             if (!wlive || c * 32 >= a.L) continue;
             tmem_ld32(scol + 32 * c, p);
             tmem_ld32(dcol + 32 * c, dp);
             au_mask_scale(p, km[c], sl);
-            if (dropping) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ks[j] = 0.f;
-              au_row_keep(a.drop, rh, i, a.L, ks, c);
-            }
+            if (dropping) kb[c] = au_row_keep_bits(a.drop, rh, i, a.L, c);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float e = ex2_ftz(p[j] - mx);
               sum += e;
-              edot = fmaf(dropping ? dp[j] * ks[j] : dp[j], e, edot);
+              const float kj = (kb[c] & (1u << j)) ? a.drop.scale : 0.f;
+              edot = fmaf(dropping ? dp[j] * kj : dp[j], e, edot);
             }
           }
           inv = 1.f / sum;
@@ -336,17 +352,13 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
               tmem_ld32(scol + 32 * c, p);
               tmem_ld32(dcol + 32 * c, dp);
               au_mask_scale(p, km[c], sl);
-              if (dropping) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) ks[j] = 0.f;
-                au_row_keep(a.drop, rh, i, a.L, ks, c);
-              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float pj = live ? ex2_ftz(p[j] - mx) * inv : 0.f;
-                const float dpj = dropping ? dp[j] * ks[j] : dp[j];        // gradient through the dropout
-                dp[j] = pj * (dpj - dot) * a.scale;                       // dS
-                p[j] = dropping ? pj * ks[j] : pj;                        // dropped probabilities: what multiplied V in the forward
+                const float kj = (kb[c] & (1u << j)) ? a.drop.scale : 0.f;
+                const float dpj = dropping ? dp[j] * kj : dp[j];        // gradient through the dropout
+                dp[j] = pj * (dpj - dot) * a.scale;                     // dS
+                p[j] = dropping ? pj * kj : pj;                         // dropped probabilities: what multiplied V in the forward
               }
             } else {
 #pragma unroll

@@ -733,14 +733,20 @@ __global__ void __launch_bounds__(256) embed_loss_kernel(CBfPtr x_out, const flo
 // fp32 on purpose: the CLIP projections feed the parity-mode (fp32-class) path and are 0.4 GFLOP per call.
 template <bool KCONTIG>
 __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ bias,
-                                                         int M, int N, int K, float* __restrict__ C, float* __restrict__ csum) {
+                                                         int M, int N, int K, float* __restrict__ C, float* __restrict__ csum,
+                                                         int k_per_split) {
   __shared__ __align__(16) float As[16][68];
   __shared__ __align__(16) float Bs[16][68];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
   float acc[4][4] = {};
   float asum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // KCONTIG = false only: gridDim.z > 1 splits the reduction (rows of a long token dimension) across blocks, partial sums are
+  // combined with fp32 atomics (the destination is a gradient accumulator anyway)
+  const int k_begin = KCONTIG ? 0 : blockIdx.z * k_per_split;
+  const int k_end = KCONTIG ? K : min(K, k_begin + k_per_split);
+  const bool split = !KCONTIG && gridDim.z > 1;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
     if (KCONTIG) {
       const int r = tid >> 2, kq = (tid & 3) * 4;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -751,8 +757,8 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
     } else {
       const int kk = tid >> 4, q = (tid & 15) * 4;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (k0 + kk < K && m0 + q < M) a = __ldg(reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * M + m0 + q));
-      if (k0 + kk < K && n0 + q < N) b = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kk) * N + n0 + q));
+      if (k0 + kk < k_end && m0 + q < M) a = __ldg(reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * M + m0 + q));
+      if (k0 + kk < k_end && n0 + q < N) b = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kk) * N + n0 + q));
       *reinterpret_cast<float4*>(&As[kk][q]) = a;
       *reinterpret_cast<float4*>(&Bs[kk][q]) = b;
     }
@@ -780,9 +786,13 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       if (KCONTIG) C[(size_t)m * N + n] = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
+      else if (split) atomicAdd(C + (size_t)m * N + n, acc[i][j]);
       else C[(size_t)m * N + n] += acc[i][j];
     }
-    if (!KCONTIG && csum != nullptr && blockIdx.y == 0 && tx == 0) csum[m] += asum[i];
+    if (!KCONTIG && csum != nullptr && blockIdx.y == 0 && tx == 0) {
+      if (split) atomicAdd(csum + m, asum[i]);
+      else csum[m] += asum[i];
+    }
   }
 }
 
@@ -1122,14 +1132,25 @@ int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* 
 int small_linear_fwd_dispatch(const float* x, const float* w, const float* b, int B, int K, int N, float* y, cudaStream_t st) {
   CLIPDLM_CHECK(x && w && y && B > 0 && K % 4 == 0, "small_linear_fwd: bad arguments (K must be a multiple of 4)");
   dim3 grid((B + 63) / 64, (N + 63) / 64);
-  small_gemm_kernel<true><<<grid, 256, 0, st>>>(x, w, b, B, N, K, y, nullptr);
+  small_gemm_kernel<true><<<grid, 256, 0, st>>>(x, w, b, B, N, K, y, nullptr, 0);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int small_linear_bwd_dispatch(const float* x, const float* dy, int B, int K, int N, float* dw, float* db, cudaStream_t st) {
   CLIPDLM_CHECK(x && dy && dw && B > 0 && K % 4 == 0 && N % 4 == 0, "small_linear_bwd: bad arguments (K, N must be multiples of 4)");
-  dim3 grid((N + 63) / 64, (K + 63) / 64);   // dW [N, K]: rows = output features, reduction over the B captions
-  small_gemm_kernel<false><<<grid, 256, 0, st>>>(dy, x, nullptr, N, K, B, dw, db);
+  dim3 grid((N + 63) / 64, (K + 63) / 64);   // dW [N, K]: rows = output features, reduction over the B rows
+  // a long reduction (the TRAIN_EMBEDDING projections reduce over every token of a chunk) is split across blocks; the CLIP
+  // projections (B = captions of the batch) keep one block per tile and plain stores
+  int splits = 1;
+  if (B > 4096) {
+    const int tiles = (int)(grid.x * grid.y);
+    splits = (4 * num_sms() + tiles - 1) / tiles;
+    if (splits > (B + 1023) / 1024) splits = (B + 1023) / 1024;
+    if (splits < 1) splits = 1;
+  }
+  const int k_per_split = ((B + splits - 1) / splits + 15) / 16 * 16;
+  grid.z = (unsigned)((B + k_per_split - 1) / k_per_split);
+  small_gemm_kernel<false><<<grid, 256, 0, st>>>(dy, x, nullptr, N, K, B, dw, db, k_per_split);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }

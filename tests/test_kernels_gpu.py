@@ -545,3 +545,18 @@ def test_pack_rows_and_embedding_bwd(G):
     G.L.check(G.lib().clipdlm_embedding_bwd(dx.data_ptr(), None, ids.data_ptr(), 1, B * Ltxt, ch, dE2.data_ptr(), G.st()))
     ref2 = torch.zeros(V, ch, device=G.DEV, dtype=torch.float64).index_add_(0, ids.long(), dx[0].double())
     assert rel(dE2, ref2) < 1e-6
+
+
+@pytest.mark.parametrize("B,K,N", [(10007 * 4, 16, 768), (9001 * 4, 768, 16)])
+def test_small_linear_long_reduction(G, B, K, N):
+    """The TRAIN_EMBEDDING projections: forward over every token of a chunk, weight / bias gradients reduced over the tokens (split across
+    blocks, fp32 atomics)."""
+    x = torch.randn(B, K, device=G.DEV); w = torch.randn(N, K, device=G.DEV) * 0.1; b = torch.randn(N, device=G.DEV)
+    y = torch.empty(B, N, device=G.DEV)
+    G.L.check(G.lib().clipdlm_small_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), B, K, N, y.data_ptr(), G.st()))
+    assert rel(y, x.double() @ w.double().t() + b.double()) < 1e-5
+    dy = torch.randn(B, N, device=G.DEV)
+    dw = torch.full((N, K), 0.5, device=G.DEV); db = torch.full((N,), -1.0, device=G.DEV)
+    G.L.check(G.lib().clipdlm_small_linear_bwd(x.data_ptr(), dy.data_ptr(), B, K, N, dw.data_ptr(), db.data_ptr(), G.st()))
+    assert rel(dw, dy.double().t() @ x.double() + 0.5) < 1e-5
+    assert rel(db, dy.double().sum(0) - 1.0) < 1e-5
