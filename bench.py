@@ -257,7 +257,22 @@ def run_ours(args):
         hp.update(TRAIN_EMBEDDING=True, IN_CHANNEL=16)
     torch.manual_seed(0)
     model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=args.chunk_rows)
-    parallel.enable_data_parallel(model)
+    dp_mode = "single GPU"
+    if world > 1:
+        dp_mode = "nccl all-reduce of the flat fp32 gradients + AdamW on every rank"
+        if args.workload == "train" and args.dp_exchange in ("auto", "fused"):
+            try:
+                parallel.enable_data_parallel(model, fused=True)
+                dp_mode = ("fused reduce-scatter + AdamW + all-gather kernel over " +
+                           ("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if model.dp_fused["multicast"] else "NVLink peer loads / stores"))
+            except Exception as ex:  # symmetric memory unavailable on this box: the NCCL exchange is the other GPU path, not a CPU fallback
+                if args.dp_exchange == "fused":
+                    raise
+                sys.stderr.write(f"bench: fused data-parallel step unavailable ({type(ex).__name__}: {ex}); using the NCCL all-reduce\n")
+                model.dp_fused = None
+                parallel.enable_data_parallel(model, fused=False)
+        else:
+            parallel.enable_data_parallel(model, fused=False)
     trainer = clipdlm.AdamW(model.parameters(), lr=hp["LEARNING_RATE"])
     host = synthetic_host_batch(B if args.workload == "train" else args.denoise_batch, seed=rank, ML=hp["MAX_LENGTH"])
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -361,7 +376,7 @@ def run_ours(args):
         line = {"metric": "training samples/sec (seq=16)" if args.workload == "train" else "denoise-loop captions/sec (100 steps)",
                 "value": value, "unit": "captions/s (1 caption = 101 noised sequences)" if args.workload == "train" else "captions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args), dp_exchange=dp_mode),
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches + (args.steps if args.workload == "train" else 0), "clocks": clocks, "roofline": roofline,
@@ -403,6 +418,8 @@ def main():
     ap.add_argument("--denoise-batch", type=int, default=1024)
     ap.add_argument("--denoise-steps", type=int, default=100)
     ap.add_argument("--train-embedding", action="store_true", help="TRAIN_EMBEDDING=True variant of the train step (use with --no-cpu-baseline)")
+    ap.add_argument("--dp-exchange", default="auto", choices=["auto", "fused", "nccl"],
+                    help="N > 1 gradient exchange: fused = reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory; auto = fused, NCCL if unavailable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: 'cuda' runs the eager PyTorch port on the GPU (extra comparison)")
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")

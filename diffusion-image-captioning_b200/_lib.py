@@ -93,6 +93,14 @@ class LossCfg(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class DpBuffers(C.Structure):
+    _fields_ = [("rank", i32), ("world", i32), ("p", c_p * MAX_PEERS), ("g", c_p * MAX_PEERS), ("shadow_hi", c_p * MAX_PEERS),
+                ("shadow_lo", c_p * MAX_PEERS), ("p_mc", c_p), ("g_mc", c_p), ("shadow_hi_mc", c_p), ("shadow_lo_mc", c_p)]
+
+
 EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD = 0, 1, 2, 3
 
 PROF_CATEGORIES = ("gemm_fwd", "gemm_dgrad", "gemm_wgrad", "gemm_lse", "gemm_smgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "embed",
@@ -130,6 +138,8 @@ _SIGS = {
     "clipdlm_small_linear_fwd": (C.c_int, [c_p, c_p, c_p, i32, i32, i32, c_p, c_p]),
     "clipdlm_small_linear_bwd": (C.c_int, [c_p, c_p, i32, i32, i32, c_p, c_p, c_p]),
     "clipdlm_adamw": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i32, f32, i32, c_p]),
+    "clipdlm_dp_slice": (C.c_int, [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "clipdlm_adamw_dp": (C.c_int, [C.POINTER(DpBuffers), c_p, c_p, i64, f32, f32, f32, f32, f32, i32, f32, c_p]),
     "clipdlm_to_bf16": (C.c_int, [c_p, c_p, c_p, i64, c_p]),
     "clipdlm_to_f32": (C.c_int, [c_p, c_p, c_p, i64, c_p]),
     "clipdlm_gather_rows_f32": (C.c_int, [C.POINTER(Bf), i64, i32, i32, i32, c_p, c_p]),

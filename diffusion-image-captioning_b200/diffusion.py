@@ -291,8 +291,9 @@ def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train:
         x_t_loss, x_1_loss, prob_loss = _finish(model, losses)
     l = x_t_loss + x_1_loss + prob_loss  # :481
     if train:
-        if model.dp_group is not None:
+        if model.dp_group is not None and model.dp_fused is None:
             torch.distributed.all_reduce(model.grad, group=model.dp_group)  # sum; AdamW applies 1/world
+        # (fused mode: trainer.step() is reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory, csrc/dp_fused.cu)
         trainer.step()  # :484
     return l, x_t_loss, x_1_loss, prob_loss
 

@@ -157,25 +157,10 @@ class DistilBertModel:
         self.grad = torch.zeros(self.n_params, device=dev)
         self.shadow_hi = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
         self.shadow_lo = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16) if precision == "bf16x3" else None
-        self._views: Dict[str, torch.Tensor] = {}
-        self._gviews: Dict[str, torch.Tensor] = {}
         self._scr: Dict[str, torch.Tensor] = {}
-        for name, slot, shape, rel in _slot_names(hp):
-            off = int(lib.clipdlm_param_offset(C.byref(self._cfg), slot)) + rel
-            cnt = int(math.prod(shape))
-            self._views[name] = self.flat[off:off + cnt].view(shape)
-            self._gviews[name] = self.grad[off:off + cnt].view(shape)
-        if sum(v.numel() for v in self._views.values()) != self.n_engine:
-            raise L.ClipdlmError("parameter name map does not cover the flat buffer")
-        if te_extra:  # the reference lists them before segment_embedding (CLIP-DDPM.py:259-265)
-            seg = [(k, self._views.pop(k), self._gviews.pop(k)) for k in ("segment_embedding.weight",) if k in self._views]
-            for name, stored, logical in te_extra:
-                o, cnt = self._te_off[name], int(math.prod(stored))
-                sl = tuple(slice(0, n) for n in logical)
-                self._views[name] = self.flat[o:o + cnt].view(stored)[sl]    # lm_head.weight: strided view into its zero-padded slot
-                self._gviews[name] = self.grad[o:o + cnt].view(stored)[sl]
-            for k, v, g in seg:
-                self._views[k], self._gviews[k] = v, g
+        self._te_extra = te_extra
+        self.dp_fused = None   # set by parallel.enable_data_parallel when the fused NVLink optimizer step is active
+        self._build_views()
         self._init_parameters(seed)
         self._engines: Dict[tuple, tuple] = {}
         self._launches_retired = 0
@@ -211,6 +196,48 @@ class DistilBertModel:
         self.sync_shadow()
 
     # ---------------------------------------------------------------------------------------------------------- params
+    def _build_views(self):
+        """Reference-named views into the flat parameter / gradient buffers."""
+        lib, hp = L.load(), self.hp
+        self._views: Dict[str, torch.Tensor] = {}
+        self._gviews: Dict[str, torch.Tensor] = {}
+        for name, slot, shape, rel in _slot_names(hp):
+            off = int(lib.clipdlm_param_offset(C.byref(self._cfg), slot)) + rel
+            cnt = int(math.prod(shape))
+            self._views[name] = self.flat[off:off + cnt].view(shape)
+            self._gviews[name] = self.grad[off:off + cnt].view(shape)
+        if sum(v.numel() for v in self._views.values()) != self.n_engine:
+            raise L.ClipdlmError("parameter name map does not cover the flat buffer")
+        if self._te_extra:  # the reference lists them before segment_embedding (CLIP-DDPM.py:259-265)
+            seg = [(k, self._views.pop(k), self._gviews.pop(k)) for k in ("segment_embedding.weight",) if k in self._views]
+            for name, stored, logical in self._te_extra:
+                o, cnt = self._te_off[name], int(math.prod(stored))
+                sl = tuple(slice(0, n) for n in logical)
+                self._views[name] = self.flat[o:o + cnt].view(stored)[sl]    # lm_head.weight: strided view into its zero-padded slot
+                self._gviews[name] = self.grad[o:o + cnt].view(stored)[sl]
+            for k, v, g in seg:
+                self._views[k], self._gviews[k] = v, g
+
+    def _rebind_buffers(self, flat, grad, shadow_hi, shadow_lo):
+        """Move the flat parameter / gradient / shadow buffers into caller-provided storage of the same size (symmetric memory for
+        the fused data-parallel step). Values are copied, the named views re-created, engines (which hold raw pointers) dropped."""
+        lib = L.load()
+        for e in self._engines.values():
+            self._launches_retired += int(lib.clipdlm_engine_launch_count(e[0]))
+            lib.clipdlm_engine_destroy(e[0])
+        self._engines = {}
+        flat.copy_(self.flat); grad.copy_(self.grad); shadow_hi.copy_(self.shadow_hi)
+        if self.shadow_lo is not None:
+            shadow_lo.copy_(self.shadow_lo)
+        self.flat, self.grad, self.shadow_hi = flat, grad, shadow_hi
+        self.shadow_lo = shadow_lo if self.shadow_lo is not None else None
+        self._build_views()
+        if self.hp["TRAIN_EMBEDDING"]:
+            self.embedding_weight = self._views["embedding.weight"]
+            self.lm_head_weight = self._views["lm_head.weight"]
+            self.embedding = _Embedding(self.embedding_weight)
+            self.lm_head = _LmHead(self)
+
     def _init_parameters(self, seed: Optional[int]):
         """HF DistilBERT init (N(0, 0.02) Linear / position weights, LayerNorm (1, 0), zero biases), nn.Linear default for the
         CLIP projections, N(0, 1) segment embedding (CLIP-DDPM.py:236,252-256)."""
@@ -490,8 +517,12 @@ class AdamW:
             raise TypeError("AdamW expects model.parameters() of a clipdlm DistilBertModel")
         self.model = owner
         self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
-        self.m = torch.zeros_like(owner.flat)
-        self.v = torch.zeros_like(owner.flat)
+        self._slice = (0, owner.n_params)
+        if owner.dp_fused is not None:  # fused data-parallel step: this rank only holds the moments of its own slice (ZeRO-1)
+            self._slice = owner.dp_fused["slice"]
+        n = self._slice[1] - self._slice[0]
+        self.m = torch.zeros(max(n, 4), device=owner.device)
+        self.v = torch.zeros(max(n, 4), device=owner.device)
         self.t = 0
 
     def zero_grad(self, set_to_none: bool = True):
@@ -503,6 +534,19 @@ class AdamW:
         g = self.param_groups[0]
         m = self.model
         self.t += 1
+        if m.dp_fused is not None:
+            f = m.dp_fused
+            if self._slice != f["slice"]:
+                raise L.ClipdlmError("AdamW was created before enable_data_parallel(): create the optimizer after it")
+            b0 = self._slice[0]
+            with torch.cuda.device(m.device):
+                f["barrier"](0)   # every rank's backward has finished writing its gradient buffer
+                L.check(L.load().clipdlm_adamw_dp(C.byref(f["bufs"]), self.m.data_ptr() - 4 * b0, self.v.data_ptr() - 4 * b0, m.n_params, g["lr"],
+                                                  g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.t, 1.0 / m.dp_world, m._stream()))
+                f["barrier"](1)   # every rank's slice of the new weights has landed in every copy
+                m.grad.zero_()
+            m._grads_dirty = False
+            return
         with torch.cuda.device(m.device):
             L.check(L.load().clipdlm_adamw(L.ptr(m.flat), L.ptr(m.grad), L.ptr(self.m), L.ptr(self.v), L.ptr(m.shadow_hi), L.ptr(m.shadow_lo),
                                            m.n_params, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.t,
@@ -510,7 +554,7 @@ class AdamW:
         m._grads_dirty = False  # the kernel zeroed them
 
     def state_dict(self):
-        return {"m": self.m.clone(), "v": self.v.clone(), "t": self.t, "param_groups": [dict(g) for g in self.param_groups]}
+        return {"m": self.m.clone(), "v": self.v.clone(), "t": self.t, "param_groups": [dict(g) for g in self.param_groups], "slice": self._slice}
 
     def load_state_dict(self, sd):
         self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])

@@ -162,6 +162,24 @@ int clipdlm_adamw(float* p, float* g, float* m, float* v, void* shadow_hi, void*
                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   int32_t zero_grad /* 1: g is cleared in the same pass (trainer.zero_grad(), CLIP-DDPM.py:471) */,
                   clipdlm_stream stream);
+/* Data-parallel step fused with the optimizer (csrc/dp_fused.cu): reduce-scatter of the gradients, AdamW on this rank's slice,
+ * all-gather of the updated fp32 weights + bf16 shadow - one kernel over NVLink / NVSwitch peer memory, replacing
+ * ncclAllReduce(flat gradients) + clipdlm_adamw. p / g / shadow_* [r] are rank r's flat buffers as mapped into THIS process (symmetric
+ * memory: same size and layout on every GPU); *_mc are the multicast (NVSwitch multimem) addresses of the same buffers, or NULL: then the
+ * slice is summed with loads from every peer and written with stores to every peer. m / v are indexed like the flat buffer but only
+ * the elements of this rank's slice (clipdlm_dp_slice) are touched, so a caller may pass (slice storage - slice begin). The caller
+ * orders the kernel against the other ranks (a barrier over the group before and after). */
+#define CLIPDLM_MAX_PEERS 16
+typedef struct clipdlm_dp_buffers {
+  int32_t rank, world;
+  float* p[CLIPDLM_MAX_PEERS]; float* g[CLIPDLM_MAX_PEERS];
+  void* shadow_hi[CLIPDLM_MAX_PEERS]; void* shadow_lo[CLIPDLM_MAX_PEERS]; /* shadow_lo[*] NULL unless split precision */
+  float* p_mc; float* g_mc; void* shadow_hi_mc; void* shadow_lo_mc;
+} clipdlm_dp_buffers_t;
+/* element range [*begin, *end) of the flat buffer of n elements owned by `rank` (multiples of 8 elements) */
+int clipdlm_dp_slice(int64_t n, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
+int clipdlm_adamw_dp(const clipdlm_dp_buffers_t* d, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int32_t step, float grad_scale /* 1 / world for a mean */, clipdlm_stream stream);
 /* fp32 -> bf16 (pair) conversion (weights shadow refresh, frozen embedding table). */
 int clipdlm_to_bf16(const float* x, void* hi, void* lo, int64_t n, clipdlm_stream stream);
 /* bf16 (pair) -> fp32. */

@@ -560,3 +560,50 @@ def test_small_linear_long_reduction(G, B, K, N):
     G.L.check(G.lib().clipdlm_small_linear_bwd(x.data_ptr(), dy.data_ptr(), B, K, N, dw.data_ptr(), db.data_ptr(), G.st()))
     assert rel(dw, dy.double().t() @ x.double() + 0.5) < 1e-5
     assert rel(db, dy.double().sum(0) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_adamw_dp_peer_path_emulated(G, world, pair):
+    """clipdlm_adamw_dp without multicast: `world` sets of flat buffers on ONE device stand in for the ranks; every "rank" runs the
+    fused kernel for its slice. All copies must end up holding AdamW(sum of the gradients) exactly as clipdlm_adamw computes it."""
+    n = 8 * 12345 + 8   # not a multiple of 8 * world
+    torch.manual_seed(3)
+    p0 = torch.randn(n, device=G.DEV)
+    gs = [torch.randn(n, device=G.DEV) * 0.1 for _ in range(world)]
+    ps = [p0.clone() for _ in range(world)]
+    his = [torch.zeros(n, device=G.DEV, dtype=torch.bfloat16) for _ in range(world)]
+    los = [torch.zeros(n, device=G.DEV, dtype=torch.bfloat16) if pair else None for _ in range(world)]
+    m_ref, v_ref = torch.rand(n, device=G.DEV) * 0.01, torch.rand(n, device=G.DEV) * 0.01
+    ms, vs = m_ref.clone(), v_ref.clone()
+    lib, Lb = G.lib(), G.L
+    # reference: plain kernel on the summed gradient
+    p_ref = p0.clone(); g_sum = torch.stack(gs).sum(0)
+    if world == 3:
+        g_sum = (gs[0] + gs[1]) + gs[2]
+    hi_ref = torch.zeros(n, device=G.DEV, dtype=torch.bfloat16); lo_ref = torch.zeros_like(hi_ref) if pair else None
+    Lb.check(lib.clipdlm_adamw(p_ref.data_ptr(), g_sum.clone().data_ptr(), m_ref.data_ptr(), v_ref.data_ptr(), hi_ref.data_ptr(), Lb.ptr(lo_ref), n,
+                               1e-3, 0.9, 0.999, 1e-8, 0.01, 5, 1.0 / world, 0, G.st()))
+    covered = torch.zeros(n, device=G.DEV, dtype=torch.int32)
+    for rank in range(world):
+        d = Lb.DpBuffers()
+        d.rank, d.world = rank, world
+        for r in range(world):
+            d.p[r], d.g[r], d.shadow_hi[r] = ps[r].data_ptr(), gs[r].data_ptr(), his[r].data_ptr()
+            d.shadow_lo[r] = los[r].data_ptr() if pair else None
+        b, e = C.c_int64(), C.c_int64()
+        Lb.check(lib.clipdlm_dp_slice(n, rank, world, C.byref(b), C.byref(e)))
+        assert b.value % 8 == 0 and (e.value % 8 == 0 or e.value == n)
+        covered[b.value:e.value] += 1
+        Lb.check(lib.clipdlm_adamw_dp(C.byref(d), ms.data_ptr(), vs.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 5, 1.0 / world, G.st()))
+    torch.cuda.synchronize()
+    assert bool((covered == 1).all())
+    tol = 0.0 if world <= 2 else 1e-6   # the order of a 3-way sum is the kernel's (rank order starting at the owner)
+    for r in range(world):
+        assert float((ps[r] - p_ref).abs().max()) <= tol * float(p_ref.abs().max()) + 0.0 if world <= 2 else rel(ps[r], p_ref) < 1e-6
+        if world <= 2:
+            assert torch.equal(his[r], hi_ref)
+            if pair:
+                assert torch.equal(los[r], lo_ref)
+    if world <= 2:
+        assert torch.equal(ms, m_ref) and torch.equal(vs, v_ref)
