@@ -160,6 +160,9 @@ _SIGS = {
     "clipdlm_feature_loss_f32": (C.c_int, [c_p, c_p, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p, c_p, i32, c_p, c_p, c_p]),
     "clipdlm_pack_rows_bf16": (C.c_int, [c_p, i64, i32, i32, i32, i32, c_p, c_p, c_p]),
     "clipdlm_embedding_bwd": (C.c_int, [c_p, c_p, c_p, i32, i64, i32, c_p, c_p]),
+    "clipdlm_row_mix_f32": (C.c_int, [c_p, c_p, c_p, f32, i32, i64, c_p]),
+    "clipdlm_row_split_f32": (C.c_int, [c_p, c_p, c_p, f32, i32, i64, c_p]),
+    "clipdlm_add_f32": (C.c_int, [c_p, c_p, i64, c_p]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
     "clipdlm_engine_profile": (C.c_int, [c_p, i32]),
     "clipdlm_engine_profile_read": (C.c_int, [c_p, c_p, i32]),

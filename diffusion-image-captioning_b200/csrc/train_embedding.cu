@@ -83,6 +83,40 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dx, const float* 
   if (acc != 0.f) atomicAdd(dE + (size_t)ids[j] * ch + c, acc);
 }
 
+// classifier-free guidance on fp32 encoder outputs (CLIP-DDPM.py:313-317): xu[r] <- guided[r] ? (1 + w) xg[r] - w xu[r] : xu[r]
+__global__ void row_mix_f32_kernel(float* __restrict__ xu, const float* __restrict__ xg, const int* __restrict__ guided, float w,
+                                   long long rowlen4, long long total4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    if (!guided[i / rowlen4]) continue;
+    const float4 a = reinterpret_cast<const float4*>(xu)[i], b = reinterpret_cast<const float4*>(xg)[i];
+    reinterpret_cast<float4*>(xu)[i] = make_float4((1.f + w) * b.x - w * a.x, (1.f + w) * b.y - w * a.y, (1.f + w) * b.z - w * a.z, (1.f + w) * b.w - w * a.w);
+  }
+}
+// its backward: the gradient of the mixed output goes (1 + w) to the guided pass and -w (1 on plain rows) to the unguided pass
+__global__ void row_split_f32_kernel(float* __restrict__ d_self, float* __restrict__ d_other, const int* __restrict__ guided, float w,
+                                     long long rowlen4, long long total4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g = reinterpret_cast<const float4*>(d_self)[i];
+    const bool gd = guided[i / rowlen4] != 0;
+    const float so = gd ? 1.f + w : 0.f, ss = gd ? -w : 1.f;
+    reinterpret_cast<float4*>(d_other)[i] = make_float4(so * g.x, so * g.y, so * g.z, so * g.w);
+    reinterpret_cast<float4*>(d_self)[i] = make_float4(ss * g.x, ss * g.y, ss * g.z, ss * g.w);
+  }
+}
+__global__ void add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    reinterpret_cast<float4*>(a)[i] = x;
+  }
+}
+static inline unsigned grid_for(long long n, int per_block = 256) {
+  long long b = (n + per_block - 1) / per_block;
+  const long long cap = 16LL * num_sms();
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 static int feature_loss_f32_dispatch(const float* y, const float* target, int target_rows, int R, int Ltxt, int L, int ch, int kind,
                                      long long R_total, int batch_size, float weight, double* loss_acc, const float* dce, int ld_dce, float* dy,
                                      float* d_target, cudaStream_t st) {
@@ -122,6 +156,28 @@ int clipdlm_pack_rows_bf16(const float* y, int64_t rows_out, int32_t Ltxt, int32
   long long blocks = (total + 255) / 256;
   if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
   pack_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, rows_out, Ltxt, L, ch, ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clipdlm_row_mix_f32(float* x_unguided, const float* x_guided, const int32_t* guided, float w, int32_t R, int64_t row_len,
+                        clipdlm_stream stream) {
+  CLIPDLM_CHECK(x_unguided && x_guided && guided && R > 0 && row_len > 0 && row_len % 4 == 0, "row_mix_f32: bad arguments");
+  const long long total4 = (long long)R * row_len / 4;
+  row_mix_f32_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(x_unguided, x_guided, guided, w, row_len / 4, total4);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int clipdlm_row_split_f32(float* d_self, float* d_other, const int32_t* guided, float w, int32_t R, int64_t row_len, clipdlm_stream stream) {
+  CLIPDLM_CHECK(d_self && d_other && guided && R > 0 && row_len > 0 && row_len % 4 == 0, "row_split_f32: bad arguments");
+  const long long total4 = (long long)R * row_len / 4;
+  row_split_f32_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(d_self, d_other, guided, w, row_len / 4, total4);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int clipdlm_add_f32(float* a, const float* b, int64_t n, clipdlm_stream stream) {
+  CLIPDLM_CHECK(a && b && n > 0 && n % 4 == 0, "add_f32: bad arguments");
+  add_f32_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }

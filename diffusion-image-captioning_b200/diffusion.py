@@ -133,7 +133,8 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
     if hp["TRAIN_EMBEDDING"]:
         if backward is None:
             backward = model.training and torch.is_grad_enabled()
-        return _loss_te(model, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, backward=backward, dropout_seed=dropout_seed)
+        return _loss_te(model, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, backward=backward, dropout_seed=dropout_seed,
+                        classifier_mask=classifier_mask)
     cfg = None
     if hp["CLASSIFIER_FREE_WEIGHT"] > 0:  # :406-410: per-row guidance draw; rows 0 / 1 pinned so that both kinds always occur
         if classifier_mask is None:
@@ -171,16 +172,22 @@ def loss(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, ma
 
 
 def _loss_te(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip, mask, idx, *, backward: bool, dropout_seed=None,
-             embed_coefs=None):
+             embed_coefs=None, classifier_mask=None):
     """loss() for TRAIN_EMBEDDING=True (train_embedding.py). The inputs x_t / x_1 / x_tgt / x_0 are functions of the trainable
     embedding; `embed_coefs = (ca_t [S], ca_1 [1], ca_tgt [S] or None)` (the sqrt(alpha_bar) factors of q_sample, CLIP-DDPM.py:360) lets
     the gradients that reach them be folded into d(embedding.weight) chunk by chunk. Called without it (a direct loss() call on
     explicit tensors) every other parameter gradient is still produced, exactly as autograd would treat detached inputs."""
     from . import train_embedding as TE
     hp = model.hp
-    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:
-        raise NotImplementedError("TRAIN_EMBEDDING=True with classifier-free-guidance TRAINING is not built (forward()/sample() support the mix)")
     S, B, ML, ch = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    cfg = None
+    if hp["CLASSIFIER_FREE_WEIGHT"] > 0:  # :406-410, as in loss()
+        if classifier_mask is None:
+            classifier_mask = (torch.rand((S * B, 1)) > hp["CLASSIFIER_FREE_PROB"]).to(torch.float32)
+            classifier_mask[0] = 0
+            classifier_mask[1] = 1
+        cfg = (classifier_mask.reshape(-1) != 0).to(model.device, torch.int32).contiguous()
+        assert cfg.numel() == S * B
     img, txt, mask32, ids32 = _prep_batch(model, image_clip, text_clip, mask, idx)
     x_t32, x_132, x_032 = x_t.float().contiguous(), x_1.float().contiguous(), x_0.float().contiguous()
     x0pred = bool(hp["X_0_PREDICTION"])
@@ -189,6 +196,7 @@ def _loss_te(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip
         assert tuple(x_tgt.shape) == tuple(x_t.shape)  # :420
     spc = max(1, model.chunk_rows // B)
     eng = model._engine(min(S, spc) * B, B, backward or model.training)
+    eng_g = model._engine(min(S, spc) * B, B, backward or model.training, tag="g") if cfg is not None else None
     losses = torch.zeros(4, dtype=torch.float64, device=model.device)
     seed = _next_seed() if dropout_seed is None else int(dropout_seed)
     d_x0 = torch.zeros_like(x_032) if backward else None
@@ -201,7 +209,8 @@ def _loss_te(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip
             target, trows = tgt_t[s0 * B:s1 * B], R
             d_tgt = torch.zeros(R, ML, ch, device=model.device) if backward else None
         dx = TE.loss_pass(model, eng, losses, 0, x16=x_t32[s0 * B:s1 * B], R=R, B=B, R_total=S * B, target=target, target_rows=trows, img=img,
-                          txt=txt, mask32=mask32, ids32=ids32, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], backward=backward, d_target=d_tgt)
+                          txt=txt, mask32=mask32, ids32=ids32, seed=seed + ci, use_embed=hp["USE_X_T_LOSS"], backward=backward, d_target=d_tgt,
+                          cfg_rows=cfg[s0 * B:s1 * B].contiguous() if cfg is not None else None, eng_guided=eng_g)
         if backward and embed_coefs is not None:
             TE.embedding_bwd(model, dx, embed_coefs[0][s0:s1].contiguous(), ids32, s1 - s0)
             if not x0pred and hp["USE_X_T_LOSS"]:
@@ -214,7 +223,7 @@ def _loss_te(model: DistilBertModel, x_t, x_1, x_tgt, x_0, image_clip, text_clip
     return _finish(model, losses)
 
 
-def _train_func_te(model: DistilBertModel, trainer, x: dict, train: bool, t, noise_t, noise_1, noise_tgt, dropout_seed):
+def _train_func_te(model: DistilBertModel, trainer, x: dict, train: bool, t, noise_t, noise_1, noise_tgt, dropout_seed, classifier_mask=None):
     """train_func (CLIP-DDPM.py:458-486) for TRAIN_EMBEDDING=True: x_0 = model.embedding(ids) carries gradient."""
     hp = model.hp
     dev = model.device
@@ -232,7 +241,7 @@ def _train_func_te(model: DistilBertModel, trainer, x: dict, train: bool, t, noi
         ca_n, _ = _coefs(hp, t_next)
     x_1 = diffuse_t(x_0, one, hp, noise_1)  # :468
     return _loss_te(model, x_t, x_1, x_tgt, x_0, x["image_clip"], x["text_clip"], x["attention_mask"], ids, backward=bool(train),
-                    dropout_seed=dropout_seed, embed_coefs=(ca, ca1, ca_n))
+                    dropout_seed=dropout_seed, embed_coefs=(ca, ca1, ca_n), classifier_mask=classifier_mask)
 
 
 def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train: bool = True, *, t: Optional[torch.Tensor] = None,
@@ -258,7 +267,7 @@ def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train:
     if train:
         trainer.zero_grad()  # :471
     if hp["TRAIN_EMBEDDING"]:
-        x_t_loss, x_1_loss, prob_loss = _train_func_te(model, trainer, x, train, t, noise_t, noise_1, noise_tgt, dropout_seed)
+        x_t_loss, x_1_loss, prob_loss = _train_func_te(model, trainer, x, train, t, noise_t, noise_1, noise_tgt, dropout_seed, classifier_mask)
     elif not hp["X_0_PREDICTION"] or hp["CLASSIFIER_FREE_WEIGHT"] > 0:
         # x_{t-1}-prediction objective (:466-467): explicit tensors through loss()
         x_0 = model.embedding(ids)

@@ -153,11 +153,14 @@ def argmax(model, y: torch.Tensor) -> torch.Tensor:
 
 
 def loss_pass(model, eng, losses: torch.Tensor, slot: int, *, x16, R, B, R_total, target, target_rows, img, txt, mask32, ids32, seed,
-              use_embed: bool, backward: bool, d_target: Optional[torch.Tensor] = None):
+              use_embed: bool, backward: bool, d_target: Optional[torch.Tensor] = None, cfg_rows: Optional[torch.Tensor] = None,
+              eng_guided=None):
     """One pass of loss() (CLIP-DDPM.py:415-437) over R rows in TRAIN_EMBEDDING mode: forward, the two loss terms into
     losses[slot] / losses[slot + 1] (float64 accumulators), and - if backward - every parameter gradient except the embedding's,
     whose input-side gradient d(x16) [R, ML, ch] is returned (the caller folds it through q_sample, see clipdlm_embedding_bwd).
-    d_target accumulates -d(loss)/d(target rows)."""
+    d_target accumulates -d(loss)/d(target rows). cfg_rows (int32 [R], 1 = classifier-free-guided row) switches on the guidance mix of
+    CLIP-DDPM.py:313-317: a second, guided encoder pass over the same projected input in `eng_guided`, the two fp32 encoder outputs
+    mixed row-wise BEFORE the output projection (:319), the gradient split (1 + w) / -w between the passes on the way back."""
     hp = model.hp
     lib = L.load()
     ML, Lf, ch, D, V = _dims(model)
@@ -168,6 +171,13 @@ def loss_pass(model, eng, losses: torch.Tensor, slot: int, *, x16, R, B, R_total
     xo = model._scratch("te_xo", (R, Lf, D), torch.float32)
     model._run_forward(eng, R=R, B=B, mode=0, guided=False, train=model.training, image_clip=img, text_clip=txt, attn_mask=mask32, x_in=u,
                        x_out=xo, drop_seed=seed)
+    w_cfg = float(hp["CLASSIFIER_FREE_WEIGHT"])
+    if cfg_rows is not None:
+        xg = model._scratch("te_xo_g", (R, Lf, D), torch.float32)
+        model._run_forward(eng_guided, R=R, B=B, mode=0, guided=True, train=model.training, image_clip=img, text_clip=txt, attn_mask=mask32,
+                           x_in=u, x_out=xg, drop_seed=seed + 104729)   # the reference's second self.model(...) call draws its own dropout
+        with torch.cuda.device(model.device):
+            L.check(lib.clipdlm_row_mix_f32(L.ptr(xo), L.ptr(xg), L.ptr(cfg_rows), w_cfg, R, Lf * D, model._stream()))
     y = out_proj(model, xo)
     ce_scale = 1.0 / R_total if kind in (0, 2) else 1.0 / hp["BATCH_SIZE"]  # CLIP-DDPM.py:437 vs :439-440
     dce = None
@@ -204,7 +214,15 @@ def loss_pass(model, eng, losses: torch.Tensor, slot: int, *, x16, R, B, R_total
     dxo = _lin_fwd(model, dy, w_out_t, None, T, ch, D, model._scratch("te_dxo", (R, Lf, D), torch.float32))
     du = model._scratch("te_du", (R, ML, D), torch.float32)
     with torch.cuda.device(model.device):
-        L.check(lib.clipdlm_engine_backward_from(eng, L.ptr(dxo), L.ptr(du), st))
+        if cfg_rows is None:
+            L.check(lib.clipdlm_engine_backward_from(eng, L.ptr(dxo), L.ptr(du), st))
+        else:
+            dxg = model._scratch("te_dxo_g", (R, Lf, D), torch.float32)
+            du_g = model._scratch("te_du_g", (R, ML, D), torch.float32)
+            L.check(lib.clipdlm_row_split_f32(L.ptr(dxo), L.ptr(dxg), L.ptr(cfg_rows), w_cfg, R, Lf * D, st))
+            L.check(lib.clipdlm_engine_backward_from(eng, L.ptr(dxo), L.ptr(du), st))
+            L.check(lib.clipdlm_engine_backward_from(eng_guided, L.ptr(dxg), L.ptr(du_g), st))
+            L.check(lib.clipdlm_add_f32(L.ptr(du), L.ptr(du_g), R * ML * D, st))   # both passes consumed the same projected input
     _lin_bwd(model, x16, du, T16, ch, D, gv["input_projection.weight"], gv["input_projection.bias"])
     w_in_t = model._views["input_projection.weight"].t().contiguous()  # [ch, D]
     dx16 = _lin_fwd(model, du, w_in_t, None, T16, D, ch, model._scratch("te_dx16", (R, ML, ch), torch.float32))

@@ -211,6 +211,14 @@ int clipdlm_feature_loss_f32(const float* y, const float* target, int32_t target
 /* Compact zero-padded GEMM operand: out[m, c] = c < ch ? y[(m / Ltxt) * L + m % Ltxt, c] : 0 for m < rows_out, c < ld; bf16 (pair). */
 int clipdlm_pack_rows_bf16(const float* y, int64_t rows_out, int32_t Ltxt, int32_t L, int32_t ch, int32_t ld, void* hi, void* lo,
                            clipdlm_stream stream);
+/* Classifier-free guidance on fp32 encoder outputs [R, row_len] (TRAIN_EMBEDDING path; CLIP-DDPM.py:313-317):
+ * x_unguided[r] <- guided[r] ? (1 + w) x_guided[r] - w x_unguided[r] : unchanged. */
+int clipdlm_row_mix_f32(float* x_unguided, const float* x_guided, const int32_t* guided, float w, int32_t R, int64_t row_len,
+                        clipdlm_stream stream);
+/* Backward of the mix: d_other[r] = guided[r] ? (1 + w) d_self[r] : 0 (gradient of the guided pass), then d_self[r] *= guided[r] ? -w : 1. */
+int clipdlm_row_split_f32(float* d_self, float* d_other, const int32_t* guided, float w, int32_t R, int64_t row_len, clipdlm_stream stream);
+/* a += b over n fp32 elements (sum of the input gradients of two encoder passes over the same input). */
+int clipdlm_add_f32(float* a, const float* b, int64_t n, clipdlm_stream stream);
 /* Gradient of nn.Embedding through q_sample: d_table[ids[j], c] += sum_s scale[s] * dx[s, j, c]; dx fp32 [S, tokens, ch], ids int32
  * [tokens], scale [S] (sqrt(alpha_bar[t_s]), CLIP-DDPM.py:360) or NULL (= 1). Replaces autograd through :459 and :347-362. */
 int clipdlm_embedding_bwd(const float* dx, const float* scale, const int32_t* ids, int32_t S, int64_t tokens, int32_t ch, float* d_table,

@@ -417,3 +417,50 @@ def test_train_embedding_speed_mode_and_state_dict(pkg):
     assert tuple(ids.shape) == (hp["BATCH_SIZE"], 16) and tuple(restored.shape) == (hp["BATCH_SIZE"], 18, 16)
     lg = model.lm_head(restored[:, :16])
     assert torch.equal(lg.argmax(-1), ids)
+
+
+@pytest.mark.parametrize("fusion", ["concat", "add"])
+def test_train_embedding_with_classifier_free_guidance_vs_oracle(pkg, fusion):
+    """TRAIN_EMBEDDING=True together with CLASSIFIER_FREE_WEIGHT > 0 (every flag of CLIP-DDPM.py:94-114 is orthogonal in the reference):
+    guided second encoder pass over the same projected input, fp32 mix before output_projection, gradient split between the passes.
+    Losses and every gradient (incl. embedding.weight / lm_head.weight / the projections / text_linear) against the oracle, 2 chunks."""
+    hp = golden_hp(TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD=fusion, CLASSIFIER_FREE_WEIGHT=0.3, CLASSIFIER_FREE_PROB=0.4,
+                   BATCH_SIZE=3, SAMPLE_SIZE=4, LOSS_FUNC="mse_series_mean")
+    P = O.init_params(hp, seed=21, closed_form=False)
+    S, B = hp["SAMPLE_SIZE"], hp["BATCH_SIZE"]
+    batch = O.synthetic_batch(hp, seed=22, ragged=True)
+    gen = torch.Generator().manual_seed(23)
+    acp = O.alpha_cumprod(hp)
+    t = torch.tensor([5, 300, 700, 990]).reshape(S, 1, 1)
+    n_t, n_1 = torch.randn(B, 16, 16, generator=gen), torch.randn(B, 16, 16, generator=gen)
+    cmask = (torch.rand((S * B, 1), generator=gen) > 0.4).float()
+    cmask[0] = 0; cmask[1] = 1
+    Po = {k: v.clone() for k, v in P.items()}
+    O.make_trainable(Po, hp)
+    x_0 = torch.nn.functional.embedding(batch["input_ids"], Po["embedding.weight"])
+    x_t, x_1 = O.diffuse_t(x_0, t, acp, n_t), O.diffuse_t(x_0, torch.ones(1, dtype=torch.int64), acp, n_1)
+    torch.set_num_threads(8)
+    ref = O.loss(Po, x_t, x_1, None, x_0, batch["image_clip"], batch["text_clip"], batch["attention_mask"], batch["input_ids"], hp,
+                 train=True, classifier_mask=cmask)
+    sum(ref).backward()
+    model = make_model(pkg, hp, P={k: v.clone() for k, v in P.items()}, chunk_rows=2 * B).train()
+    tr = pkg.AdamW(model.parameters(), lr=0.0, weight_decay=0.0)
+    snap = {}
+    orig_step = tr.step
+    def step_and_snapshot():
+        snap.update({k: v.clone() for k, v in model.named_grads().items()})
+        orig_step()
+    tr.step = step_and_snapshot
+    got = pkg.train_func(model, tr, to_dev(batch), t=t, noise_t=n_t, noise_1=n_1, classifier_mask=cmask)
+    for x, y in zip(got[1:], ref):
+        assert abs(x.item() - y.item()) < 1e-3 * abs(y.item()), (x.item(), y.item())
+    gscale = max(float(Po[n].grad.double().norm()) for n in O.trainable_names(hp) if Po[n].grad is not None)
+    checked = 0
+    for n in O.trainable_names(hp):
+        if Po[n].grad is None:
+            continue
+        r = Po[n].grad.double()
+        mine = snap[n].cpu().double()
+        assert float((mine - r).norm()) <= 2e-3 * max(float(r.norm()), 1e-3 * gscale), n
+        checked += 1
+    assert checked >= 40 and float(Po["text_linear.weight"].grad.abs().max()) > 0   # the guided pass sees the text CLIP feature
