@@ -152,3 +152,21 @@ def test_postprocess_and_bleu():
     # two references: clipping takes the max count over references, length = closest reference
     s = clipdlm.bleu_score(["a a b c d e"], [["a b c d e f", "a a b c d e"]])
     assert abs(s - 1.0) < 1e-12
+
+
+def _build_c_host(out):
+    from clipdlm import _lib as L
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    cuda = "/usr/local/cuda"
+    cmd = ["gcc", "-O2", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "examples", "c_host.c"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(cuda, "include"), "-L" + os.path.dirname(L.LIB_PATH), "-lclipdlm", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + os.path.dirname(L.LIB_PATH), "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", out]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+def test_c_host_example_compiles_against_the_header(tmp_path):
+    """include/clipdlm.h is plain C: a C99 host (examples/c_host.c, no Python / torch) compiles warning-free and links against the .so."""
+    r = _build_c_host(str(tmp_path / "c_host"))
+    assert r.returncode == 0, r.stderr
