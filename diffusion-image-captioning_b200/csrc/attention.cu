@@ -329,6 +329,9 @@ __device__ __forceinline__ void qk_product(uint32_t x, uint32_t y, const AttGeo&
 __device__ __forceinline__ void softmax_rows(float (&p)[2][4][4], uint32_t keybits, int L, float scale, int lane) {
   const int t = lane & 3;
   const float sl = scale * LOG2E;
+  // visible keys clipped to the length, shifted so that bit (nt * 8 + cc) is this lane's column nt * 8 + 2 t + cc: one constant-position
+  // bit test per score
+  const uint32_t kb = (keybits & (L >= 32 ? 0xffffffffu : ((1u << L) - 1u))) >> (2 * t);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -338,8 +341,7 @@ __device__ __forceinline__ void softmax_rows(float (&p)[2][4][4], uint32_t keybi
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          const int j = nt * 8 + 2 * t + cc;
-          const bool ok = j < L && ((keybits >> j) & 1u);
+          const bool ok = (kb & (1u << (nt * 8 + cc))) != 0u;
           const float v = ok ? p[mt][nt][hh * 2 + cc] * sl : -INFINITY;
           p[mt][nt][hh * 2 + cc] = v;
           mx = fmaxf(mx, v);
