@@ -241,11 +241,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(CBfPtr z, const floa
 // Plain-bf16, D = 768 specialisation of the forward: persistent warps, rows streamed through a per-warp bulk-copy ring, packed
 // fp32 math, w / b held in registers.  (The generic kernel: one row per warp, 319 instructions per row, latency-exposed loads.)
 constexpr int LNF_STAGES = 4;
-template <bool F32OUT>
+template <bool F32OUT, int NV = 3>
 __global__ void __launch_bounds__(256, 2) layernorm_fwd_fast_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w,
                                                                     const float* __restrict__ b, float eps, long long rows,
                                                                     __nv_bfloat16* __restrict__ y, float* __restrict__ y_f32) {
-  constexpr int D = 768, NV = 3, NW = 8;
+  constexpr int D = NV * 256, NW = 8;   // NV = 3: D = 768 (the reference model); NV = 4: D = 1024 (bert-large geometry)
   constexpr uint32_t row_bytes = D * 2;
   extern __shared__ __align__(16) uint8_t lnf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -468,8 +468,9 @@ __global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a
 // Plain-bf16 specialisation of the kernel above: same row ring, the per-element arithmetic in packed fp32 pairs (FFMA2 / FADD2 /
 // FMUL2), the optional features as template flags (no per-row branches), reciprocal-multiplies instead of divisions.  The generic
 // kernel spends 742 warp instructions per 768-wide row (357 of them scalar fp32 math) and is issue-bound at 12 warps per SM.
+// NV = 3 (D = 768): 168 registers, 3 CTAs per SM; NV = 4 (D = 1024, the bert-large geometry): 32 more packed accumulators, 2 CTAs per SM.
 template <int NV, bool DROP_OUT, bool DZ_DROP, bool GELU, bool DBIAS>
-__global__ void __launch_bounds__(128, 3) layernorm_bwd_fast_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(128, NV <= 3 ? 3 : 2) layernorm_bwd_fast_kernel(const LnBwdArgs a) {
   extern __shared__ __align__(16) uint8_t lnb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) pdl_launch_dependents();
@@ -1019,6 +1020,21 @@ int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b
                            float* y_f32, unsigned long long seed, uint32_t site, float p, cudaStream_t st) {
   CLIPDLM_CHECK(z && z->hi && w && b && rows > 0 && ((y && y->hi) || y_f32), "layernorm_fwd: bad arguments");
   const DropoutCfg d = make_drop(seed, site, p);
+  if (z->lo == nullptr && (!y || y->lo == nullptr) && D == 1024 && d.thresh16 == 0 && rows >= 64) {
+    const size_t smem = (size_t)8 * LNF_STAGES * 1024 * 2 + 8 * LNF_STAGES * sizeof(uint64_t);
+    static bool set4 = false;
+    if (!set4) {
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_fwd_fast_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_fwd_fast_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set4 = true;
+    }
+    const long long want = (rows + 7) / 8;
+    const int fgrid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
+    __nv_bfloat16* yh = y ? (__nv_bfloat16*)y->hi : nullptr;
+    if (y_f32 != nullptr) CLIPDLM_CUDA_OK(launch_pdl(layernorm_fwd_fast_kernel<true, 4>, dim3(fgrid), dim3(256), smem, st, (const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, y_f32));
+    else CLIPDLM_CUDA_OK(launch_pdl(layernorm_fwd_fast_kernel<false, 4>, dim3(fgrid), dim3(256), smem, st, (const __nv_bfloat16*)z->hi, w, b, eps, rows, yh, (float*)nullptr));
+    return 0;
+  }
   if (z->lo == nullptr && (!y || y->lo == nullptr) && D == 768 && d.thresh16 == 0 && rows >= 64) {
     const size_t smem = (size_t)8 * LNF_STAGES * 768 * 2 + 8 * LNF_STAGES * sizeof(uint64_t);
     static bool set = false;
@@ -1068,21 +1084,23 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
       smem_set = 120 * 1024;
     }
   }
-  // plain bf16, D = 768 (the reference model): packed-math specialisations for the four feature combinations the engine uses
-  if (a.z.lo == nullptr && a.dz.lo == nullptr && D == 768 && a.dw != nullptr && a.db != nullptr) {
+  // plain bf16, D = 768 (the reference model) or 1024 (bert-large geometry): packed-math specialisations for the feature combinations the engine uses
+  if (a.z.lo == nullptr && a.dz.lo == nullptr && (D == 768 || D == 1024) && a.dw != nullptr && a.db != nullptr) {
+    if (D == 1024) grid = (int)(want < 2LL * num_sms() ? want : 2LL * num_sms());
     const bool f_do = a.drop_out.thresh16 != 0, f_dd = a.dz_drop.hi != nullptr, f_g = a.gelu_u.hi != nullptr, f_b = a.dbias != nullptr;
     const int combo = (f_do ? 1 : 0) | (f_dd ? 2 : 0) | (f_g ? 4 : 0) | (f_b ? 8 : 0);
     const bool plain_aux = (!f_dd || a.dz_drop.lo == nullptr) && (!f_g || a.gelu_u.lo == nullptr);
-#define LNB_FAST(DO, DD, GE, DB)                                                                                              \
+#define LNB_FAST_NV(NVV, DO, DD, GE, DB)                                                                                      \
   {                                                                                                                           \
     static bool set = false;                                                                                                  \
     if (!set) {                                                                                                               \
-      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_fast_kernel<3, DO, DD, GE, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); \
+      CLIPDLM_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_fast_kernel<NVV, DO, DD, GE, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); \
       set = true;                                                                                                             \
     }                                                                                                                         \
-    CLIPDLM_CUDA_OK(launch_pdl(layernorm_bwd_fast_kernel<3, DO, DD, GE, DB>, dim3(grid), dim3(128), smem, st, a));            \
+    CLIPDLM_CUDA_OK(launch_pdl(layernorm_bwd_fast_kernel<NVV, DO, DD, GE, DB>, dim3(grid), dim3(128), smem, st, a));          \
     return 0;                                                                                                                 \
   }
+#define LNB_FAST(DO, DD, GE, DB) { if (D == 768) LNB_FAST_NV(3, DO, DD, GE, DB) else LNB_FAST_NV(4, DO, DD, GE, DB) }
     if (plain_aux) {
       switch (combo) {
         case 8: LNB_FAST(false, false, false, true)     // sa_layer_norm: + out_lin bias gradient
@@ -1094,6 +1112,7 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
       }
     }
 #undef LNB_FAST
+#undef LNB_FAST_NV
   }
   DISPATCH_NV(D, layernorm_bwd_kernel<NV><<<grid, 128, smem, st>>>(a));
   CLIPDLM_CUDA_OK(cudaGetLastError());

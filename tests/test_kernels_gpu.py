@@ -167,6 +167,39 @@ def test_layernorm_fwd_bwd(G, D, pair):
     assert rel(G.join(g2h, g2l), zr.grad * ur.grad) < (3e-5 if pair else 8e-3)
 
 
+@pytest.mark.parametrize("D", [768, 1024])
+@pytest.mark.parametrize("combo", ["dbias", "dz_drop+dbias", "gelu+dbias", "drop_out", "plain"])
+def test_layernorm_bwd_fast_matches_generic(G, D, combo):
+    """The packed-math specialisations (plain bf16, D = 768 / 1024, the five feature combinations the engine uses) against the generic
+    kernel fed the same values through pair storage (lo = 0): same dropout masks, same sums."""
+    rows, p = 777, 0.1
+    z = (torch.randn(rows, D, device=G.DEV) * 2 + 0.3).bfloat16(); dy = torch.randn(rows, D, device=G.DEV).bfloat16()
+    u = torch.randn(rows, D, device=G.DEV).bfloat16()
+    w = torch.randn(D, device=G.DEV) * 0.2 + 1
+    zero = torch.zeros(rows, D, device=G.DEV, dtype=torch.bfloat16)
+    lib, L = G.lib(), G.L
+    outs = []
+    for pair in (False, True):
+        lo = (lambda: zero.clone()) if pair else (lambda: None)
+        dz = (torch.zeros_like(z), lo()); dzd = (torch.zeros_like(z), lo())
+        dw = torch.zeros(D, device=G.DEV); db = torch.zeros(D, device=G.DEV); dbias = torch.zeros(D, device=G.DEV)
+        use_dd, use_g, use_do = combo == "dz_drop+dbias", combo == "gelu+dbias", combo == "drop_out"
+        use_b = combo in ("dbias", "dz_drop+dbias", "gelu+dbias")
+        L.check(lib.clipdlm_layernorm_bwd(C.byref(G.bfp(z, lo())), C.byref(G.bfp(dy, lo())), w.data_ptr(), 1e-12, rows, D, C.byref(G.bfp(*dz)),
+                                          dw.data_ptr(), db.data_ptr(), 4321, 6, p if use_do else 0.0,
+                                          C.byref(G.bfp(*dzd)) if use_dd else None, 9, p if use_dd else 0.0,
+                                          C.byref(G.bfp(u, lo())) if use_g else None, dbias.data_ptr() if use_b else None, G.st()))
+        torch.cuda.synchronize()
+        outs.append((G.join(*dz), G.join(*dzd), dw, db, dbias))
+    fast, gen = outs
+    assert rel(fast[0], gen[0]) < 4e-3 and rel(fast[2], gen[2]) < 1e-4 and rel(fast[3], gen[3]) < 1e-4
+    if combo == "dz_drop+dbias":
+        assert rel(fast[1], gen[1]) < 4e-3
+        assert torch.equal(fast[1] == 0, gen[1] == 0) or ((fast[1] == 0) != (gen[1] == 0)).float().mean() < 1e-4   # same mask
+    if combo != "drop_out" and combo != "plain":
+        assert rel(fast[4], gen[4]) < 1e-3
+
+
 def test_layernorm_dropout_masks_consistent(G):
     rows, D, p = 512, 768, 0.1
     z = torch.randn(rows, D, device=G.DEV)
