@@ -24,7 +24,7 @@ constexpr int ROWP = 65;  // smem row pitch in floats: conflict-free for both "l
 // The mma kernel therefore needs 4 Philox calls per thread for a 32 x 32 score tile; the SIMT kernel evaluates the same
 // function per element, so both produce identical masks (forward, backward, bf16 and split precision).
 __device__ __forceinline__ uint4 attn_rand_block(const DropoutCfg& d, unsigned long long rh, int lane_p, int q) {
-  return philox4x32_10(make_uint4((uint32_t)rh, (uint32_t)(rh >> 32), (uint32_t)lane_p | ((uint32_t)q << 8), d.site ^ 0xa77e0000u),
+  return philox4x32(make_uint4((uint32_t)rh, (uint32_t)(rh >> 32), (uint32_t)lane_p | ((uint32_t)q << 8), d.site ^ 0xa77e0000u),
                        make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
 }
 __device__ __forceinline__ uint32_t attn_field16(const uint4& rnd, int f) {

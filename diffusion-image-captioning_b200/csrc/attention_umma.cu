@@ -40,7 +40,7 @@ constexpr float AU_LOG2E = 1.4426950408889634f;
 // same counter layout as attention.cu (attn_rand_block / attn_keep_ij): element (i, j) of pair rh draws field ((j / 8) % 4) * 2 + j % 2
 // of the Philox block (rh, lane' = (i % 8) * 4 + (j % 8) / 2, q = (i / 8) * 4 + j / 32) - the SIMT and ring kernels see the same masks.
 __device__ __forceinline__ uint4 au_rand_block(const DropoutCfg& d, unsigned long long rh, int lane_p, int q) {
-  return philox4x32_10(make_uint4((uint32_t)rh, (uint32_t)(rh >> 32), (uint32_t)lane_p | ((uint32_t)q << 8), d.site ^ 0xa77e0000u),
+  return philox4x32(make_uint4((uint32_t)rh, (uint32_t)(rh >> 32), (uint32_t)lane_p | ((uint32_t)q << 8), d.site ^ 0xa77e0000u),
                        make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
 }
 // keep-scale (0 or 1 / (1 - p)) for the 32 keys of query row i
