@@ -346,14 +346,18 @@ def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dic
                 model.hp["ROUNDING_WEIGHT"] = float(((acc_x_t + acc_x_1) / acc_prob).item() * hp["DYNAMIC_ROUNDING_WEIGHT"])
             if hp["DEBUG"]:
                 break
-        n_batches = max(n_batches, 1)
+        # the reference divides by len(train_loader) (:547,554), also when DEBUG cut the epoch after one batch
+        n_batches = max(len(train_loader) if hasattr(train_loader, "__len__") else n_batches, 1)
         rec = dict(epoch=epoch, x_t_loss=acc_x_t / n_batches, x_1_loss=acc_x_1 / n_batches, prob_loss=acc_prob / n_batches, lr=trainer.param_groups[0]["lr"])
         if val_loader is not None:
             val_x_t, val_x_1, val_prob = validate(model, val_loader)
             rec.update(val_x_t=val_x_t, val_x_1=val_x_1, val_prob=val_prob)
             if val_x_t + val_x_1 + val_prob > hp["EARLY_STOP_RATIO"] * acc_l / n_batches:
-                if not early_stopped and on_early_stop is not None:
-                    on_early_stop(model, epoch)
+                if not early_stopped:
+                    if summary is not None:
+                        summary.write("early stop! \n")  # :549
+                    if on_early_stop is not None:
+                        on_early_stop(model, epoch)  # the reference saves the whole-module pickle here (:550-551)
                 early_stopped = True
         rec["early_stopped"] = early_stopped
         if summary is not None:

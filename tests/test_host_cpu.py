@@ -170,3 +170,91 @@ def test_c_host_example_compiles_against_the_header(tmp_path):
     """include/clipdlm.h is plain C: a C99 host (examples/c_host.c, no Python / torch) compiles warning-free and links against the .so."""
     r = _build_c_host(str(tmp_path / "c_host"))
     assert r.returncode == 0, r.stderr
+
+
+class _StubModel:
+    """Just enough of DistilBertModel for the epoch loop: hp, training flag, train()/eval()."""
+
+    def __init__(self, hp):
+        self.hp, self.training = hp, False
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+
+class _StubTrainer:
+    def __init__(self, lr):
+        self.param_groups = [{"lr": lr}]
+
+
+def _run_epoch_loop(monkeypatch, hp, train_losses, val_losses, n_batches=3, with_val=True):
+    """Drive clipdlm.train() (CLIP-DDPM.py:515-557) with a scripted train_func: (x_t, x_1, prob) per call."""
+    import io
+    import clipdlm
+    from clipdlm import diffusion
+    calls = {"train": [], "val": [], "weights": [], "early": []}
+    it_train, it_val = iter(train_losses), iter(val_losses)
+
+    def fake_train_func(model, trainer, x, train=True, **kw):
+        a, b, c = (torch.tensor(float(v)) for v in (next(it_train) if train else next(it_val)))
+        calls["train" if train else "val"].append((trainer.param_groups[0]["lr"] if train else None, model.training, torch.is_grad_enabled()))
+        calls["weights"].append(model.hp["ROUNDING_WEIGHT"])
+        return a + b + c, a, b, c
+
+    monkeypatch.setattr(diffusion, "train_func", fake_train_func)
+    model, trainer = _StubModel(hp), _StubTrainer(hp["LEARNING_RATE"])
+    summary = io.StringIO()
+    hist = clipdlm.train(model, trainer, [{}] * n_batches, hp, val_loader=[{}] * 2 if with_val else None, summary=summary,
+                         on_early_stop=lambda m, e: calls["early"].append(e))
+    return hist, calls, summary.getvalue(), model, trainer
+
+
+def test_epoch_loop_learning_rates_and_summary(monkeypatch):
+    import clipdlm
+    hp = clipdlm.default_hparams(EPOCH_NUM=3)
+    hist, calls, text, model, trainer = _run_epoch_loop(monkeypatch, hp, [(1, 2, 3)] * 9, [(1, 2, 3)] * 6)
+    lrs = clipdlm.learning_rates(hp)
+    assert [c[0] for c in calls["train"]] == [lr for lr in lrs for _ in range(3)]  # :520-522: lr set once per epoch
+    assert all(c[1] and c[2] for c in calls["train"])           # train mode, grad enabled
+    assert all(not c[1] and not c[2] for c in calls["val"])     # validate: eval mode under no_grad (:489-490)
+    assert model.training                                        # ... and back to train mode (:500)
+    assert [float(h["x_t_loss"]) for h in hist] == [1.0] * 3 and [float(h["prob_loss"]) for h in hist] == [3.0] * 3
+    assert [float(h["val_x_1"]) for h in hist] == [2.0] * 3
+    assert not any(h["early_stopped"] for h in hist) and calls["early"] == []
+    lines = text.strip().split("\n")
+    assert len(lines) == 3 and lines[1].startswith("epoch 1 average x_t_loss, x_1_loss, prob_loss, val losses: 1.0, 2.0, 3.0, 1.0, 2.0, 3.0")
+    # equal endpoints: the reference leaves the optimizer's lr alone (:519)
+    hp2 = clipdlm.default_hparams(EPOCH_NUM=2, LEARNING_RATE=5e-5, END_LEARNING_RATE=5e-5)
+    _, calls2, _, _, tr2 = _run_epoch_loop(monkeypatch, hp2, [(1, 1, 1)] * 6, [(1, 1, 1)] * 4)
+    assert {c[0] for c in calls2["train"]} == {5e-5}
+
+
+def test_epoch_loop_early_stop_fires_once(monkeypatch):
+    import clipdlm
+    hp = clipdlm.default_hparams(EPOCH_NUM=3, EARLY_STOP_RATIO=1.05)
+    # epoch 0: val 6.0 <= 1.05 * 6.0; epoch 1: val 6.6 > 6.3 -> early stop; epoch 2: still above, hook must NOT fire again (:548-553)
+    hist, calls, text, _, _ = _run_epoch_loop(monkeypatch, hp, [(1, 2, 3)] * 9, [(1, 2, 3)] * 2 + [(1.2, 2.2, 3.2)] * 4)
+    assert [h["early_stopped"] for h in hist] == [False, True, True]
+    assert calls["early"] == [1]
+    assert text.count("early stop! \n") == 1 and text.index("early stop!") < text.index("epoch 1 average")
+
+
+def test_epoch_loop_dynamic_rounding_weight_and_debug(monkeypatch):
+    import clipdlm
+    hp = clipdlm.default_hparams(EPOCH_NUM=1, DYNAMIC_ROUNDING_WEIGHT=2.0, ROUNDING_WEIGHT=0.5)
+    # :535-536: after each batch ROUNDING_WEIGHT <- (acc_x_t + acc_x_1) / acc_prob * DYNAMIC_ROUNDING_WEIGHT (running sums of the epoch)
+    hist, calls, _, model, _ = _run_epoch_loop(monkeypatch, hp, [(1, 1, 4), (3, 1, 2), (1, 1, 1)], [], with_val=False)
+    assert calls["weights"][0] == 0.5
+    assert calls["weights"][1] == pytest.approx(2.0 * 2 / 4)
+    assert calls["weights"][2] == pytest.approx(2.0 * 6 / 6)
+    assert model.hp["ROUNDING_WEIGHT"] == pytest.approx(2.0 * 8 / 7)
+    assert "val_x_t" not in hist[0]
+    # DEBUG: one batch, one epoch (:543-544,556-557); the averages still divide by len(train_loader) like the reference (:554)
+    hp = clipdlm.default_hparams(EPOCH_NUM=4, DEBUG=True)
+    hist, calls, _, _, _ = _run_epoch_loop(monkeypatch, hp, [(3, 6, 9)], [(1, 1, 1)] * 2)
+    assert len(hist) == 1 and len(calls["train"]) == 1
+    assert float(hist[0]["x_t_loss"]) == pytest.approx(1.0) and float(hist[0]["prob_loss"]) == pytest.approx(3.0)
