@@ -30,7 +30,11 @@ static float* dev_f32(const float* host, size_t n) {
 int main(void) {
   if (clipdlm_device_ok() != 1) { fprintf(stderr, "needs a compute-capability 10.x GPU (B200)\n"); return 2; }
   enum { LAYERS = 2, D = 768, HEADS = 12, FFN = 3072, VOCAB = 1000, ML = 16, CLIP = 512, MAXPOS = 64, B = 4, S = 3, L = ML + 2 };
-  clipdlm_config_t cfg = {LAYERS, D, HEADS, FFN, VOCAB, ML, CLIP, MAXPOS, /*fusion concat*/ 0, /*precision bf16*/ 0, 1e-12f, 0.0f, 0.0f};
+  const char* env_dbg = getenv("C_HOST_GEMM_DEBUG_FLAGS"); /* e.g. 1024: row-wise global stores instead of TMA stores (see clipdlm_gemm_debug_flags) */
+  if (env_dbg) clipdlm_gemm_debug_flags((uint32_t)strtoul(env_dbg, NULL, 0));
+  const char* env_drop = getenv("C_HOST_DROPOUT"); /* e.g. 0.1: train with dropout (tools/sanitize_c_host.sh runs both settings under compute-sanitizer) */
+  const float pdrop = env_drop ? (float)atof(env_drop) : 0.0f;
+  clipdlm_config_t cfg = {LAYERS, D, HEADS, FFN, VOCAB, ML, CLIP, MAXPOS, /*fusion concat*/ 0, /*precision bf16*/ 0, 1e-12f, pdrop, pdrop};
   const int64_t n = clipdlm_param_count(&cfg);
   if (n <= 0) { fprintf(stderr, "bad config: %s\n", clipdlm_last_error()); return 1; }
 
