@@ -39,6 +39,7 @@ class Gemm(C.Structure):
         ("targets", c_p), ("tgt_period", i32),
         ("lse", c_p),
         ("grad_scale", f32),
+        ("exp_shift", c_p), ("row_scale", c_p),
     ]
 
 
@@ -101,7 +102,8 @@ class DpBuffers(C.Structure):
                 ("shadow_lo", c_p * MAX_PEERS), ("p_mc", c_p), ("g_mc", c_p), ("shadow_hi_mc", c_p), ("shadow_lo_mc", c_p)]
 
 
-EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD = 0, 1, 2, 3
+EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD, EPI_LSE_EXP, EPI_STORE_ROWSCALE = 0, 1, 2, 3, 4, 5
+OPT_FUSED_SOFTMAX_GRAD, OPT_EXP_SHIFT_PTR = 1, 2
 
 PROF_CATEGORIES = ("gemm_fwd", "gemm_dgrad", "gemm_wgrad", "gemm_lse", "gemm_smgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "embed",
                    "loss", "colsum", "other")
@@ -124,6 +126,7 @@ _SIGS = {
     "clipdlm_gemm_debug_mn_desc": (None, [u32, u32]),
     "clipdlm_gemm_debug_flags": (None, [u32]),
     "clipdlm_lse_combine": (C.c_int, [c_p, c_p, c_p, i32, i32, c_p, c_p, c_p, c_p, f64, c_p]),
+    "clipdlm_ce_row_terms": (C.c_int, [c_p, c_p, c_p, i32, f32, i32, c_p, i64, c_p, i64, i32, i32, i32, c_p, c_p]),
     "clipdlm_embed_fwd": (C.c_int, [C.POINTER(Embed), c_p]),
     "clipdlm_embed_bwd": (C.c_int, [C.POINTER(Bf), i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p, c_p, c_p]),
     "clipdlm_layernorm_fwd": (C.c_int, [C.POINTER(Bf), c_p, c_p, f32, i64, i32, C.POINTER(Bf), c_p, u64, u32, f32, c_p]),
@@ -163,6 +166,7 @@ _SIGS = {
     "clipdlm_row_mix_f32": (C.c_int, [c_p, c_p, c_p, f32, i32, i64, c_p]),
     "clipdlm_row_split_f32": (C.c_int, [c_p, c_p, c_p, f32, i32, i64, c_p]),
     "clipdlm_add_f32": (C.c_int, [c_p, c_p, i64, c_p]),
+    "clipdlm_engine_set_option": (C.c_int, [c_p, i32, i64]),
     "clipdlm_engine_launch_count": (i64, [c_p]),
     "clipdlm_engine_profile": (C.c_int, [c_p, i32]),
     "clipdlm_engine_profile_read": (C.c_int, [c_p, c_p, i32]),

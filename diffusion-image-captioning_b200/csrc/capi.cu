@@ -19,6 +19,8 @@ void set_last_error(const char* fmt, ...) {
 int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st);
 int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
                          int* argmax, double* loss_acc, double scale, cudaStream_t st);
+int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st);
 void gemm_debug_mn_desc(uint32_t lbo, uint32_t sbo);
 void gemm_debug_flags(uint32_t flags);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
@@ -75,6 +77,12 @@ int clipdlm_lse_combine(const float* part_max, const float* part_sum, const int3
   return lse_combine_dispatch(part_max, part_sum, part_arg, n_tiles, M, tgt_logit, lse, argmax, loss_acc, scale, (cudaStream_t)stream);
 }
 
+int clipdlm_ce_row_terms(const float* lse, const float* exp_shift, const int32_t* targets, int32_t tgt_period, float scale, int32_t M,
+                         const void* w_bf16, int64_t ldw, void* dx_bf16, int64_t ldx, int32_t scatter_len, int32_t scatter_stride, int32_t D,
+                         float* row_scale, clipdlm_stream stream) {
+  return ce_row_terms_dispatch(lse, exp_shift, targets, tgt_period, scale, M, w_bf16, ldw, dx_bf16, ldx, scatter_len, scatter_stride, D, row_scale,
+                               (cudaStream_t)stream);
+}
 
 #define ST ((cudaStream_t)stream)
 int clipdlm_embed_fwd(const clipdlm_embed_t* e, clipdlm_stream stream) { return embed_fwd_dispatch(e, ST); }

@@ -29,6 +29,8 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
                            const clipdlm_bf_t* dz_drop, uint32_t site_in, float p_in, const clipdlm_bf_t* gelu_u, float* dbias,
                            cudaStream_t st);
 int colsum_dispatch(const clipdlm_bf_t* x, long long rows, int N, float* out, cudaStream_t st);
+int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st);
 int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* ids, const float* tgt, int tgt_rows, int R, int B, int Ltxt,
                         int L, int D, int kind, long long R_total, int batch_size, float weight, double* loss_acc, const clipdlm_bf_t* dx,
                         cudaStream_t st);
@@ -134,6 +136,9 @@ struct clipdlm_engine {
   // last forward
   clipdlm_pass_t last;
   int have_fwd;
+  // options (clipdlm_engine_set_option)
+  int fused_smgrad;          // CLIPDLM_OPT_FUSED_SOFTMAX_GRAD
+  const float* exp_shift;    // CLIPDLM_OPT_EXP_SHIFT_PTR (device scalar) or NULL
 };
 
 namespace clipdlm {
@@ -261,7 +266,7 @@ struct ProfScope {
 static int gemm_cat(const clipdlm_gemm_t& g) {
   switch (g.epilogue) {
     case CLIPDLM_EPI_WGRAD: return CLIPDLM_PROF_GEMM_WGRAD;
-    case CLIPDLM_EPI_LSE: return CLIPDLM_PROF_GEMM_LSE;
+    case CLIPDLM_EPI_LSE: case CLIPDLM_EPI_LSE_EXP: return CLIPDLM_PROF_GEMM_LSE;
     case CLIPDLM_EPI_SMGRAD: return CLIPDLM_PROF_GEMM_SMGRAD;
     default: return g.b_major ? CLIPDLM_PROF_GEMM_DGRAD : CLIPDLM_PROF_GEMM_FWD;
   }
@@ -270,7 +275,7 @@ static double gemm_bytes(const clipdlm_gemm_t& g, int es) {
   double b = ((double)g.M * g.K + (double)g.N * g.K) * es;
   if (g.epilogue == CLIPDLM_EPI_WGRAD) b += (double)g.M * g.N * 8;  // fp32 accumulate: read + write
   else if (g.epilogue == CLIPDLM_EPI_SMGRAD) b += (double)g.M * g.N * es;
-  else if (g.epilogue == CLIPDLM_EPI_STORE) {
+  else if (g.epilogue == CLIPDLM_EPI_STORE || g.epilogue == CLIPDLM_EPI_STORE_ROWSCALE) {
     if (g.out_hi) b += (double)g.M * g.N * es;
     if (g.out2_hi) b += (double)g.M * g.N * es;
     if (g.out_f32) b += (double)g.M * g.N * 4;
@@ -363,8 +368,9 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
 }
 
 // LSE-fused lm_head over x_out[:, :Ltxt]: partials -> combine.  targets may be NULL (argmax only).
+// exp_mode (factored softmax gradient): keep_logits receives bf16(exp(logit - *exp_shift)) instead of the logits, see CLIPDLM_EPI_LSE_EXP.
 static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period, int32_t* argmax, double* loss_acc, double scale,
-                       cudaStream_t st, void* keep_logits = nullptr) {
+                       cudaStream_t st, void* keep_logits = nullptr, bool exp_mode = false) {
   const clipdlm_config_t& c = e->cfg;
   const int M = e->last.R * e->Ltxt;
   Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
@@ -374,6 +380,7 @@ static int lm_head_lse(clipdlm_engine* e, const int32_t* targets, int tgt_period
   g.part_max = e->part_max; g.part_sum = e->part_sum; g.part_arg = argmax ? e->part_arg : nullptr; g.tgt_logit = e->tgt_logit;
   g.targets = targets; g.tgt_period = tgt_period;
   if (keep_logits != nullptr) { g.out_hi = keep_logits; g.ldo = e->ldl; }   // bf16 logits for the in-place softmax gradient
+  if (exp_mode) { g.epilogue = CLIPDLM_EPI_LSE_EXP; g.exp_shift = e->exp_shift; }
   RUNG(g);
   RUNP(CLIPDLM_PROF_LOSS, 0, 6.0 * e->n_vtiles * M * 4, lse_combine_dispatch(e->part_max, e->part_sum, argmax ? e->part_arg : nullptr, 2 * e->n_vtiles, M, targets ? e->tgt_logit : nullptr, e->lse, argmax, loss_acc,
                            scale, st));
@@ -474,9 +481,26 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
     // softmax-CE gradient in place - 8 GB of traffic instead of recomputing the 3 TFLOP lm_head GEMM.  Split precision (parity
     // mode) recomputes the vocabulary tiles with fp32 accumulators instead (SMGRAD epilogue).
     const bool store_logits = bwd && !e->pair;
-    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st, store_logits ? e->dlog.hi : nullptr);
+    // Option FUSED_SOFTMAX_GRAD: d x = sum_v softmax_v W_v - W_tgt with softmax_v = exp(s_v - c) / sum_u exp(s_u - c): the lm_head pass stores
+    // exp(s - c), the 1 / sum factor scales the ROWS of the gradient GEMM's accumulator and the one-hot term is a gather of W rows - the
+    // in-place pass over the 8 GB of stored logits (read + write) drops out of the step.
+    const bool factored = store_logits && e->fused_smgrad != 0;
+    int rc = lm_head_lse(e, p.ids, B * Ltxt, nullptr, &losses[1], ce_scale, st, store_logits ? e->dlog.hi : nullptr, factored);
     if (rc) return rc;
-    if (bwd) {
+    if (bwd && factored) {
+      const float gs = (float)(lc->rounding_weight * ce_scale);
+      // row factors into the (now free) target-logit buffer; one-hot term folded into d(x_out) rows, which already hold the embedding-loss gradient
+      RUNP(CLIPDLM_PROF_LOSS, 0, (double)M16 * D * 6.0,
+           ce_row_terms_dispatch(e->lse, e->exp_shift, p.ids, B * Ltxt, gs, M16, e->bufs.emb_hi, D, e->g0.hi, D, Ltxt, L, D, e->tgt_logit, st));
+      Act emb{e->bufs.emb_hi, nullptr};
+      clipdlm_gemm_t g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
+      g.epilogue = CLIPDLM_EPI_STORE_ROWSCALE;
+      g.row_scale = e->tgt_logit;
+      g.out_hi = e->g0.hi; g.ldo = D;
+      g.res_hi = e->g0.hi; g.ldr = D;
+      g.scatter_len = Ltxt; g.scatter_stride = L;
+      RUNG(g);
+    } else if (bwd) {
       Act emb{e->bufs.emb_hi, e->pair ? e->bufs.emb_lo : nullptr};
       clipdlm_gemm_t g;
       if (store_logits) {
@@ -626,6 +650,22 @@ int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float
   if (dx_in != nullptr) RUN(gather_rows_f32_dispatch(&e->g1, (long long)e->last.R * e->Ltxt, e->Ltxt, e->L, e->cfg.dim, dx_in, st));
   return 0;
 }
+int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value) {
+  CLIPDLM_CHECK(e != nullptr, "set_option: null engine");
+  switch (option) {
+    case CLIPDLM_OPT_FUSED_SOFTMAX_GRAD:
+      CLIPDLM_CHECK(value == 0 || !e->pair, "FUSED_SOFTMAX_GRAD needs plain-bf16 precision (split precision recomputes the vocabulary tiles in fp32)");
+      e->fused_smgrad = value != 0;
+      return 0;
+    case CLIPDLM_OPT_EXP_SHIFT_PTR:
+      e->exp_shift = reinterpret_cast<const float*>(static_cast<uintptr_t>(value));
+      return 0;
+    default:
+      CLIPDLM_CHECK(false, "set_option: unknown option %d", (int)option);
+  }
+  return 0;
+}
+
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e) { return e ? e->launches : -1; }
 
 int clipdlm_engine_profile(clipdlm_engine_t* e, int32_t enable) {

@@ -69,8 +69,8 @@ struct GemmArgs {
   float* tgt_logit;
   const int* targets;
   int tgt_period;
-  const float* lse;
-  float grad_scale;
+  const float* lse;          // SMGRAD: lse[M];  LSE_EXP: the exponent shift (device scalar, may be NULL);  STORE_ROWSCALE: row_scale[M]
+  float grad_scale;          // (one slot for the three: GemmArgs keeps its layout, so the other instantiations compile to the same SASS)
 };
 
 __device__ __forceinline__ long long map_row(const GemmArgs& g, int m) {
@@ -188,7 +188,7 @@ __device__ __forceinline__ void stage_row32(uint32_t buf, int row, int half, con
   }
 }
 
-template <bool BIAS, int AUX, bool DUAL, bool DROP>
+template <bool BIAS, int AUX, bool DUAL, bool DROP, bool RSCALE = false>
 __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr, int col0, int m, bool valid, long long mr, uint32_t sbias_u32,
                                                uint64_t* tfull, uint32_t tphase, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint32_t stg,
                                                int row_base) {
@@ -203,6 +203,8 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
     for (int i = 0; i < 16; ++i) { aux0[i] = 0u; aux1[i] = 0u; }
     if (valid) ld_row64(aux_row, true, aux0);      // first chunk: in flight while the MMAs of this tile still run
   }
+  float rs = 1.f;
+  if (RSCALE) rs = valid ? g.lse[m] : 0.f;   // STORE_ROWSCALE: this thread's accumulator row is scaled before the residual is added
   mbar_wait(tfull, tphase);
   tc_fence_after();
   // one 32-column chunk; cur holds its auxiliary operand, nxt receives the next chunk's
@@ -210,6 +212,11 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
     float v[32];
     tmem_ld32(taddr + cc * 32, v);
     if (AUX != 0 && cc + 1 < 4 && valid) ld_row64(aux_row + (cc + 1) * 32, true, nxt);
+    if (RSCALE) {
+      const f32x2 rs2 = pk2(rs, rs);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) upk2(mul2(pk2(v[2 * j], v[2 * j + 1]), rs2), v[2 * j], v[2 * j + 1]);
+    }
     if (BIAS) {
       const uint32_t sb = sbias_u32 + cc * 128;
 #pragma unroll
@@ -464,6 +471,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
       const bool valid = m < g.M;
       const long long mr = valid ? map_row(g, m) : 0;
+      if (EPI == CLIPDLM_EPI_STORE_ROWSCALE) {   // out = acc * row_scale[m] + residual (the host checked the specialised-epilogue preconditions)
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_lo * 32;
+        epi_store_fast<false, 1, false, false, true>(g, ta, n_blk * BN + c_lo * 32, m, valid, mr, 0u, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg),
+                                                     row_base);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty0_leader + as * 8);
+          else mbar_arrive(&tempty_bar[as]);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
       if (EPI == CLIPDLM_EPI_STORE && g.fast_mode >= 0) {
         const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_lo * 32;
         const int col0 = n_blk * BN + c_lo * 32;
@@ -558,6 +578,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           g.part_max[slot] = mx;
           g.part_sum[slot] = sum;
           if (want_arg) g.part_arg[slot] = arg;
+          if (has_t && g.tgt_logit != nullptr) g.tgt_logit[m] = tl;
+        }
+      } else if (EPI == CLIPDLM_EPI_LSE_EXP) {
+        // Factored softmax gradient, pass 1: e = exp(logit - shift) with a per-launch constant shift - no running maximum, one FFMA +
+        // FMNMX + MUFU.EX2 + FADD per logit. bf16(e) is what the gradient GEMM reads; the fp32 sum over this warp's 128 columns is the
+        // partial of log-sum-exp = shift + log(sum e), reported with part_max = shift so that lse_combine_kernel serves both variants.
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float shift = g.lse != nullptr ? *g.lse : 0.f;
+        const float nb = -shift * LOG2E;
+        const int tgt = (m < g.M && g.targets != nullptr) ? g.targets[m % g.tgt_period] : -1;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, tl = 0.f; bool has_t = false;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= g.N) break;
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if ((unsigned)(tgt - n0) < 32u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + j == tgt) tl = v[j];
+            has_t = true;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ex2_ftz(fminf(fmaf(v[j], LOG2E, nb), 100.f));
+          if (n0 + 32 > g.N) {   // vocabulary tail: the padding columns add nothing (the gradient GEMM never reads them: TMA clips at K = N)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (n0 + j) < g.N ? v[j] : 0.f;
+          }
+          if (m < g.M) row_store_pair(g.out_hi + (long long)m * g.ldo + n0, nullptr, g.al32 != 0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+        }
+        if (m < g.M) {
+          const size_t slot = (size_t)(n_blk * 2 + hsel) * g.M + m;
+          g.part_max[slot] = shift;
+          g.part_sum[slot] = (s0 + s1) + (s2 + s3);
           if (has_t && g.tgt_logit != nullptr) g.tgt_logit[m] = tl;
         }
       } else {
@@ -775,6 +831,51 @@ int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row terms of the factored softmax gradient (CLIPDLM_EPI_LSE_EXP / _STORE_ROWSCALE): one warp per lm_head row.
+//   row_scale[m] = scale * exp(shift - lse[m]);   dx[row(m), :] -= scale * W[tgt(m), :]   (bf16 read-modify-write, fp32 math)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ce_row_terms_kernel(const float* __restrict__ lse, const float* __restrict__ exp_shift,
+                                                           const int* __restrict__ targets, int tgt_period, float scale, int M,
+                                                           const __nv_bfloat16* __restrict__ W, long long ldw, __nv_bfloat16* __restrict__ dx,
+                                                           long long ldx, int scatter_len, int scatter_stride, int D, float* __restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  if (lane == 0) {
+    const float shift = exp_shift != nullptr ? *exp_shift : 0.f;
+    const float r = scale * __expf(shift - lse[m]);
+    row_scale[m] = (r == r && fabsf(r) <= 3.0e38f) ? r : 0.f;   // sum exp(s - shift) flushed to zero or overflowed: no softmax term rather than NaN
+  }
+  const int tgt = targets[m % tgt_period];
+  const long long row = scatter_len > 0 ? (long long)(m / scatter_len) * scatter_stride + (m % scatter_len) : (long long)m;
+  const uint4* w = reinterpret_cast<const uint4*>(W + (long long)tgt * ldw);
+  uint4* d = reinterpret_cast<uint4*>(dx + row * ldx);
+  for (int v = lane; v < D / 8; v += 32) {
+    const uint4 a = d[v], b = w[v];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(bw[i]);
+      o[i] = pack_bf16x2(fmaf(-scale, y.x, x.x), fmaf(-scale, y.y, x.y));
+    }
+    d[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st) {
+  CLIPDLM_CHECK(lse && targets && w && dx && row_scale && M > 0 && tgt_period > 0 && D > 0, "ce_row_terms: bad arguments");
+  CLIPDLM_CHECK(D % 8 == 0 && ldw % 8 == 0 && ldx % 8 == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+                "ce_row_terms: rows must be 16-byte aligned (D, pitches multiples of 8 elements)");
+  CLIPDLM_CHECK(scatter_len >= 0 && (scatter_len == 0 || scatter_stride >= scatter_len), "ce_row_terms: bad scatter %d / %d", scatter_len, scatter_stride);
+  ce_row_terms_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(lse, exp_shift, targets, tgt_period, scale, M, (const __nv_bfloat16*)w, ldw,
+                                                              (__nv_bfloat16*)dx, ldx, scatter_len, scatter_stride, D, row_scale);
+  CLIPDLM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -987,8 +1088,17 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   ga.part_max = g->part_max; ga.part_sum = g->part_sum; ga.part_arg = g->part_arg; ga.tgt_logit = g->tgt_logit;
   ga.targets = g->targets; ga.tgt_period = g->tgt_period > 0 ? g->tgt_period : 1;
   ga.lse = g->lse; ga.grad_scale = g->grad_scale;
+  if (g->epilogue == CLIPDLM_EPI_LSE_EXP) ga.lse = g->exp_shift;
+  if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) ga.lse = g->row_scale;
   ga.dbg = g_dbg_flags;
   ga.fast_mode = -1;
+  if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) {
+    CLIPDLM_CHECK(g->row_scale && g->out_hi && g->res_hi && !g->bias && !g->u_hi && !g->out2_hi && !g->out_f32 && !g->out_lo && !g->res_lo &&
+                      !g->a_lo && !g->b_lo && g->drop_p == 0.f,
+                  "STORE_ROWSCALE: plain-bf16 out = acc * row_scale + residual only");
+    CLIPDLM_CHECK(ga.al32 && g->N % BN == 0, "STORE_ROWSCALE needs 32-byte aligned rows (pitches %% 16 == 0) and N %% 256 == 0 (N = %d)", g->N);
+    ga.fast_mode = 2;   // epi_store_fast<no bias, residual> + row scale; also switches the TMA-store output maps on below
+  }
   if (g->epilogue == CLIPDLM_EPI_STORE && ga.al32 && g->N % BN == 0 && !g->out_lo && !g->out2_lo && !g->res_lo && !g->u_lo && !g->out_f32 &&
       !(g->res_hi && g->u_hi) && (g->out_hi || g->out2_hi) && !(g_dbg_flags & 7u)) {  // (bits 7, 8: triage of the dual-store mode)
     const int aux = g->u_hi ? 2 : (g->res_hi ? 1 : 0);
@@ -1033,6 +1143,17 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
                                    (reinterpret_cast<uintptr_t>(g->out_hi) & 15) == 0),
                     "LSE epilogue: the optional bf16 logits output needs a 16-byte aligned plain-bf16 buffer with pitch >= %d", ga.num_n_tiles * BN);
       return launch_gemm<0, 0, CLIPDLM_EPI_LSE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+    case CLIPDLM_EPI_LSE_EXP:
+      CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "LSE_EXP epilogue expects K-major operands");
+      CLIPDLM_CHECK(g->part_max && g->part_sum && (!g->targets || g->tgt_logit) && !g->part_arg, "LSE_EXP epilogue buffers missing (no arg-max tracking in this mode)");
+      CLIPDLM_CHECK(g->out_hi && !g->out_lo && !g->a_lo && !g->b_lo && g->ldo >= (long long)ga.num_n_tiles * BN && g->ldo % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(g->out_hi) & 15) == 0,
+                    "LSE_EXP epilogue: needs a 16-byte aligned plain-bf16 output with pitch >= %d", ga.num_n_tiles * BN);
+      return launch_gemm<0, 0, CLIPDLM_EPI_LSE_EXP>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+    case CLIPDLM_EPI_STORE_ROWSCALE:
+      CLIPDLM_CHECK(g->a_major == 0, "STORE_ROWSCALE epilogue expects K-major A");
+      if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE_ROWSCALE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+      return launch_gemm<0, 1, CLIPDLM_EPI_STORE_ROWSCALE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
       CLIPDLM_CHECK(g->out_hi && g->lse && g->targets, "SMGRAD epilogue buffers missing");

@@ -77,6 +77,8 @@ def _loss_pass(model: DistilBertModel, eng, losses: torch.Tensor, slot: int, *, 
     gradient of the mixed output split between the two passes ((1 + w) to the guided one, -w / 1 to the unguided one)."""
     hp = model.hp
     lib = L.load()
+    if model.fused_softmax_grad and backward and slot == 0 and hp["USE_PROB_LOSS"]:
+        model.refresh_exp_shift()   # the weights moved since the last step; every x_t chunk of this call reads the same device scalar
     fw = dict(R=R, B=B, mode=mode, train=model.training, image_clip=image_clip, text_clip=text_clip, attn_mask=mask32, x_in=x_in,
               ids=ids32, noise=noise, coef_a=coef_a, coef_b=coef_b)
     model._run_forward(eng, guided=guided, drop_seed=seed, **fw)

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -107,7 +108,7 @@ class DistilBertModel:
     """
 
     def __init__(self, embedding=None, projection=None, config=None, hp: Optional[dict] = None, precision: str = "bf16",
-                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192):
+                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192, fused_softmax_grad: Optional[bool] = None):
         lib = L.load()
         if not torch.cuda.is_available():
             raise L.ClipdlmError("clipdlm needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -132,6 +133,12 @@ class DistilBertModel:
         self.precision = precision
         self.training = True
         self.chunk_rows = int(chunk_rows)
+        # Experimental (round 1: built, default off, to be validated on the GPU): factored softmax-CE gradient of the lm_head in
+        # precision="bf16" (clipdlm.h CLIPDLM_OPT_FUSED_SOFTMAX_GRAD). None = the CLIPDLM_FUSED_SOFTMAX_GRAD=1 environment switch.
+        if fused_softmax_grad is None:
+            fused_softmax_grad = os.environ.get("CLIPDLM_FUSED_SOFTMAX_GRAD", "0") == "1"
+        self.fused_softmax_grad = bool(fused_softmax_grad) and precision == "bf16" and not hp["TRAIN_EMBEDDING"]
+        self._exp_shift = None
         self.dp_group = None  # set by parallel.enable_data_parallel
         self.dp_world = 1
         self._cfg = L.Config(hp["N_LAYERS"], hp["DIM"], hp["N_HEADS"], hp["HIDDEN_DIM"], hp["VOCAB_SIZE"], hp["MAX_LENGTH"], hp["CLIP_DIM"],
@@ -305,12 +312,27 @@ class DistilBertModel:
     def sync_shadow(self):
         """Refresh the bf16 (pair) copies the GEMMs read, after any out-of-band change of the fp32 master weights."""
         lib, st = L.load(), self._stream()
+        self._lm_head_max_norm = None   # the lm_head weight may have been replaced (load_state_dict)
         with torch.cuda.device(self.device):
             L.check(lib.clipdlm_to_bf16(L.ptr(self.flat), L.ptr(self.shadow_hi), L.ptr(self.shadow_lo), self.n_params, st))
             if self.hp["TRAIN_EMBEDDING"]:
                 return  # the lm_head operand is part of the flat shadow
             n = self.hp["VOCAB_SIZE"] * self.hp["DIM"]
             L.check(lib.clipdlm_to_bf16(L.ptr(self.lm_head_weight), L.ptr(self.emb_hi), L.ptr(self.emb_lo), n, st))
+
+    def refresh_exp_shift(self):
+        """Exponent shift c of the factored softmax gradient (clipdlm.h CLIPDLM_OPT_EXP_SHIFT_PTR), from a bound that needs no pass
+        over the logits: x_out = LN_v(.) has |x_out| <= sqrt(D) max|w| + |b|, so every logit is <= B = that * max_v |W_v| (Cauchy-Schwarz).
+        c = clamp(B - 69, 0, 60): exp(s - c) can then not reach the 2^100 clamp (s - c <= 69), and for B <= 69 - the usual case, B ~ 17
+        at random init, ~ 40-70 with pretrained BERT embeddings - c = 0 and the stored values are plain exp(s). A few tiny torch
+        kernels on the current stream, no host sync; called once per train_func / loss call."""
+        if self._exp_shift is None:
+            return
+        if getattr(self, "_lm_head_max_norm", None) is None:
+            self._lm_head_max_norm = self.lm_head_weight.norm(dim=1).max()   # frozen (CLIP-DDPM.py:246-247): once
+        w, b = self._views["model.vocab_layer_norm.weight"], self._views["model.vocab_layer_norm.bias"]
+        bound = (math.sqrt(self.hp["DIM"]) * w.abs().max() + b.norm()) * self._lm_head_max_norm
+        self._exp_shift.copy_((bound - 69.0).clamp(0.0, 60.0).reshape(1))
 
     # ---------------------------------------------------------------------------------------------------------- nn.Module-ish
     def train(self, mode: bool = True):
@@ -366,6 +388,12 @@ class DistilBertModel:
         if not h:
             raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
         self._engines[key] = (h, rows, batch, ws)
+        if self.fused_softmax_grad:
+            if self._exp_shift is None:
+                self._exp_shift = torch.zeros(1, device=self.device)
+                self.refresh_exp_shift()
+            L.check(lib.clipdlm_engine_set_option(h, L.OPT_EXP_SHIFT_PTR, self._exp_shift.data_ptr()))
+            L.check(lib.clipdlm_engine_set_option(h, L.OPT_FUSED_SOFTMAX_GRAD, 1))
         if getattr(self, "_profiling", False):
             L.check(lib.clipdlm_engine_profile(h, 1))
         return h

@@ -37,7 +37,15 @@ enum {
   CLIPDLM_EPI_STORE = 0,  /* out = f(acc): +bias, dropout, +residual, gelu dual-store, *gelu'(u); bf16 pair / f32 */
   CLIPDLM_EPI_WGRAD = 1,  /* acc_f32[M,N] += acc   (split-K, fp32 red.add) */
   CLIPDLM_EPI_LSE = 2,    /* per (row, 128-col half tile) max / sum-exp / argmax partials + target logit; no logits in HBM */
-  CLIPDLM_EPI_SMGRAD = 3  /* out = (exp(acc - lse[m]) - [n == tgt[m]]) * scale   (softmax-CE gradient, bf16 pair) */
+  CLIPDLM_EPI_SMGRAD = 3, /* out = (exp(acc - lse[m]) - [n == tgt[m]]) * scale   (softmax-CE gradient, bf16 pair) */
+  /* Factored softmax gradient (plain bf16; see clipdlm_ce_row_terms): d x = sum_v softmax_v W_v - W_tgt, and
+   * softmax_v = exp(s_v - c) / sum_u exp(s_u - c) for ANY per-launch constant c, so the 1 / sum factor leaves the reduction over v:
+   * the lm_head pass stores exp(s - c) (LSE_EXP), the gradient GEMM reads that array as it is and scales its accumulator ROWS
+   * (STORE_ROWSCALE) - the pass over the [M, V] array that forms (softmax - onehot) * scale disappears. */
+  CLIPDLM_EPI_LSE_EXP = 4,        /* as LSE without arg-max tracking, partials relative to the constant *exp_shift (part_max = shift,
+                                   * part_sum = sum exp(acc - shift)); out_hi (required) receives bf16(exp(acc - shift)), exponent clamped
+                                   * to 2^100 */
+  CLIPDLM_EPI_STORE_ROWSCALE = 5  /* out = acc * row_scale[m] + residual  (plain bf16, 32-byte aligned rows, N % 256 == 0, K-major A) */
 };
 
 typedef struct clipdlm_gemm {
@@ -65,6 +73,8 @@ typedef struct clipdlm_gemm {
   const int32_t* targets; int32_t tgt_period; /* target of row m = targets[m % tgt_period] */
   const float* lse;               /* [M] (SMGRAD) */
   float grad_scale;               /* SMGRAD */
+  const float* exp_shift;         /* LSE_EXP: device scalar c (natural-log units), NULL = 0 */
+  const float* row_scale;         /* STORE_ROWSCALE: [M] fp32, indexed by the GEMM row m (before scatter) */
 } clipdlm_gemm_t;
 
 int clipdlm_gemm(const clipdlm_gemm_t* g, clipdlm_stream stream);
@@ -79,6 +89,16 @@ void clipdlm_gemm_debug_flags(uint32_t flags);
 int clipdlm_lse_combine(const float* part_max, const float* part_sum, const int32_t* part_arg, int32_t n_tiles, int32_t M,
                         const float* tgt_logit, float* lse, int32_t* argmax, double* loss_acc, double scale,
                         clipdlm_stream stream);
+
+/* Row terms of the factored softmax-CE gradient, after clipdlm_lse_combine produced lse[m] from LSE_EXP partials:
+ *   row_scale[m] = scale * exp(*exp_shift - lse[m])            (= scale / sum_v exp(s_v - shift); 0 if that is not finite)
+ *   dx[row(m), 0..D) -= scale * W[targets[m % tgt_period], 0..D)   (the one-hot term; dx bf16, read-modify-write; W = the bf16
+ *                                                                    lm_head operand of the gradient GEMM, pitch ldw)
+ * row(m) = (m / scatter_len) * scatter_stride + m % scatter_len when scatter_len > 0, else m. D % 8 == 0, 16-byte aligned rows.
+ * Replaces, together with LSE_EXP / STORE_ROWSCALE, softmax -> gather -> log -> backward of CLIP-DDPM.py:436-437 for the lm_head rows. */
+int clipdlm_ce_row_terms(const float* lse, const float* exp_shift, const int32_t* targets, int32_t tgt_period, float scale, int32_t M,
+                         const void* w_bf16, int64_t ldw, void* dx_bf16, int64_t ldx, int32_t scatter_len, int32_t scatter_stride, int32_t D,
+                         float* row_scale, clipdlm_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * HBM-bound kernels
@@ -321,6 +341,14 @@ int clipdlm_engine_backward(clipdlm_engine_t* e, clipdlm_stream stream);
  * forward returned) and, optionally, the gradient of the mode-0 input x_in (fp32 [R, max_len, dim]) written to dx_in. Used when the
  * encoder sits between caller-side layers (TRAIN_EMBEDDING=True: input_projection / output_projection, CLIP-DDPM.py:292-293,319-320). */
 int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float* dx_in /* may be NULL */, clipdlm_stream stream);
+
+/* Engine options (default 0). FUSED_SOFTMAX_GRAD = 1: plain-bf16 training passes take the factored softmax gradient
+ * (LSE_EXP lm_head pass -> clipdlm_ce_row_terms -> STORE_ROWSCALE gradient GEMM) instead of the in-place softmax-gradient pass over the
+ * stored logits; EXP_SHIFT_PTR: device pointer (as int64) to the fp32 scalar c of that path, 0 = use c = 0. The path needs
+ * max_v s_v - 69 <= c <= max_v s_v + 87 for every row (exp(s - c) must neither saturate the 2^100 clamp nor flush to zero);
+ * c = 0 holds whenever the largest logit of every row lies in [-87, 69]. Experimental in round 1: validated on the GPU in round 2. */
+enum { CLIPDLM_OPT_FUSED_SOFTMAX_GRAD = 1, CLIPDLM_OPT_EXP_SHIFT_PTR = 2 };
+int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value);
 
 /* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */
 int64_t clipdlm_engine_launch_count(const clipdlm_engine_t* e);
