@@ -258,3 +258,30 @@ def test_epoch_loop_dynamic_rounding_weight_and_debug(monkeypatch):
     hist, calls, _, _, _ = _run_epoch_loop(monkeypatch, hp, [(3, 6, 9)], [(1, 1, 1)] * 2)
     assert len(hist) == 1 and len(calls["train"]) == 1
     assert float(hist[0]["x_t_loss"]) == pytest.approx(1.0) and float(hist[0]["prob_loss"]) == pytest.approx(3.0)
+
+
+def test_factored_softmax_gradient_arithmetic():
+    """CPU emulation (torch, bf16 roundings where the kernels round) of the factored softmax-CE gradient chain that
+    tests/test_fused_softmax_grad_gpu.py checks on the GPU: stored e = bf16(exp(s - c)), fp32 row sums, row factor scale * exp(c - lse),
+    one-hot term as a gathered W row. It pins the identity the kernels rely on and the tolerances the GPU test asserts, and shows the
+    CE part of the gradient is MORE accurate than the default bf16 path's bf16((softmax - onehot) * scale)."""
+    torch.manual_seed(0)
+    bf = lambda x: x.to(torch.bfloat16).float()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    M, D, V, scale = 48, 768, 30522, 0.37
+    W = bf(torch.randn(V, D) * 0.05).double()
+    x = bf(torch.randn(M, D)).double()
+    logits = x @ W.t()
+    tgt = torch.randint(0, V, (M,))
+    ref = ((torch.softmax(logits, -1) - torch.nn.functional.one_hot(tgt, V).double()) * scale) @ W
+    ref_lse = torch.logsumexp(logits, -1)
+    for shift in (0.0, 3.5):
+        e32 = torch.exp2(torch.clamp((logits.float() - shift) * 1.4426950408889634, max=100.0))
+        lse = shift + torch.log(e32.sum(-1))
+        assert rel(lse, ref_lse) < 1e-6
+        rs = scale * torch.exp(shift - lse)
+        new = (bf(e32).double() @ W) * rs.double()[:, None] - scale * W[tgt]
+        assert rel(new, ref) < 2e-4
+    dl = bf(torch.exp(bf(logits.float()) - ref_lse.float()[:, None]) * scale - torch.nn.functional.one_hot(tgt, V).float() * scale)
+    old = dl.double() @ W
+    assert rel(old, ref) > 5 * rel(new, ref)   # default path: ~2e-3 (bf16 logits, bf16 p - 1); factored path: ~2e-5
