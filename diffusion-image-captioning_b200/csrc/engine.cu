@@ -462,11 +462,9 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
   CLIPDLM_CHECK(!lc->backward || (e->last.train || e->training), "backward needs a training engine");
   CLIPDLM_CHECK(!lc->backward || e->training, "engine was created without training buffers");
   const clipdlm_pass_t& p = e->last;
-  const int R = p.R, B = p.B, L = e->L, Ltxt = e->Ltxt, D = c.dim, F = c.hidden_dim, NL = c.n_layers;
+  const int R = p.R, B = p.B, L = e->L, Ltxt = e->Ltxt, D = c.dim;
   const int T = R * L, M16 = R * Ltxt;
   const bool bwd = lc->backward != 0;
-  const bool train = p.train != 0;
-  const float pdrop = train ? c.dropout : 0.f, padrop = train ? c.attn_dropout : 0.f;
   const long long R_total = lc->R_total > 0 ? lc->R_total : R;
   const bool mean_kind = lc->loss_kind == 0 || lc->loss_kind == 2;
   const double ce_scale = mean_kind ? 1.0 / (double)R_total : 1.0 / (double)lc->batch_size;  // CLIP-DDPM.py:437 vs :439-440
