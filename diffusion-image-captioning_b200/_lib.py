@@ -102,8 +102,8 @@ class DpBuffers(C.Structure):
                 ("shadow_lo", c_p * MAX_PEERS), ("p_mc", c_p), ("g_mc", c_p), ("shadow_hi_mc", c_p), ("shadow_lo_mc", c_p)]
 
 
-EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD, EPI_LSE_EXP, EPI_STORE_ROWSCALE = 0, 1, 2, 3, 4, 5
-OPT_FUSED_SOFTMAX_GRAD, OPT_EXP_SHIFT_PTR = 1, 2
+EPI_STORE, EPI_WGRAD, EPI_LSE, EPI_SMGRAD, EPI_LSE_EXP, EPI_STORE_ROWSCALE, EPI_STORE_GELU_DERIV, EPI_STORE_MULAUX = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_FUSED_SOFTMAX_GRAD, OPT_EXP_SHIFT_PTR, OPT_GELU_DERIV_STORE = 1, 2, 3
 
 PROF_CATEGORIES = ("gemm_fwd", "gemm_dgrad", "gemm_wgrad", "gemm_lse", "gemm_smgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "embed",
                    "loss", "colsum", "other")

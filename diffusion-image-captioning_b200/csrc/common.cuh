@@ -249,6 +249,23 @@ __device__ __forceinline__ f32x2 dgelu2(float x0, float x1) {
   const f32x2 cdf = add2(pk2(t0, t1), pk2(0.5f, 0.5f));
   return fma2(x, pdf, cdf);
 }
+// gelu(x) and gelu'(x) from ONE evaluation of the Phi tail: the forward epilogue that stores gelu'(u) for the backward
+// (CLIPDLM_EPI_STORE_GELU_DERIV) pays the exp(-x^2/2) term on top of gelu2, the backward then only multiplies.
+__device__ __forceinline__ void gelu_dgelu2(float x0, float x1, f32x2& g, f32x2& d) {
+  f32x2 an;
+  const f32x2 h = phi_tail2(x0, x1, an);
+  g = fma2(an, h, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  const f32x2 x = pk2(x0, x1);
+  const f32x2 arg = fma2(mul2(x, x), pk2(-0.72134752044448170f, -0.72134752044448170f), pk2(-1.32574806473616470f, -1.32574806473616470f));
+  float a0, a1;
+  upk2(arg, a0, a1);
+  const f32x2 pdf = pk2(ex2_ftz(a0), ex2_ftz(a1));
+  float t0, t1;
+  upk2(fma2(h, pk2(-1.f, -1.f), pk2(0.5f, 0.5f)), t0, t1);
+  t0 = __uint_as_float(__float_as_uint(t0) | (__float_as_uint(x0) & 0x80000000u));
+  t1 = __uint_as_float(__float_as_uint(t1) | (__float_as_uint(x1) & 0x80000000u));
+  d = fma2(x, pdf, add2(pk2(t0, t1), pk2(0.5f, 0.5f)));
+}
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier (shared::cta) with a bounded spin: a protocol bug traps instead of hanging the GPU.

@@ -139,6 +139,8 @@ struct clipdlm_engine {
   // options (clipdlm_engine_set_option)
   int fused_smgrad;          // CLIPDLM_OPT_FUSED_SOFTMAX_GRAD
   const float* exp_shift;    // CLIPDLM_OPT_EXP_SHIFT_PTR (device scalar) or NULL
+  int gelu_deriv;            // CLIPDLM_OPT_GELU_DERIV_STORE
+  int last_gelu_deriv;       // the last forward stored gelu'(u) in the blocks' u buffers
 };
 
 namespace clipdlm {
@@ -275,7 +277,7 @@ static double gemm_bytes(const clipdlm_gemm_t& g, int es) {
   double b = ((double)g.M * g.K + (double)g.N * g.K) * es;
   if (g.epilogue == CLIPDLM_EPI_WGRAD) b += (double)g.M * g.N * 8;  // fp32 accumulate: read + write
   else if (g.epilogue == CLIPDLM_EPI_SMGRAD) b += (double)g.M * g.N * es;
-  else if (g.epilogue == CLIPDLM_EPI_STORE || g.epilogue == CLIPDLM_EPI_STORE_ROWSCALE) {
+  else if (g.epilogue == CLIPDLM_EPI_STORE || g.epilogue >= CLIPDLM_EPI_STORE_ROWSCALE) {
     if (g.out_hi) b += (double)g.M * g.N * es;
     if (g.out2_hi) b += (double)g.M * g.N * es;
     if (g.out_f32) b += (double)g.M * g.N * 4;
@@ -337,6 +339,7 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
   em.drop_seed = p->drop_seed; em.drop_site = 0; em.drop_p = pdrop;
   RUNP(CLIPDLM_PROF_EMBED, 0, (double)T * D * (e->pair ? 4.0 : 2.0) * (train ? 2 : 1) + (double)B * Ltxt * D * 8, embed_fwd_dispatch(&em, st));
 
+  const bool gelu_deriv = e->gelu_deriv != 0 && !e->pair && e->training && e->lay[0].u.hi != nullptr;
   for (int l = 0; l < NL; ++l) {
     const LayerBufs& b = e->lay[l];
     const Act& hin = e->h[l];
@@ -350,6 +353,7 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
                                nullptr, 0, 0, 0.f, st));
     g = linear_fwd(b.h1, shadow(e, lslot(l, CLIPDLM_PL_FF1_W)), param(e, lslot(l, CLIPDLM_PL_FF1_B)), T, F, D, b.u);
     g.out2_hi = b.g.hi; g.out2_lo = b.g.lo;
+    if (gelu_deriv) g.epilogue = CLIPDLM_EPI_STORE_GELU_DERIV;   // b.u receives gelu'(u): the backward multiplies instead of evaluating it
     RUNG(g);
     g = linear_fwd(b.g, shadow(e, lslot(l, CLIPDLM_PL_FF2_W)), param(e, lslot(l, CLIPDLM_PL_FF2_B)), T, D, F, b.z2);
     g.res_hi = b.h1.hi; g.res_lo = b.h1.lo; g.ldr = D;
@@ -363,6 +367,7 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
   RUNG(g);
   RUNP(CLIPDLM_PROF_LN_FWD, 0, (double)T * 2 * D * (e->pair ? 4.0 : 2.0), layernorm_fwd_dispatch(&e->gv, param(e, CLIPDLM_P_VLN_W), param(e, CLIPDLM_P_VLN_B), c.ln_eps, T, D, &e->xo, p->x_out, 0, 0, 0.f, st));
   e->last = *p;
+  e->last_gelu_deriv = gelu_deriv ? 1 : 0;
   e->have_fwd = 1;
   return 0;
 }
@@ -418,6 +423,7 @@ static int backward_from_g0(clipdlm_engine* e, cudaStream_t st) {
     RUNG(g);
     g = linear_dgrad(dffn, shadow(e, lslot(l, CLIPDLM_PL_FF2_W)), T, D, F, e->gf);
     g.u_hi = b.u.hi; g.u_lo = b.u.lo; g.ldu = F;  // * gelu'(u)
+    if (e->last_gelu_deriv) g.epilogue = CLIPDLM_EPI_STORE_MULAUX;   // ... which the forward already evaluated and stored
     RUNG(g);
     RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * F * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gf, T, F, grad(e, lslot(l, CLIPDLM_PL_FF1_B)), st));
     g = linear_wgrad(e->gf, b.h1, T, F, D, grad(e, lslot(l, CLIPDLM_PL_FF1_W)));
@@ -657,6 +663,10 @@ int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value
       return 0;
     case CLIPDLM_OPT_EXP_SHIFT_PTR:
       e->exp_shift = reinterpret_cast<const float*>(static_cast<uintptr_t>(value));
+      return 0;
+    case CLIPDLM_OPT_GELU_DERIV_STORE:
+      CLIPDLM_CHECK(value == 0 || !e->pair, "GELU_DERIV_STORE needs plain-bf16 precision");
+      e->gelu_deriv = value != 0;
       return 0;
     default:
       CLIPDLM_CHECK(false, "set_option: unknown option %d", (int)option);

@@ -188,7 +188,9 @@ __device__ __forceinline__ void stage_row32(uint32_t buf, int row, int half, con
   }
 }
 
-template <bool BIAS, int AUX, bool DUAL, bool DROP, bool RSCALE = false>
+// GD: 0 = none; 1 = forward of a GELU layer whose backward is to be a plain multiply: out = gelu'(acc + bias), out2 = gelu(acc + bias)
+// (STORE_GELU_DERIV); 2 = that backward: out = acc * aux, aux = the stored gelu'(u) (STORE_MULAUX).
+template <bool BIAS, int AUX, bool DUAL, bool DROP, bool RSCALE = false, int GD = 0>
 __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr, int col0, int m, bool valid, long long mr, uint32_t sbias_u32,
                                                uint64_t* tfull, uint32_t tphase, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint32_t stg,
                                                int row_base) {
@@ -236,7 +238,10 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
         for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = ((keep >> i) & 1u) ? v[j8 * 8 + i] * g.drop.scale : 0.f;
       }
     }
-    if (AUX == 2) {
+    if (AUX == 2 && GD == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) upk2(mul2(pk2(v[2 * j], v[2 * j + 1]), bf2_to_f2(cur[j])), v[2 * j], v[2 * j + 1]);
+    } else if (AUX == 2) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const f32x2 r = mul2(pk2(v[2 * j], v[2 * j + 1]), dgelu2(__uint_as_float(cur[j] << 16), __uint_as_float(cur[j] & 0xffff0000u)));
@@ -244,6 +249,16 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       }
     } else if (AUX == 1) {
       row_unpack<true>(cur, v);
+    }
+    float dv[32];   // GD == 1: gelu'(pre-activation) for the first output; v becomes gelu(pre-activation) for the second
+    if (GD == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        f32x2 gg, dd;
+        gelu_dgelu2(v[2 * j], v[2 * j + 1], gg, dd);
+        upk2(dd, dv[2 * j], dv[2 * j + 1]);
+        upk2(gg, v[2 * j], v[2 * j + 1]);
+      }
     }
     if (g.tma_out) {
       // Outputs leave through shared memory + TMA: the row-wise 32-byte stores cost one L1 transaction per sector (2 K per
@@ -256,10 +271,12 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
         if (lane == 0) { if (single) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
         __syncwarp();
       }
-      if (!DUAL || out_row != nullptr) stage_row32(bufU, lane, cc & 1, v);
+      if (!DUAL || out_row != nullptr) stage_row32(bufU, lane, cc & 1, GD == 1 ? dv : v);
       if (DUAL) {
+        if (GD != 1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) upk2(gelu2(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) upk2(gelu2(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
+        }
         stage_row32(bufG, lane, cc & 1, v);
       }
       if (cc & 1) {
@@ -272,9 +289,9 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
         }
       }
     } else if (valid) {
-      if ((!DUAL || out_row != nullptr) && !(g.dbg & 256u)) row_store_pair(out_row + cc * 32, nullptr, true, v);
+      if ((!DUAL || out_row != nullptr) && !(g.dbg & 256u)) row_store_pair(out_row + cc * 32, nullptr, true, GD == 1 ? dv : v);
       if (DUAL) {
-        if (!(g.dbg & 128u)) {
+        if (GD != 1 && !(g.dbg & 128u)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) upk2(gelu2(v[2 * j], v[2 * j + 1]), v[2 * j], v[2 * j + 1]);
         }
@@ -284,7 +301,7 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
   };
   // Math-heavy bodies (GELU, gelu', Philox) stay rolled: four unrolled copies (~25 KB of SASS per mode) thrash the instruction
   // cache and measured slower than the generic loop; the light ones are fully unrolled.
-  constexpr bool HEAVY = DUAL || DROP || AUX == 2;
+  constexpr bool HEAVY = DUAL || DROP || (AUX == 2 && GD != 2);
   if (HEAVY) {
 #pragma unroll 1
     for (int c2 = 0; c2 < 4; c2 += 2) {
@@ -460,7 +477,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int row_base = (m_blk * CG + cta_rank) * BM + q * 32;
       const int m = row_base + lane;
 
-      if (EPI == CLIPDLM_EPI_STORE && g.bias != nullptr) {
+      if ((EPI == CLIPDLM_EPI_STORE || EPI == CLIPDLM_EPI_STORE_GELU_DERIV) && g.bias != nullptr) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's readers done
         for (int i = threadIdx.x - 128; i < BN; i += 32 * EPI_WARPS) {
           const int n = n_blk * BN + i;
@@ -471,10 +488,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
       const bool valid = m < g.M;
       const long long mr = valid ? map_row(g, m) : 0;
-      if (EPI == CLIPDLM_EPI_STORE_ROWSCALE) {   // out = acc * row_scale[m] + residual (the host checked the specialised-epilogue preconditions)
+      if (EPI == CLIPDLM_EPI_STORE_ROWSCALE || EPI == CLIPDLM_EPI_STORE_GELU_DERIV || EPI == CLIPDLM_EPI_STORE_MULAUX) {
+        // single-mode instantiations of the specialised epilogue (the host checked its preconditions): their own kernels, so the
+        // STORE kernels of the default path do not change
         const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_lo * 32;
-        epi_store_fast<false, 1, false, false, true>(g, ta, n_blk * BN + c_lo * 32, m, valid, mr, 0u, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg),
-                                                     row_base);
+        const int col0 = n_blk * BN + c_lo * 32;
+        const uint32_t sb = smem_u32(sbias) + c_lo * 128;
+        if (EPI == CLIPDLM_EPI_STORE_ROWSCALE)      // out = acc * row_scale[m] + residual
+          epi_store_fast<false, 1, false, false, true>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg), row_base);
+        else if (EPI == CLIPDLM_EPI_STORE_GELU_DERIV)   // out = gelu'(acc + bias), out2 = gelu(acc + bias)
+          epi_store_fast<true, 0, true, false, false, 1>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg), row_base);
+        else                                            // out = acc * u  (u = the stored gelu')
+          epi_store_fast<false, 2, false, false, false, 2>(g, ta, col0, m, valid, mr, sb, &tfull_bar[as], aphase, &tmO, &tmO2, smem_u32(stg), row_base);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -1099,6 +1124,20 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
     CLIPDLM_CHECK(ga.al32 && g->N % BN == 0, "STORE_ROWSCALE needs 32-byte aligned rows (pitches %% 16 == 0) and N %% 256 == 0 (N = %d)", g->N);
     ga.fast_mode = 2;   // epi_store_fast<no bias, residual> + row scale; also switches the TMA-store output maps on below
   }
+  if (g->epilogue == CLIPDLM_EPI_STORE_GELU_DERIV) {
+    CLIPDLM_CHECK(g->bias && g->out_hi && g->out2_hi && !g->res_hi && !g->u_hi && !g->out_f32 && !g->out_lo && !g->out2_lo && !g->a_lo && !g->b_lo &&
+                      g->drop_p == 0.f && g->scatter_len == 0 && g->b_major == 0,
+                  "STORE_GELU_DERIV: plain-bf16 out = gelu'(acc + bias), out2 = gelu(acc + bias), K-major operands only");
+    CLIPDLM_CHECK(ga.al32 && g->N % BN == 0, "STORE_GELU_DERIV needs 32-byte aligned rows (pitch %% 16 == 0) and N %% 256 == 0 (N = %d)", g->N);
+    ga.fast_mode = 9;
+  }
+  if (g->epilogue == CLIPDLM_EPI_STORE_MULAUX) {
+    CLIPDLM_CHECK(g->u_hi && g->out_hi && !g->bias && !g->res_hi && !g->out2_hi && !g->out_f32 && !g->out_lo && !g->u_lo && !g->a_lo && !g->b_lo &&
+                      g->drop_p == 0.f && g->b_major == 1,
+                  "STORE_MULAUX: plain-bf16 out = acc * u with an MN-major B operand only");
+    CLIPDLM_CHECK(ga.al32 && g->N % BN == 0, "STORE_MULAUX needs 32-byte aligned rows (pitches %% 16 == 0) and N %% 256 == 0 (N = %d)", g->N);
+    ga.fast_mode = 4;
+  }
   if (g->epilogue == CLIPDLM_EPI_STORE && ga.al32 && g->N % BN == 0 && !g->out_lo && !g->out2_lo && !g->res_lo && !g->u_lo && !g->out_f32 &&
       !(g->res_hi && g->u_hi) && (g->out_hi || g->out2_hi) && !(g_dbg_flags & 7u)) {  // (bits 7, 8: triage of the dual-store mode)
     const int aux = g->u_hi ? 2 : (g->res_hi ? 1 : 0);
@@ -1154,6 +1193,12 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
       CLIPDLM_CHECK(g->a_major == 0, "STORE_ROWSCALE epilogue expects K-major A");
       if (g->b_major == 0) return launch_gemm<0, 0, CLIPDLM_EPI_STORE_ROWSCALE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
       return launch_gemm<0, 1, CLIPDLM_EPI_STORE_ROWSCALE>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+    case CLIPDLM_EPI_STORE_GELU_DERIV:
+      CLIPDLM_CHECK(g->a_major == 0, "STORE_GELU_DERIV epilogue expects K-major A");
+      return launch_gemm<0, 0, CLIPDLM_EPI_STORE_GELU_DERIV>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
+    case CLIPDLM_EPI_STORE_MULAUX:
+      CLIPDLM_CHECK(g->a_major == 0, "STORE_MULAUX epilogue expects K-major A");
+      return launch_gemm<0, 1, CLIPDLM_EPI_STORE_MULAUX>(cg, a0, a1, b0, b1, o0, o1, ga, grid, st);
     case CLIPDLM_EPI_SMGRAD:
       CLIPDLM_CHECK(g->a_major == 0 && g->b_major == 0, "SMGRAD epilogue expects K-major operands");
       CLIPDLM_CHECK(g->out_hi && g->lse && g->targets, "SMGRAD epilogue buffers missing");

@@ -108,7 +108,8 @@ class DistilBertModel:
     """
 
     def __init__(self, embedding=None, projection=None, config=None, hp: Optional[dict] = None, precision: str = "bf16",
-                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192, fused_softmax_grad: Optional[bool] = None):
+                 device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192, fused_softmax_grad: Optional[bool] = None,
+                 gelu_deriv_store: Optional[bool] = None):
         lib = L.load()
         if not torch.cuda.is_available():
             raise L.ClipdlmError("clipdlm needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -139,6 +140,11 @@ class DistilBertModel:
             fused_softmax_grad = os.environ.get("CLIPDLM_FUSED_SOFTMAX_GRAD", "0") == "1"
         self.fused_softmax_grad = bool(fused_softmax_grad) and precision == "bf16" and not hp["TRAIN_EMBEDDING"]
         self._exp_shift = None
+        # Experimental, same status: lin1 stores gelu'(u) instead of u and the lin2 gradient GEMM multiplies by it
+        # (clipdlm.h CLIPDLM_OPT_GELU_DERIV_STORE). None = the CLIPDLM_GELU_DERIV_STORE=1 environment switch.
+        if gelu_deriv_store is None:
+            gelu_deriv_store = os.environ.get("CLIPDLM_GELU_DERIV_STORE", "0") == "1"
+        self.gelu_deriv_store = bool(gelu_deriv_store) and precision == "bf16"
         self.dp_group = None  # set by parallel.enable_data_parallel
         self.dp_world = 1
         self._cfg = L.Config(hp["N_LAYERS"], hp["DIM"], hp["N_HEADS"], hp["HIDDEN_DIM"], hp["VOCAB_SIZE"], hp["MAX_LENGTH"], hp["CLIP_DIM"],
@@ -394,6 +400,8 @@ class DistilBertModel:
                 self.refresh_exp_shift()
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_EXP_SHIFT_PTR, self._exp_shift.data_ptr()))
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_FUSED_SOFTMAX_GRAD, 1))
+        if self.gelu_deriv_store:
+            L.check(lib.clipdlm_engine_set_option(h, L.OPT_GELU_DERIV_STORE, 1))
         if getattr(self, "_profiling", False):
             L.check(lib.clipdlm_engine_profile(h, 1))
         return h

@@ -45,7 +45,12 @@ enum {
   CLIPDLM_EPI_LSE_EXP = 4,        /* as LSE without arg-max tracking, partials relative to the constant *exp_shift (part_max = shift,
                                    * part_sum = sum exp(acc - shift)); out_hi (required) receives bf16(exp(acc - shift)), exponent clamped
                                    * to 2^100 */
-  CLIPDLM_EPI_STORE_ROWSCALE = 5  /* out = acc * row_scale[m] + residual  (plain bf16, 32-byte aligned rows, N % 256 == 0, K-major A) */
+  CLIPDLM_EPI_STORE_ROWSCALE = 5, /* out = acc * row_scale[m] + residual  (plain bf16, 32-byte aligned rows, N % 256 == 0, K-major A) */
+  /* GELU layer whose backward is a plain multiply (plain bf16, same alignment rules): the forward stores gelu'(u) where STORE's dual
+   * mode stores u, the backward's epilogue multiplies by it instead of evaluating gelu' (two exp2 and a degree-6 polynomial per
+   * element in the epilogue of a K = 3072 -> N = 3072 gradient GEMM that is epilogue-issue bound). */
+  CLIPDLM_EPI_STORE_GELU_DERIV = 6, /* out = gelu'(acc + bias), out2 = gelu(acc + bias)   (K-major operands, bias required) */
+  CLIPDLM_EPI_STORE_MULAUX = 7      /* out = acc * u   (u_hi = an array a STORE_GELU_DERIV forward wrote; MN-major B) */
 };
 
 typedef struct clipdlm_gemm {
@@ -347,7 +352,10 @@ int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float
  * stored logits; EXP_SHIFT_PTR: device pointer (as int64) to the fp32 scalar c of that path, 0 = use c = 0. The path needs
  * max_v s_v - 69 <= c <= max_v s_v + 87 for every row (exp(s - c) must neither saturate the 2^100 clamp nor flush to zero);
  * c = 0 holds whenever the largest logit of every row lies in [-87, 69]. Experimental in round 1: validated on the GPU in round 2. */
-enum { CLIPDLM_OPT_FUSED_SOFTMAX_GRAD = 1, CLIPDLM_OPT_EXP_SHIFT_PTR = 2 };
+/* GELU_DERIV_STORE = 1 (plain bf16): lin1 of every block stores gelu'(u) instead of u in passes of an engine with training buffers
+ * (STORE_GELU_DERIV) and the lin2 gradient GEMM multiplies by it (STORE_MULAUX). Set it before the forward whose backward should use it.
+ * Experimental in round 1 as well. */
+enum { CLIPDLM_OPT_FUSED_SOFTMAX_GRAD = 1, CLIPDLM_OPT_EXP_SHIFT_PTR = 2, CLIPDLM_OPT_GELU_DERIV_STORE = 3 };
 int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value);
 
 /* Number of kernel launches issued by this engine since creation (bench "gpu_launches"). */

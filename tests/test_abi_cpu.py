@@ -121,6 +121,8 @@ def test_enums_match_the_binding(tmp_path):
     names = {"CLIPDLM_EPI_STORE": L.EPI_STORE, "CLIPDLM_EPI_WGRAD": L.EPI_WGRAD, "CLIPDLM_EPI_LSE": L.EPI_LSE, "CLIPDLM_EPI_SMGRAD": L.EPI_SMGRAD,
              "CLIPDLM_EPI_LSE_EXP": L.EPI_LSE_EXP, "CLIPDLM_EPI_STORE_ROWSCALE": L.EPI_STORE_ROWSCALE,
              "CLIPDLM_OPT_FUSED_SOFTMAX_GRAD": L.OPT_FUSED_SOFTMAX_GRAD, "CLIPDLM_OPT_EXP_SHIFT_PTR": L.OPT_EXP_SHIFT_PTR,
+             "CLIPDLM_EPI_STORE_GELU_DERIV": L.EPI_STORE_GELU_DERIV, "CLIPDLM_EPI_STORE_MULAUX": L.EPI_STORE_MULAUX,
+             "CLIPDLM_OPT_GELU_DERIV_STORE": L.OPT_GELU_DERIV_STORE,
              "CLIPDLM_P_POS": L.P_POS, "CLIPDLM_P_SEG": L.P_SEG, "CLIPDLM_P_LAYER0": L.P_LAYER0, "CLIPDLM_PL_QKV_W": L.PL_QKV_W,
              "CLIPDLM_PL_LN2_B": L.PL_LN2_B, "CLIPDLM_P_PER_LAYER": L.P_PER_LAYER, "CLIPDLM_PROF_NCAT": len(L.PROF_CATEGORIES),
              "CLIPDLM_MAX_PEERS": L.MAX_PEERS}

@@ -154,3 +154,66 @@ def test_exp_shift_bound_and_large_logits():
         assert abs(a - b) < 5e-4 * abs(a)
     g0, g1 = res[False][1], res[True][1]
     assert torch.isfinite(g1).all() and float((g0 * g1).sum() / (g0.norm() * g1.norm())) > 0.999
+
+
+# ------------------------------------------------------------------------------------------------ gelu'(u) stored by the forward
+@pytest.mark.parametrize("M", [144, 4096 + 48])
+def test_gelu_deriv_store_and_mulaux_kernels(G, M):
+    """STORE_GELU_DERIV (out = gelu'(xW^T + b), out2 = gelu(xW^T + b)) and STORE_MULAUX (out = (dy W) * u) against fp64 torch."""
+    K, N = 768, 3072
+    x = (torch.randn(M, K, device=DEV) * 0.7).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) * 0.04).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV) * 0.3
+    d = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16); g = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    G.gemm(a_hi=x, b_hi=w, lda=K, ldb=K, M=M, N=N, K=K, epilogue=G.L.EPI_STORE_GELU_DERIV, out_hi=d, out2_hi=g, ldo=N, bias=bias)
+    u = x.double() @ w.double().t() + bias.double()
+    Phi = 0.5 * (1 + torch.erf(u / 2 ** 0.5)); pdf = torch.exp(-0.5 * u * u) / (2 * torch.pi) ** 0.5
+    assert rel(g.float(), u * Phi) < 4e-3
+    assert rel(d.float(), Phi + u * pdf) < 4e-3
+    assert float((d.float().double() - (Phi + u * pdf)).abs().max()) < 6e-3     # bf16 rounding of values up to 1.13
+    # backward: dU = (dY W2) * gelu'(u), W2 stored [N_out = K][F = N] and read as the MN-major B operand
+    dy = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(K, N, device=DEV) * 0.04).to(torch.bfloat16)
+    du = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    G.gemm(a_hi=dy, b_hi=w2, lda=K, ldb=N, M=M, N=N, K=K, a_major=0, b_major=1, epilogue=G.L.EPI_STORE_MULAUX, out_hi=du, ldo=N, u_hi=d, ldu=N)
+    assert rel(du.float(), (dy.double() @ w2.double()) * d.float().double()) < 4e-3
+    # and it is the same gradient the default epilogue forms from the stored pre-activation
+    ub = u.float().to(torch.bfloat16)
+    du0 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    G.gemm(a_hi=dy, b_hi=w2, lda=K, ldb=N, M=M, N=N, K=K, a_major=0, b_major=1, epilogue=G.L.EPI_STORE, out_hi=du0, ldo=N, u_hi=ub, ldu=N)
+    assert rel(du.float(), du0.float()) < 8e-3
+
+
+def test_gelu_deriv_epilogues_reject_unsupported_operands(G):
+    a = torch.zeros(256, 256, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(G.L.ClipdlmError):   # no bias
+        G.gemm(a_hi=a, b_hi=a, lda=256, ldb=256, M=256, N=256, K=256, epilogue=G.L.EPI_STORE_GELU_DERIV, out_hi=a, out2_hi=a, ldo=256)
+    with pytest.raises(G.L.ClipdlmError):   # K-major B
+        G.gemm(a_hi=a, b_hi=a, lda=256, ldb=256, M=256, N=256, K=256, epilogue=G.L.EPI_STORE_MULAUX, out_hi=a, ldo=256, u_hi=a, ldu=256)
+
+
+@pytest.mark.parametrize("both", [False, True])
+def test_train_step_with_gelu_deriv_store_matches_the_default_path(both):
+    """Same weights / draws, dropout ON (the masks are counter-based, so both runs drop the same elements): losses equal (the forward
+    values do not change), gradients equal up to the bf16 rounding of gelu'(u). both=True also switches the factored softmax gradient on."""
+    import clipdlm as pkg
+    hp = pkg.default_hparams(BATCH_SIZE=6, SAMPLE_SIZE=5, N_LAYERS=2)
+    g = torch.Generator().manual_seed(4)
+    batch = {"input_ids": torch.randint(0, 30522, (6, 16), generator=g).to(DEV), "attention_mask": torch.ones(6, 16, dtype=torch.int64, device=DEV),
+             "image_clip": F.normalize(torch.randn(6, 512, generator=g), dim=-1).to(DEV), "text_clip": F.normalize(torch.randn(6, 512, generator=g), dim=-1).to(DEV)}
+    t = torch.tensor([0, 17, 400, 999, 250]).reshape(5, 1, 1)
+    n_t, n_1 = torch.randn(6, 16, 768, generator=g), torch.randn(6, 16, 768, generator=g)
+    outs = {}
+    for flag in (False, True):
+        model = pkg.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=12, gelu_deriv_store=flag,
+                                    fused_softmax_grad=flag and both).train()
+        trainer = pkg.AdamW(model.parameters(), lr=1e-4)
+        snap = {}
+        trainer.step = lambda m=model, s=snap: s.update(g=m.grad.clone())
+        losses = pkg.train_func(model, trainer, batch, t=t, noise_t=n_t, noise_1=n_1, dropout_seed=7)
+        outs[flag] = ([x.item() for x in losses], snap["g"].double())
+    (l0, g0), (l1, g1) = outs[False], outs[True]
+    for a, b in zip(l0, l1):
+        assert abs(a - b) < (2e-4 if both else 1e-6) * abs(a), (l0, l1)
+    cos = float((g0 * g1).sum() / (g0.norm() * g1.norm()))
+    assert cos > 0.999 and abs(float(g1.norm() / g0.norm()) - 1) < 1e-2, (cos, float(g1.norm() / g0.norm()))
