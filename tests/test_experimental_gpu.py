@@ -3,7 +3,7 @@
 
 Built in round 1 after the GPU budget was spent: the kernels compile for sm_100a, every kernel of the default path is unchanged
 (tools/sass_diff.py), but nothing here has run on a B200 yet - hence the switch. Round 2: run
-`CLIPDLM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_fused_softmax_grad_gpu.py -m gpu`, then `bench.py --fused-softmax-grad`."""
+`CLIPDLM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -m gpu`, then `bench.py --fused-softmax-grad`."""
 import ctypes as C
 import os
 

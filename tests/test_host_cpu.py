@@ -262,7 +262,7 @@ def test_epoch_loop_dynamic_rounding_weight_and_debug(monkeypatch):
 
 def test_factored_softmax_gradient_arithmetic():
     """CPU emulation (torch, bf16 roundings where the kernels round) of the factored softmax-CE gradient chain that
-    tests/test_fused_softmax_grad_gpu.py checks on the GPU: stored e = bf16(exp(s - c)), fp32 row sums, row factor scale * exp(c - lse),
+    tests/test_experimental_gpu.py checks on the GPU: stored e = bf16(exp(s - c)), fp32 row sums, row factor scale * exp(c - lse),
     one-hot term as a gathered W row. It pins the identity the kernels rely on and the tolerances the GPU test asserts, and shows the
     CE part of the gradient is MORE accurate than the default bf16 path's bf16((softmax - onehot) * scale)."""
     torch.manual_seed(0)

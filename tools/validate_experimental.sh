@@ -1,14 +1,14 @@
 #!/bin/bash
 # One gpurun call that validates and measures the two experimental paths of DESIGN.md section 8 (factored softmax-CE gradient,
 # gelu'(u) stored by the forward):
-#   gpurun --timeout 540 -- 'bash tools/validate_fused_softmax_grad.sh'
+#   gpurun --timeout 540 -- 'bash tools/validate_experimental.sh'
 # 1. the experimental GPU tests; 2. the WHOLE GPU suite with the path switched on through the environment; 3. bench A/B on the same box.
 # Everything lands in gpurun_out/fsg_*.  Make it the default (model.py: fused_softmax_grad default) only if 1 and 2 are green and 3 is a gain.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export CLIPDLM_TEST_EXPERIMENTAL=1
-python -m pytest tests/test_fused_softmax_grad_gpu.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/fsg_tests.log
+python -m pytest tests/test_experimental_gpu.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/fsg_tests.log
 CLIPDLM_FUSED_SOFTMAX_GRAD=1 CLIPDLM_GELU_DERIV_STORE=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/fsg_full_suite_switched_on.log
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/fsg_bench_default.json 2> gpurun_out/fsg_bench_default.err
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --fused-softmax-grad > gpurun_out/fsg_bench_fused.json 2> gpurun_out/fsg_bench_fused.err
