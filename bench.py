@@ -258,7 +258,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=args.chunk_rows,
                                     fused_softmax_grad=True if args.fused_softmax_grad else None,
-                                    gelu_deriv_store=True if args.gelu_deriv_store else None)
+                                    gelu_deriv_store=args.gelu_deriv_store if args.gelu_deriv_store else None)
     dp_mode = "single GPU"
     if world > 1:
         dp_mode = "nccl all-reduce of the flat fp32 gradients + AdamW on every rank"
@@ -379,7 +379,7 @@ def run_ours(args):
                 "value": value, "unit": "captions/s (1 caption = 101 noised sequences)" if args.workload == "train" else "captions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args), dp_exchange=dp_mode, **({"fused_softmax_grad": True} if model.fused_softmax_grad else {}),
-                                               **({"gelu_deriv_store": True} if model.gelu_deriv_store else {})),
+                                               **({"gelu_deriv_store": model.gelu_deriv_store} if model.gelu_deriv_store else {})),
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches + (args.steps if args.workload == "train" else 0), "clocks": clocks, "roofline": roofline,
@@ -425,8 +425,9 @@ def main():
                     help="N > 1 gradient exchange: fused = reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory; auto = fused, NCCL if unavailable")
     ap.add_argument("--fused-softmax-grad", action="store_true",
                     help="experimental: factored softmax-CE gradient of the lm_head (no in-place pass over the stored logits); default off")
-    ap.add_argument("--gelu-deriv-store", action="store_true",
-                    help="experimental: lin1 stores gelu'(u), the lin2 gradient GEMM multiplies by it instead of evaluating gelu'; default off")
+    ap.add_argument("--gelu-deriv-store", type=int, nargs="?", const=1, default=0, choices=[0, 1, 2],
+                    help="experimental: lin1 stores gelu'(u), the lin2 gradient GEMM multiplies by it instead of evaluating gelu' "
+                         "(2: that GEMM also sums the lin1 bias gradient in its epilogue); default off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: 'cuda' runs the eager PyTorch port on the GPU (extra comparison)")
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")

@@ -424,8 +424,11 @@ static int backward_from_g0(clipdlm_engine* e, cudaStream_t st) {
     g = linear_dgrad(dffn, shadow(e, lslot(l, CLIPDLM_PL_FF2_W)), T, D, F, e->gf);
     g.u_hi = b.u.hi; g.u_lo = b.u.lo; g.ldu = F;  // * gelu'(u)
     if (e->last_gelu_deriv) g.epilogue = CLIPDLM_EPI_STORE_MULAUX;   // ... which the forward already evaluated and stored
+    const bool fused_bias = e->last_gelu_deriv && e->gelu_deriv >= 2;
+    if (fused_bias) g.acc_f32 = grad(e, lslot(l, CLIPDLM_PL_FF1_B));   // d(lin1 bias) = column sums of gf, formed in that GEMM's epilogue
     RUNG(g);
-    RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * F * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gf, T, F, grad(e, lslot(l, CLIPDLM_PL_FF1_B)), st));
+    if (!fused_bias)
+      RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * F * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gf, T, F, grad(e, lslot(l, CLIPDLM_PL_FF1_B)), st));
     g = linear_wgrad(e->gf, b.h1, T, F, D, grad(e, lslot(l, CLIPDLM_PL_FF1_W)));
     RUNG(g);
     g = linear_dgrad(e->gf, shadow(e, lslot(l, CLIPDLM_PL_FF1_W)), T, F, D, e->g0);
@@ -666,7 +669,8 @@ int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value
       return 0;
     case CLIPDLM_OPT_GELU_DERIV_STORE:
       CLIPDLM_CHECK(value == 0 || !e->pair, "GELU_DERIV_STORE needs plain-bf16 precision");
-      e->gelu_deriv = value != 0;
+      CLIPDLM_CHECK(value >= 0 && value <= 2, "GELU_DERIV_STORE: value 0, 1 or 2");
+      e->gelu_deriv = (int)value;
       return 0;
     default:
       CLIPDLM_CHECK(false, "set_option: unknown option %d", (int)option);

@@ -282,6 +282,21 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       if (cc & 1) {
         fence_async_smem();
         __syncwarp();
+        if (GD == 2 && g.part_max != nullptr) {
+          // STORE_MULAUX with a fused bias gradient: column sums of this warp's staged [32 rows][64 columns] bf16 tile (the values the
+          // TMA store below writes; rows past M are exact zeros), one fp32 red.add pair per lane. Lane l owns columns 2l, 2l + 1: the
+          // 16-byte chunk (l >> 2) of every row, swizzled like stage_row32 - the 32 lanes of a load hit 32 different banks.
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                         : "r"(bufU + (uint32_t)r * 128u + ((uint32_t)((lane >> 2) ^ (r & 7)) << 4) + (uint32_t)(lane & 3) * 4u));
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xffff0000u);
+          }
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g.part_max + col0 + (cc >> 1) * 64 + 2 * lane), "f"(s0), "f"(s1) : "memory");
+        }
         if (lane == 0) {
           const int c0 = col0 + (cc >> 1) * 64;
           if (!DUAL || out_row != nullptr) { tma_store_2d(tmO, bufU, c0, row_base); bulk_commit(); }
@@ -1137,6 +1152,11 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
                   "STORE_MULAUX: plain-bf16 out = acc * u with an MN-major B operand only");
     CLIPDLM_CHECK(ga.al32 && g->N % BN == 0, "STORE_MULAUX needs 32-byte aligned rows (pitches %% 16 == 0) and N %% 256 == 0 (N = %d)", g->N);
     ga.fast_mode = 4;
+    if (g->acc_f32 != nullptr) {   // fused bias gradient: acc_f32[n] += sum_m out[m, n]; needs the TMA-store side of the epilogue (staged tiles)
+      CLIPDLM_CHECK(g->scatter_len == 0 && !(g_dbg_flags & 1024u) && (reinterpret_cast<uintptr_t>(g->acc_f32) & 7) == 0,
+                    "STORE_MULAUX column sums need an unscattered output and an 8-byte aligned fp32 accumulator");
+      ga.part_max = g->acc_f32;
+    }
   }
   if (g->epilogue == CLIPDLM_EPI_STORE && ga.al32 && g->N % BN == 0 && !g->out_lo && !g->out2_lo && !g->res_lo && !g->u_lo && !g->out_f32 &&
       !(g->res_hi && g->u_hi) && (g->out_hi || g->out2_hi) && !(g_dbg_flags & 7u)) {  // (bits 7, 8: triage of the dual-store mode)

@@ -142,9 +142,12 @@ class DistilBertModel:
         self._exp_shift = None
         # Experimental, same status: lin1 stores gelu'(u) instead of u and the lin2 gradient GEMM multiplies by it
         # (clipdlm.h CLIPDLM_OPT_GELU_DERIV_STORE). None = the CLIPDLM_GELU_DERIV_STORE=1 environment switch.
+        # 2 = additionally the lin1 bias gradient is summed in that GEMM's epilogue (no colsum pass over the [tokens, 3072] gradient).
         if gelu_deriv_store is None:
-            gelu_deriv_store = os.environ.get("CLIPDLM_GELU_DERIV_STORE", "0") == "1"
-        self.gelu_deriv_store = bool(gelu_deriv_store) and precision == "bf16"
+            gelu_deriv_store = int(os.environ.get("CLIPDLM_GELU_DERIV_STORE", "0") or 0)
+        self.gelu_deriv_store = int(gelu_deriv_store) if precision == "bf16" else 0
+        if self.gelu_deriv_store not in (0, 1, 2):
+            raise ValueError("gelu_deriv_store must be 0 / False, 1 / True or 2")
         self.dp_group = None  # set by parallel.enable_data_parallel
         self.dp_world = 1
         self._cfg = L.Config(hp["N_LAYERS"], hp["DIM"], hp["N_HEADS"], hp["HIDDEN_DIM"], hp["VOCAB_SIZE"], hp["MAX_LENGTH"], hp["CLIP_DIM"],
@@ -401,7 +404,7 @@ class DistilBertModel:
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_EXP_SHIFT_PTR, self._exp_shift.data_ptr()))
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_FUSED_SOFTMAX_GRAD, 1))
         if self.gelu_deriv_store:
-            L.check(lib.clipdlm_engine_set_option(h, L.OPT_GELU_DERIV_STORE, 1))
+            L.check(lib.clipdlm_engine_set_option(h, L.OPT_GELU_DERIV_STORE, self.gelu_deriv_store))
         if getattr(self, "_profiling", False):
             L.check(lib.clipdlm_engine_profile(h, 1))
         return h

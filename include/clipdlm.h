@@ -50,7 +50,9 @@ enum {
    * mode stores u, the backward's epilogue multiplies by it instead of evaluating gelu' (two exp2 and a degree-6 polynomial per
    * element in the epilogue of a K = 3072 -> N = 3072 gradient GEMM that is epilogue-issue bound). */
   CLIPDLM_EPI_STORE_GELU_DERIV = 6, /* out = gelu'(acc + bias), out2 = gelu(acc + bias)   (K-major operands, bias required) */
-  CLIPDLM_EPI_STORE_MULAUX = 7      /* out = acc * u   (u_hi = an array a STORE_GELU_DERIV forward wrote; MN-major B) */
+  CLIPDLM_EPI_STORE_MULAUX = 7      /* out = acc * u   (u_hi = an array a STORE_GELU_DERIV forward wrote; MN-major B). If acc_f32 is set
+                                     * (fp32 [N], 8-byte aligned, unscattered output): acc_f32[n] += sum_m out[m, n] of the bf16-rounded
+                                     * outputs - the bias gradient of the layer in front, without a pass over out */
 };
 
 typedef struct clipdlm_gemm {
@@ -354,6 +356,8 @@ int clipdlm_engine_backward_from(clipdlm_engine_t* e, const float* dx_out, float
  * c = 0 holds whenever the largest logit of every row lies in [-87, 69]. Experimental in round 1: validated on the GPU in round 2. */
 /* GELU_DERIV_STORE = 1 (plain bf16): lin1 of every block stores gelu'(u) instead of u in passes of an engine with training buffers
  * (STORE_GELU_DERIV) and the lin2 gradient GEMM multiplies by it (STORE_MULAUX). Set it before the forward whose backward should use it.
+ * GELU_DERIV_STORE = 2: additionally that GEMM's epilogue accumulates lin1's bias gradient (column sums of its output), which
+ * replaces one clipdlm_colsum pass over the [tokens, hidden_dim] gradient per block.
  * Experimental in round 1 as well. */
 enum { CLIPDLM_OPT_FUSED_SOFTMAX_GRAD = 1, CLIPDLM_OPT_EXP_SHIFT_PTR = 2, CLIPDLM_OPT_GELU_DERIV_STORE = 3 };
 int clipdlm_engine_set_option(clipdlm_engine_t* e, int32_t option, int64_t value);

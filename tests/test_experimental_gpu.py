@@ -177,6 +177,12 @@ def test_gelu_deriv_store_and_mulaux_kernels(G, M):
     du = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
     G.gemm(a_hi=dy, b_hi=w2, lda=K, ldb=N, M=M, N=N, K=K, a_major=0, b_major=1, epilogue=G.L.EPI_STORE_MULAUX, out_hi=du, ldo=N, u_hi=d, ldu=N)
     assert rel(du.float(), (dy.double() @ w2.double()) * d.float().double()) < 4e-3
+    # the same launch with the fused bias gradient: acc_f32[n] += column sums of the (bf16-rounded) output
+    du2 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    cs = torch.full((N,), 0.25, device=DEV)
+    G.gemm(a_hi=dy, b_hi=w2, lda=K, ldb=N, M=M, N=N, K=K, a_major=0, b_major=1, epilogue=G.L.EPI_STORE_MULAUX, out_hi=du2, ldo=N, u_hi=d, ldu=N, acc_f32=cs)
+    assert torch.equal(du2, du)
+    assert rel(cs, 0.25 + du.float().double().sum(0)) < 1e-5
     # and it is the same gradient the default epilogue forms from the stored pre-activation
     ub = u.float().to(torch.bfloat16)
     du0 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
@@ -192,8 +198,8 @@ def test_gelu_deriv_epilogues_reject_unsupported_operands(G):
         G.gemm(a_hi=a, b_hi=a, lda=256, ldb=256, M=256, N=256, K=256, epilogue=G.L.EPI_STORE_MULAUX, out_hi=a, ldo=256, u_hi=a, ldu=256)
 
 
-@pytest.mark.parametrize("both", [False, True])
-def test_train_step_with_gelu_deriv_store_matches_the_default_path(both):
+@pytest.mark.parametrize("both,level", [(False, 1), (False, 2), (True, 2)])
+def test_train_step_with_gelu_deriv_store_matches_the_default_path(both, level):
     """Same weights / draws, dropout ON (the masks are counter-based, so both runs drop the same elements): losses equal (the forward
     values do not change), gradients equal up to the bf16 rounding of gelu'(u). both=True also switches the factored softmax gradient on."""
     import clipdlm as pkg
@@ -205,7 +211,7 @@ def test_train_step_with_gelu_deriv_store_matches_the_default_path(both):
     n_t, n_1 = torch.randn(6, 16, 768, generator=g), torch.randn(6, 16, 768, generator=g)
     outs = {}
     for flag in (False, True):
-        model = pkg.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=12, gelu_deriv_store=flag,
+        model = pkg.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=12, gelu_deriv_store=level if flag else 0,
                                     fused_softmax_grad=flag and both).train()
         trainer = pkg.AdamW(model.parameters(), lr=1e-4)
         snap = {}
