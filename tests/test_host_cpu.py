@@ -285,3 +285,25 @@ def test_factored_softmax_gradient_arithmetic():
     dl = bf(torch.exp(bf(logits.float()) - ref_lse.float()[:, None]) * scale - torch.nn.functional.one_hot(tgt, V).float() * scale)
     old = dl.double() @ W
     assert rel(old, ref) > 5 * rel(new, ref)   # default path: ~2e-3 (bf16 logits, bf16 p - 1); factored path: ~2e-5
+
+
+def test_exp_shift_bound_formula():
+    """DistilBertModel.refresh_exp_shift on a stub (CPU tensors): c = clamp((sqrt(D) max|w| + |b|) max_v |W_v| - 69, 0, 60), and the bound
+    really bounds the logits of LayerNorm outputs."""
+    from clipdlm.model import DistilBertModel
+    import types
+    torch.manual_seed(0)
+    D, V = 768, 500
+    for scale, expect_zero in ((0.02, True), (0.2, False), (5.0, False)):
+        W = torch.randn(V, D) * scale
+        w, b = 1 + 0.1 * torch.randn(D), 0.05 * torch.randn(D)
+        stub = types.SimpleNamespace(_exp_shift=torch.zeros(1), _lm_head_max_norm=None, lm_head_weight=W, hp={"DIM": D},
+                                     _views={"model.vocab_layer_norm.weight": w, "model.vocab_layer_norm.bias": b})
+        DistilBertModel.refresh_exp_shift(stub)
+        bound = float((D ** 0.5 * w.abs().max() + b.norm()) * W.norm(dim=1).max())
+        assert float(stub._exp_shift) == pytest.approx(min(max(bound - 69.0, 0.0), 60.0), rel=1e-5, abs=1e-6)
+        assert (float(stub._exp_shift) == 0.0) == expect_zero
+        x = torch.nn.functional.layer_norm(torch.randn(64, D) * 3, (D,), w, b, eps=1e-12)
+        assert float((x @ W.t()).max()) <= bound
+    stub._exp_shift = None
+    DistilBertModel.refresh_exp_shift(stub)   # option off: nothing to do
