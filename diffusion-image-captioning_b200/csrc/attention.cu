@@ -7,6 +7,7 @@
 // written to HBM: the backward recomputes the probabilities from q, k and the key mask, and regenerates the dropout mask
 // from the counter-based RNG, so no [R, H, L, L] tensor ever exists in memory.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/clipdlm.h"
 #include <cudaTypedefs.h>
 
@@ -686,6 +687,10 @@ static int launch_ring(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, cons
   a.stages = (int)((216u * 1024u) / stage_bytes);
   if (a.stages > 32) a.stages = 32;
   a.consumers = BWD ? 10 : 14;
+  if (BWD) {   // tuning knob (tools/attn_perf.py): the backward's launch bound of 384 threads leaves room for 11 consumer warps + the producer
+    static const int env_consumers = [] { const char* v = getenv("CLIPDLM_ATTN_BWD_CONSUMERS"); return v ? atoi(v) : 0; }();
+    if (env_consumers >= 1 && env_consumers <= 11) a.consumers = env_consumers;
+  }
   if (a.consumers > a.stages - 4) a.consumers = a.stages - 4;
   const size_t smem = 1024 + (size_t)a.stages * stage_bytes + 1024 + (size_t)2 * a.stages * sizeof(uint64_t);
   static bool attr_set = false;

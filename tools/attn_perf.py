@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the attention kernels at the train-chunk shape (R = 4096 sequences x L = 18, 12 heads): paths 0 (tcgen05 packed
 tiles), 2 (mma.sync TMA ring), with and without dropout. Triage tool.
+CLIPDLM_ATTN_BWD_CONSUMERS=9..11 overrides the consumer-warp count of the TMA-ring backward (default 10).
 SEQ / DIM / ROWS env vars select other shapes (SEQ > 32: the one- / two-sequence-per-tile tcgen05 kernels, e.g. SEQ=66 DIM=1024)."""
 import ctypes as C
 import os
