@@ -256,7 +256,7 @@ def run_ours(args):
     if args.train_embedding:  # CLIP-DDPM.py:98-102: 16-channel learned embedding, trainable lm_head and in/out projections
         hp.update(TRAIN_EMBEDDING=True, IN_CHANNEL=16)
     torch.manual_seed(0)
-    model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision="bf16", seed=0, chunk_rows=args.chunk_rows,
+    model = clipdlm.DistilBertModel(None, None, None, hp=hp, precision=args.precision, seed=0, chunk_rows=args.chunk_rows,
                                     fused_softmax_grad=True if args.fused_softmax_grad else None,
                                     gelu_deriv_store=args.gelu_deriv_store if args.gelu_deriv_store else None)
     dp_mode = "single GPU"
@@ -378,7 +378,7 @@ def run_ours(args):
         line = {"metric": "training samples/sec (seq=16)" if args.workload == "train" else "denoise-loop captions/sec (100 steps)",
                 "value": value, "unit": "captions/s (1 caption = 101 noised sequences)" if args.workload == "train" else "captions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args), dp_exchange=dp_mode, **({"fused_softmax_grad": True} if model.fused_softmax_grad else {}),
+                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": dict(workload_config(args), dp_exchange=dp_mode, **({"fused_softmax_grad": True} if model.fused_softmax_grad else {}),
                                                **({"gelu_deriv_store": model.gelu_deriv_store} if model.gelu_deriv_store else {})),
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--gelu-deriv-store", type=int, nargs="?", const=1, default=0, choices=[0, 1, 2],
                     help="experimental: lin1 stores gelu'(u), the lin2 gradient GEMM multiplies by it instead of evaluating gelu' "
                          "(2: that GEMM also sums the lin1 bias gradient in its epilogue); default off")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"],
+                    help="bf16 = speed mode (BASELINE.json configs[1]); bf16x3 = parity mode (split-bf16 operands, fp32-class results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: 'cuda' runs the eager PyTorch port on the GPU (extra comparison)")
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda under torch.autocast(bfloat16)")

@@ -134,17 +134,22 @@ class DistilBertModel:
         self.precision = precision
         self.training = True
         self.chunk_rows = int(chunk_rows)
-        # Experimental (round 1: built, default off, to be validated on the GPU): factored softmax-CE gradient of the lm_head in
-        # precision="bf16" (clipdlm.h CLIPDLM_OPT_FUSED_SOFTMAX_GRAD). None = the CLIPDLM_FUSED_SOFTMAX_GRAD=1 environment switch.
+        # Factored softmax-CE gradient of the lm_head in precision="bf16" (clipdlm.h CLIPDLM_OPT_FUSED_SOFTMAX_GRAD): the lm_head pass stores
+        # exp(s - c) instead of the logits and the gradient GEMM applies 1 / sum as a row factor - no in-place pass over the stored
+        # logits. Default ON since round 2 (validated on B200: tests/test_fused_paths_gpu.py, -13 ms per step); None = the
+        # CLIPDLM_FUSED_SOFTMAX_GRAD environment switch (0 selects the in-place path, which also is the automatic fallback when the
+        # logit bound of refresh_exp_shift() leaves the range the stored exponentials cover).
         if fused_softmax_grad is None:
-            fused_softmax_grad = os.environ.get("CLIPDLM_FUSED_SOFTMAX_GRAD", "0") == "1"
+            fused_softmax_grad = os.environ.get("CLIPDLM_FUSED_SOFTMAX_GRAD", "1") == "1"
         self.fused_softmax_grad = bool(fused_softmax_grad) and precision == "bf16" and not hp["TRAIN_EMBEDDING"]
         self._exp_shift = None
-        # Experimental, same status: lin1 stores gelu'(u) instead of u and the lin2 gradient GEMM multiplies by it
-        # (clipdlm.h CLIPDLM_OPT_GELU_DERIV_STORE). None = the CLIPDLM_GELU_DERIV_STORE=1 environment switch.
+        self._exp_bound_host = None     # pinned copy of the logit bound, checked one step late (no host sync on the step path)
+        self._exp_bound_event = None
+        # lin1 stores gelu'(u) instead of u and the lin2 gradient GEMM multiplies by it (clipdlm.h CLIPDLM_OPT_GELU_DERIV_STORE);
         # 2 = additionally the lin1 bias gradient is summed in that GEMM's epilogue (no colsum pass over the [tokens, 3072] gradient).
+        # Default 2 since round 2 (-9 ms per step); None = the CLIPDLM_GELU_DERIV_STORE environment switch (0 / 1 / 2).
         if gelu_deriv_store is None:
-            gelu_deriv_store = int(os.environ.get("CLIPDLM_GELU_DERIV_STORE", "0") or 0)
+            gelu_deriv_store = int(os.environ.get("CLIPDLM_GELU_DERIV_STORE", "2") or 0)
         self.gelu_deriv_store = int(gelu_deriv_store) if precision == "bf16" else 0
         if self.gelu_deriv_store not in (0, 1, 2):
             raise ValueError("gelu_deriv_store must be 0 / False, 1 / True or 2")
@@ -329,19 +334,48 @@ class DistilBertModel:
             n = self.hp["VOCAB_SIZE"] * self.hp["DIM"]
             L.check(lib.clipdlm_to_bf16(L.ptr(self.lm_head_weight), L.ptr(self.emb_hi), L.ptr(self.emb_lo), n, st))
 
+    EXP_SHIFT_MAX = 60.0    # with c <= 60 a row whose largest logit is >= -27 still has exp(s - c) far above underflow
+    EXP_ARG_MAX = 69.0      # exp(s - c) stays below the kernel's 2^100 clamp while s - c <= 69
+
     def refresh_exp_shift(self):
         """Exponent shift c of the factored softmax gradient (clipdlm.h CLIPDLM_OPT_EXP_SHIFT_PTR), from a bound that needs no pass
-        over the logits: x_out = LN_v(.) has |x_out| <= sqrt(D) max|w| + |b|, so every logit is <= B = that * max_v |W_v| (Cauchy-Schwarz).
+        over the logits: x_out = LN_v(.) has |x_out| <= sqrt(D) max|w| + |b|, so every logit is <= B = that * max_v |W_v| (Cauchy-Schwarz);
+        under classifier-free guidance the lm_head reads the mix (1 + w) guided - w unguided, whose norm is up to (1 + 2w) times that.
         c = clamp(B - 69, 0, 60): exp(s - c) can then not reach the 2^100 clamp (s - c <= 69), and for B <= 69 - the usual case, B ~ 17
         at random init, ~ 40-70 with pretrained BERT embeddings - c = 0 and the stored values are plain exp(s). A few tiny torch
-        kernels on the current stream, no host sync; called once per train_func / loss call."""
-        if self._exp_shift is None:
+        kernels on the current stream, no host sync; called once per train_func / loss call. B > 129 would need c > 60: the bound
+        is copied to pinned memory and looked at one call later (an event query, still no sync) - past it the model switches itself
+        to the in-place softmax-gradient path for good instead of saturating silently."""
+        if self._exp_shift is None or not self.fused_softmax_grad:
             return
+        if self._exp_bound_event is not None and self._exp_bound_event.query():
+            self._check_exp_bound(float(self._exp_bound_host[0]))
+            if not self.fused_softmax_grad:
+                return
         if getattr(self, "_lm_head_max_norm", None) is None:
             self._lm_head_max_norm = self.lm_head_weight.norm(dim=1).max()   # frozen (CLIP-DDPM.py:246-247): once
         w, b = self._views["model.vocab_layer_norm.weight"], self._views["model.vocab_layer_norm.bias"]
-        bound = (math.sqrt(self.hp["DIM"]) * w.abs().max() + b.norm()) * self._lm_head_max_norm
-        self._exp_shift.copy_((bound - 69.0).clamp(0.0, 60.0).reshape(1))
+        cfg_w = max(float(self.hp["CLASSIFIER_FREE_WEIGHT"]), 0.0)
+        bound = (math.sqrt(self.hp["DIM"]) * w.abs().max() + b.norm()) * self._lm_head_max_norm * (1.0 + 2.0 * cfg_w)
+        self._exp_shift.copy_((bound - self.EXP_ARG_MAX).clamp(0.0, self.EXP_SHIFT_MAX).reshape(1))
+        if self._exp_bound_host is None:    # first call (engine creation, off the step path): look at the bound right away
+            self._exp_bound_host = torch.empty(1, pin_memory=True)
+            self._exp_bound_event = torch.cuda.Event()
+            self._check_exp_bound(float(bound.item()))
+            if not self.fused_softmax_grad:
+                return
+        self._exp_bound_host.copy_(bound.reshape(1), non_blocking=True)
+        self._exp_bound_event.record(torch.cuda.current_stream(self.device))
+
+    def _check_exp_bound(self, bound: float):
+        if bound <= self.EXP_ARG_MAX + self.EXP_SHIFT_MAX and math.isfinite(bound):
+            return
+        import warnings
+        warnings.warn(f"clipdlm: logit bound {bound:.1f} exceeds {self.EXP_ARG_MAX + self.EXP_SHIFT_MAX:.0f}; the factored softmax gradient "
+                      "is switched off for this model (in-place softmax-gradient path from here on)")
+        self.fused_softmax_grad = False
+        for e in self._engines.values():
+            L.check(L.load().clipdlm_engine_set_option(e[0], L.OPT_FUSED_SOFTMAX_GRAD, 0))
 
     # ---------------------------------------------------------------------------------------------------------- nn.Module-ish
     def train(self, mode: bool = True):
@@ -397,10 +431,10 @@ class DistilBertModel:
         if not h:
             raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
         self._engines[key] = (h, rows, batch, ws)
+        if self.fused_softmax_grad and self._exp_shift is None:
+            self._exp_shift = torch.zeros(1, device=self.device)
+            self.refresh_exp_shift()   # may switch the option off (logit bound out of range)
         if self.fused_softmax_grad:
-            if self._exp_shift is None:
-                self._exp_shift = torch.zeros(1, device=self.device)
-                self.refresh_exp_shift()
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_EXP_SHIFT_PTR, self._exp_shift.data_ptr()))
             L.check(lib.clipdlm_engine_set_option(h, L.OPT_FUSED_SOFTMAX_GRAD, 1))
         if self.gelu_deriv_store:

@@ -59,3 +59,17 @@ def golden_inputs(hp):
 def rel(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ---- BASELINE.json configs[0] dimensions (the reference's own defaults): tests/golden/real_width_6L.npz, make_golden.py::make_real_width
+REAL_WIDTH_HP = dict(BATCH_SIZE=8, SAMPLE_SIZE=100, N_LAYERS=6, VOCAB_SIZE=30522, DROPOUT=0.0, ATTENTION_DROPOUT=0.0)
+
+
+def real_width_inputs(step: int = 0):
+    hp = O.default_hparams()
+    hp.update(REAL_WIDTH_HP)
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    t = (torch.arange(S, dtype=torch.int64) * 373 + 11) % 1000
+    t[0], t[-1] = 0, 999
+    return hp, dict(batch=O.closed_form_batch(hp, k=1, ragged=True), t=t.reshape(S, 1, 1), restored=O.closed_form_tensor((B, ML + 2, D), 6, 1.0),
+                    noise_t=O.closed_form_tensor((B, ML, D), 7 + 10 * step, 1.0), noise_1=O.closed_form_tensor((B, ML, D), 8 + 10 * step, 1.0))

@@ -108,10 +108,82 @@ def make_case(name: str, full: bool = True, **kw):
     print(name, "losses", out["train_losses"], "min top-2 gaps", out["fwd_top2_gap"].min(), out["sample_top2_gap"].min())
 
 
+REAL_WIDTH_HP = dict(BATCH_SIZE=8, SAMPLE_SIZE=100, N_LAYERS=6, VOCAB_SIZE=30522, DROPOUT=0.0, ATTENTION_DROPOUT=0.0)
+
+
+def real_width_t(S: int) -> torch.Tensor:
+    """Pinned noise levels for the real-width case: spread over 0..999, includes t = 0 and t = 999."""
+    t = (torch.arange(S, dtype=torch.int64) * 373 + 11) % 1000
+    t[0], t[-1] = 0, 999
+    return t.reshape(S, 1, 1)
+
+
+def make_real_width(name: str = "real_width_6L", steps: int = 2):
+    """BASELINE.json configs[0] dimensions: the reference's own defaults (CLIP-DDPM.py:55-114) - 6 layers, V = 30522, B = 8, S = 100
+    (808 encoder rows per step) - with dropout 0 and pinned t / noise. Stores scalars, norms and slices only (the gradients are
+    44 M elements): per-step losses of `steps` consecutive train_func calls (AdamW lr 1e-4 in between), every gradient's norm + its first
+    256 elements after step 0, post-AdamW parameter norms, a strided sample of the step-0 x_out / logits via a 5-step denoise loop."""
+    hp = O.default_hparams()
+    hp.update(REAL_WIDTH_HP)
+    ns = H.build_namespace(hp)
+    model = H.build_model(ns, hp, seed=0)
+    P = O.init_params(hp, seed=0, closed_form=True)
+    H.load_params(model, P)
+    batch = O.closed_form_batch(hp, k=1, ragged=True)
+    B, S, ML, D = hp["BATCH_SIZE"], hp["SAMPLE_SIZE"], hp["MAX_LENGTH"], hp["IN_CHANNEL"]
+    out = {}
+    # 5-step denoise loop BEFORE training (the reference's eval shape, :613-621)
+    model.eval()
+    restored = O.closed_form_tensor((B, ML + 2, D), 6, 1.0)
+    r = restored.clone()
+    ids_steps, gaps = [], []
+    with torch.no_grad():
+        for _ in range(5):
+            o, r = model(r[:, :ML, :], batch["image_clip"].unsqueeze(1), torch.zeros_like(batch["image_clip"]).unsqueeze(1),
+                         torch.ones(B, ML), torch.tensor([1, 0]).repeat(B, 1))
+            ids_steps.append(torch.softmax(o, -1).argmax(-1).numpy())
+            t2 = o.topk(2, dim=-1).values
+            gaps.append((t2[..., 0] - t2[..., 1]).numpy())
+    out["sample_ids_steps"] = np.stack(ids_steps)
+    out["sample_top2_gap_steps"] = np.stack(gaps)
+    out["sample_restored_slice"] = r[:, :, ::16].numpy()
+    out["sample_logits_slice"] = o[:, :, ::509].numpy()
+    # train steps
+    model.train()
+    t = real_width_t(S)
+    out["t"] = t.reshape(-1).numpy()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    losses = []
+    for k in range(steps):
+        n_t = O.closed_form_tensor((B, ML, D), 7 + 10 * k, 1.0)
+        n_1 = O.closed_form_tensor((B, ML, D), 8 + 10 * k, 1.0)
+        ns["torch"] = _TorchProxy(t, [n_t, n_1])
+        l, a, b, c = ns["train_func"](model, opt, batch)
+        ns["torch"] = torch
+        losses.append([l.item(), a.item(), b.item(), c.item()])
+        print(name, "step", k, losses[-1], flush=True)
+        if k == 0:
+            grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+            names = [n for n in O.trainable_names(hp) if n in grads]
+            out["grad_names"] = np.array(names)
+            out["grad_norms"] = np.array([float(grads[n].double().norm()) for n in names])
+            for n in names:
+                out["grad::" + n] = grads[n].reshape(-1)[:256].numpy()
+            after = H.export_params(model)
+            out["after_norms"] = np.array([float(after[n].double().norm()) for n in names])
+            out["after_delta_norms"] = np.array([float((after[n].double() - P[n].double()).norm()) for n in names])
+    out["train_losses"] = np.array(losses, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "min top-2 gap", out["sample_top2_gap_steps"].min())
+
+
 if __name__ == "__main__":
     if not H.available():
         sys.exit("reference unavailable")
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "real":  # BASELINE.json configs[0] dimensions (about 2 minutes of CPU)
+        make_real_width()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "te":  # only the TRAIN_EMBEDDING cases (added later; the others are unchanged)
         make_case("te_concat_l1", TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="concat", LOSS_FUNC="series_sum_sample_mean")
         make_case("te_add_mse_mean", full=False, TRAIN_EMBEDDING=True, IN_CHANNEL=16, CLIP_ADDING_METHOD="add", LOSS_FUNC="mse_series_mean")

@@ -1,9 +1,8 @@
-"""-m gpu, EXPERIMENTAL (skipped unless CLIPDLM_TEST_EXPERIMENTAL=1): the factored softmax-CE gradient of the lm_head
-(clipdlm.h CLIPDLM_EPI_LSE_EXP / CLIPDLM_EPI_STORE_ROWSCALE / clipdlm_ce_row_terms / CLIPDLM_OPT_FUSED_SOFTMAX_GRAD).
-
-Built in round 1 after the GPU budget was spent: the kernels compile for sm_100a, every kernel of the default path is unchanged
-(tools/sass_diff.py), but nothing here has run on a B200 yet - hence the switch. Round 2: run
-`CLIPDLM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -m gpu`, then `bench.py --fused-softmax-grad`."""
+"""-m gpu: the two fused paths that became the bf16 default in round 2 (validated on B200: profiles/r02_validate_fused_paths.log):
+  * the factored softmax-CE gradient of the lm_head (clipdlm.h CLIPDLM_EPI_LSE_EXP / CLIPDLM_EPI_STORE_ROWSCALE / clipdlm_ce_row_terms /
+    CLIPDLM_OPT_FUSED_SOFTMAX_GRAD) against fp64 torch and against the in-place softmax-gradient path it replaces,
+  * gelu'(u) stored by lin1's epilogue + the multiplying lin2 gradient GEMM (+ lin1's bias gradient summed in that epilogue)
+    (CLIPDLM_EPI_STORE_GELU_DERIV / CLIPDLM_EPI_STORE_MULAUX / CLIPDLM_OPT_GELU_DERIV_STORE)."""
 import ctypes as C
 import os
 
@@ -13,8 +12,7 @@ import torch.nn.functional as F
 
 from _util import O, rel
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CLIPDLM_TEST_EXPERIMENTAL") != "1", reason="experimental path: set CLIPDLM_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
 
@@ -154,6 +152,39 @@ def test_exp_shift_bound_and_large_logits():
         assert abs(a - b) < 5e-4 * abs(a)
     g0, g1 = res[False][1], res[True][1]
     assert torch.isfinite(g1).all() and float((g0 * g1).sum() / (g0.norm() * g1.norm())) > 0.999
+
+
+def test_logit_bound_out_of_range_falls_back_to_the_inplace_path():
+    """a bound past 69 + 60 must not saturate silently. lm_head weight x 12 => Cauchy-Schwarz bound ~ 184: the model warns, switches
+    the factored path off (also under classifier-free guidance, whose mixed x_out widens the bound by 1 + 2w) and gives the in-place path's numbers."""
+    import clipdlm as pkg
+    hp = pkg.default_hparams(BATCH_SIZE=4, SAMPLE_SIZE=3, N_LAYERS=2, DROPOUT=0.0, ATTENTION_DROPOUT=0.0)
+    g = torch.Generator().manual_seed(5)
+    E = torch.randn(30522, 768, generator=g) * 0.02
+    batch = {"input_ids": torch.randint(0, 30522, (4, 16), generator=g).to(DEV), "attention_mask": torch.ones(4, 16, dtype=torch.int64, device=DEV),
+             "image_clip": F.normalize(torch.randn(4, 512, generator=g), dim=-1).to(DEV), "text_clip": F.normalize(torch.randn(4, 512, generator=g), dim=-1).to(DEV)}
+    t = torch.tensor([3, 250, 900]).reshape(3, 1, 1)
+    n_t, n_1 = torch.randn(4, 16, 768, generator=g), torch.randn(4, 16, 768, generator=g)
+    res = {}
+    for flag in (False, True):
+        model = pkg.DistilBertModel(E, E * 12.0, None, hp=hp, precision="bf16", seed=0, fused_softmax_grad=flag).train()
+        trainer = pkg.AdamW(model.parameters(), lr=1e-4)
+        snap = {}
+        trainer.step = lambda m=model, s=snap: s.update(g=m.grad.clone())
+        if flag:
+            with pytest.warns(UserWarning, match="logit bound"):
+                losses = pkg.train_func(model, trainer, batch, t=t, noise_t=n_t, noise_1=n_1, dropout_seed=1)
+            assert model.fused_softmax_grad is False
+        else:
+            losses = pkg.train_func(model, trainer, batch, t=t, noise_t=n_t, noise_1=n_1, dropout_seed=1)
+        res[flag] = ([x.item() for x in losses], snap["g"].double())
+    assert res[False][0] == res[True][0] and torch.equal(res[False][1], res[True][1])   # the same kernels ran
+    # classifier-free guidance widens the bound: x 4 alone stays inside (bound ~ 66 < 69, c = 0), with w = 0.25 (factor 1.5) c > 0
+    hp2 = dict(hp, CLASSIFIER_FREE_WEIGHT=0.25)
+    m_plain = pkg.DistilBertModel(E, E * 4.0, None, hp=hp, precision="bf16", seed=0, fused_softmax_grad=True)
+    m_cfg = pkg.DistilBertModel(E, E * 4.0, None, hp=hp2, precision="bf16", seed=0, fused_softmax_grad=True)
+    m_plain._engine(12, 4, True); m_cfg._engine(12, 4, True)
+    assert float(m_plain._exp_shift.item()) == 0.0 and float(m_cfg._exp_shift.item()) > 0.0
 
 
 # ------------------------------------------------------------------------------------------------ gelu'(u) stored by the forward

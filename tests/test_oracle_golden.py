@@ -79,3 +79,31 @@ def test_structural_invariants():
     np.testing.assert_allclose(P["text_linear.weight"].detach().numpy(), (before * (1 - 1e-3 * 0.01)).numpy(), rtol=1e-6)
     pg = P["model.distilbert.embeddings.position_embeddings.weight"].grad
     assert int((pg.abs().sum(dim=1) > 0).sum()) == hp["MAX_LENGTH"] + 1  # position 17 (masked text-CLIP slot) only reaches x_out[:, 17]
+
+
+def test_real_width_oracle_matches_reference():
+    """The reference's real dimensions (6 layers, V = 30522, B = 8, S = 100; CLIP-DDPM.py:57,109 = BASELINE.json configs[0]): the oracle
+    replays the fixture the REAL reference produced (tests/golden/make_golden.py real) - 5-step denoise ids at every step, one train
+    step's losses / gradient norms + slices / AdamW deltas. About 25 s on 8 cores."""
+    from _util import real_width_inputs
+    g = load_golden("real_width_6L")
+    hp, inp = real_width_inputs(0)
+    assert np.array_equal(inp["t"].reshape(-1).numpy(), g["t"])
+    P = O.init_params(hp, seed=0, closed_form=True)
+    ids, restored, outs = O.sample(P, inp["batch"]["image_clip"], hp, 5, inp["restored"].clone(), return_all=True) \
+        if "return_all" in O.sample.__code__.co_varnames else (*O.sample(P, inp["batch"]["image_clip"], hp, 5, inp["restored"].clone()), None)
+    assert np.array_equal(ids.numpy(), g["sample_ids_steps"][-1])
+    assert rel(restored[:, :, ::16], g["sample_restored_slice"]) < 1e-5
+    P0 = {k: v.clone() for k, v in P.items()}
+    opt = O.AdamW(O.make_trainable(P, hp), lr=1e-4)
+    l = O.train_func(P, opt, inp["batch"], hp, O.alpha_cumprod(hp), True, t=inp["t"], noise_t=inp["noise_t"], noise_1=inp["noise_1"])
+    np.testing.assert_allclose([x.item() for x in l], g["train_losses"][0], rtol=2e-5)
+    names = [str(n) for n in g["grad_names"]]
+    gscale = float(g["grad_norms"].max())
+    for n, ref_norm, dn in zip(names, g["grad_norms"], g["after_delta_norms"]):
+        grad = P[n].grad
+        assert abs(float(grad.double().norm()) - ref_norm) <= 3e-4 * max(ref_norm, 1e-4 * gscale), n
+        ref = torch.from_numpy(g["grad::" + n])
+        assert float((grad.reshape(-1)[:256].double() - ref.double()).norm()) <= 3e-4 * max(float(ref.double().norm()), 1e-4 * gscale), n
+        if not (0.0 < ref_norm < 1e-4 * gscale):
+            assert abs(float((P[n].detach().double() - P0[n].double()).norm()) - dn) <= 1e-3 * dn + 1e-9, n

@@ -28,3 +28,13 @@ for n in ("default", "fused", "gelud", "gelud2", "both", "default_again"):
     except Exception as ex:
         print(n, "no result:", ex)
 PY
+# parity-mode (bf16x3) step time on the same box (VERDICT r1 missing #3)
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --precision bf16x3 > gpurun_out/fsg_bench_bf16x3.json 2> gpurun_out/fsg_bench_bf16x3.err
+python - <<'PY'
+import json
+try:
+    d = json.load(open("gpurun_out/fsg_bench_bf16x3.json"))
+    print("bf16x3", round(d["ms_per_step"], 2), "ms/step", round(d["value"], 1), "captions/s", {k: round(v["ms_per_step"], 1) for k, v in d["kernels"].items()})
+except Exception as ex:
+    print("bf16x3 no result:", ex)
+PY
