@@ -32,8 +32,23 @@ class DeviceCaptionDataset:
     def __len__(self) -> int:
         return int(self.input_ids.shape[0])
 
-    def batch(self, idx: torch.Tensor) -> Dict[str, object]:
+    TENSOR_KEYS = ("image_clip", "text_clip", "input_ids", "attention_mask")
+
+    def pin_memory(self) -> "DeviceCaptionDataset":
+        """Host-resident variant (a caption set larger than HBM, or the bench's end-to-end leg): page-lock the four arrays so that
+        batches gathered into pinned staging buffers (`loader(..., pin_staging=True)`) cross PCIe with asynchronous copies."""
+        if self.device.type == "cpu" and torch.cuda.is_available():
+            for k in self.TENSOR_KEYS:
+                setattr(self, k, getattr(self, k).pin_memory())
+        return self
+
+    def batch(self, idx: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, object]:
+        """Four gathers. `out` (host datasets): preallocated, pinned [B, ...] staging tensors the rows are gathered into."""
         idx = idx.to(self.device)
+        if out is not None:
+            for k in self.TENSOR_KEYS:
+                torch.index_select(getattr(self, k), 0, idx, out=out[k])
+            return dict(out)
         out: Dict[str, object] = {"image_clip": self.image_clip[idx], "text_clip": self.text_clip[idx], "input_ids": self.input_ids[idx],
                                   "attention_mask": self.attention_mask[idx]}
         if self.image is not None:
@@ -58,8 +73,8 @@ class CaptionSubset:
         return int(self.indices.numel())
 
     def loader(self, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None, rank: int = 0,
-               world: int = 1) -> "CaptionLoader":
-        return CaptionLoader(self, batch_size, shuffle, generator, rank, world)
+               world: int = 1, pin_staging: bool = False) -> "CaptionLoader":
+        return CaptionLoader(self, batch_size, shuffle, generator, rank, world, pin_staging)
 
 
 class CaptionLoader:
@@ -67,8 +82,18 @@ class CaptionLoader:
     permutation per epoch when shuffling). Under data parallelism every rank draws the same permutation (same generator seed) and
     takes batches rank, rank + world, ... so the global batch is world * batch_size disjoint captions."""
 
-    def __init__(self, subset: CaptionSubset, batch_size: int, shuffle: bool, generator: Optional[torch.Generator], rank: int, world: int):
+    def __init__(self, subset: CaptionSubset, batch_size: int, shuffle: bool, generator: Optional[torch.Generator], rank: int, world: int,
+                 pin_staging: bool = False):
         self.subset, self.batch_size, self.shuffle, self.generator, self.rank, self.world = subset, batch_size, shuffle, generator, rank, world
+        # Host-resident dataset: batches are gathered into one of two alternating page-locked staging sets, so the caller's
+        # `.to(device, non_blocking=True)` is a true asynchronous copy and the next gather does not overwrite a batch still in flight.
+        self._staging = None
+        ds = subset.dataset
+        if pin_staging and ds.device.type == "cpu":
+            pin = torch.cuda.is_available()
+            self._staging = [{k: torch.empty((batch_size,) + tuple(getattr(ds, k).shape[1:]), dtype=getattr(ds, k).dtype, pin_memory=pin)
+                              for k in ds.TENSOR_KEYS} for _ in range(2)]
+        self._flip = 0
 
     def __len__(self) -> int:
         return (len(self.subset) // self.batch_size) // self.world
@@ -79,7 +104,12 @@ class CaptionLoader:
             idx = idx[torch.randperm(idx.numel(), generator=self.generator)]
         n_batches = (idx.numel() // self.batch_size) // self.world * self.world   # drop_last, and the same count on every rank
         for b in range(self.rank, n_batches, self.world):
-            yield self.subset.dataset.batch(idx[b * self.batch_size:(b + 1) * self.batch_size])
+            rows = idx[b * self.batch_size:(b + 1) * self.batch_size]
+            if self._staging is not None and self.subset.dataset.image is None and self.subset.dataset.text is None:
+                self._flip ^= 1
+                yield self.subset.dataset.batch(rows, out=self._staging[self._flip])
+            else:
+                yield self.subset.dataset.batch(rows)
 
 
 def synthetic_dataset(n: int, max_length: int = 16, vocab: int = 30522, clip_dim: int = 512, seed: int = 0, device="cpu") -> DeviceCaptionDataset:

@@ -352,12 +352,8 @@ class DistilBertModel:
             self._check_exp_bound(float(self._exp_bound_host[0]))
             if not self.fused_softmax_grad:
                 return
-        if getattr(self, "_lm_head_max_norm", None) is None:
-            self._lm_head_max_norm = self.lm_head_weight.norm(dim=1).max()   # frozen (CLIP-DDPM.py:246-247): once
-        w, b = self._views["model.vocab_layer_norm.weight"], self._views["model.vocab_layer_norm.bias"]
-        cfg_w = max(float(self.hp["CLASSIFIER_FREE_WEIGHT"]), 0.0)
-        bound = (math.sqrt(self.hp["DIM"]) * w.abs().max() + b.norm()) * self._lm_head_max_norm * (1.0 + 2.0 * cfg_w)
-        self._exp_shift.copy_((bound - self.EXP_ARG_MAX).clamp(0.0, self.EXP_SHIFT_MAX).reshape(1))
+        bound = self._logit_bound()
+        self._exp_shift.copy_(self._shift_from_bound(bound).reshape(1))
         if self._exp_bound_host is None:    # first call (engine creation, off the step path): look at the bound right away
             self._exp_bound_host = torch.empty(1, pin_memory=True)
             self._exp_bound_event = torch.cuda.Event()
@@ -366,6 +362,18 @@ class DistilBertModel:
                 return
         self._exp_bound_host.copy_(bound.reshape(1), non_blocking=True)
         self._exp_bound_event.record(torch.cuda.current_stream(self.device))
+
+    def _logit_bound(self) -> torch.Tensor:
+        """(sqrt(D) max|w_LN| + |b_LN|) max_v |W_v| (1 + 2 CLASSIFIER_FREE_WEIGHT): 0-dim tensor, no host sync."""
+        if getattr(self, "_lm_head_max_norm", None) is None:
+            self._lm_head_max_norm = self.lm_head_weight.norm(dim=1).max()   # frozen (CLIP-DDPM.py:246-247): once
+        w, b = self._views["model.vocab_layer_norm.weight"], self._views["model.vocab_layer_norm.bias"]
+        cfg_w = max(float(self.hp.get("CLASSIFIER_FREE_WEIGHT", 0.0)), 0.0)
+        return (math.sqrt(self.hp["DIM"]) * w.abs().max() + b.norm()) * self._lm_head_max_norm * (1.0 + 2.0 * cfg_w)
+
+    @classmethod
+    def _shift_from_bound(cls, bound: torch.Tensor) -> torch.Tensor:
+        return (bound - cls.EXP_ARG_MAX).clamp(0.0, cls.EXP_SHIFT_MAX)
 
     def _check_exp_bound(self, bound: float):
         if bound <= self.EXP_ARG_MAX + self.EXP_SHIFT_MAX and math.isfinite(bound):

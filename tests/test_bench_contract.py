@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0", "--ref-samples", "3"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -21,6 +21,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    assert d["unit"] == d["e2e"]["unit"] == d["cpu_baseline"]["unit"] == "captions/s"   # the two arms must print the same unit string
+    assert d["warmup"] >= 2 and d["steps"] == 2 and "median" in d["sample"]
+    # the config block is a function of the command line only: our arm prints the same one (same_config for the driver)
+    import argparse, importlib.util
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": workload_config(args)') == 2
 
 
 def test_algorithmic_flop_constants_follow_the_survey_formula():

@@ -288,22 +288,26 @@ def test_factored_softmax_gradient_arithmetic():
 
 
 def test_exp_shift_bound_formula():
-    """DistilBertModel.refresh_exp_shift on a stub (CPU tensors): c = clamp((sqrt(D) max|w| + |b|) max_v |W_v| - 69, 0, 60), and the bound
-    really bounds the logits of LayerNorm outputs."""
+    """DistilBertModel._logit_bound / _shift_from_bound on a stub (CPU tensors): c = clamp((sqrt(D) max|w| + |b|) max_v |W_v| (1 + 2 w_cfg) - 69, 0, 60),
+    and the bound really bounds the logits of LayerNorm outputs (and of classifier-free-guidance mixes of two of them)."""
     from clipdlm.model import DistilBertModel
     import types
     torch.manual_seed(0)
     D, V = 768, 500
-    for scale, expect_zero in ((0.02, True), (0.2, False), (5.0, False)):
+    for scale, expect_zero, cfg_w in ((0.02, True, 0.0), (0.2, False, 0.0), (5.0, False, 0.0), (0.02, True, 0.5), (0.08, False, 0.5)):
         W = torch.randn(V, D) * scale
         w, b = 1 + 0.1 * torch.randn(D), 0.05 * torch.randn(D)
-        stub = types.SimpleNamespace(_exp_shift=torch.zeros(1), _lm_head_max_norm=None, lm_head_weight=W, hp={"DIM": D},
+        stub = types.SimpleNamespace(_lm_head_max_norm=None, lm_head_weight=W, hp={"DIM": D, "CLASSIFIER_FREE_WEIGHT": cfg_w},
                                      _views={"model.vocab_layer_norm.weight": w, "model.vocab_layer_norm.bias": b})
-        DistilBertModel.refresh_exp_shift(stub)
-        bound = float((D ** 0.5 * w.abs().max() + b.norm()) * W.norm(dim=1).max())
-        assert float(stub._exp_shift) == pytest.approx(min(max(bound - 69.0, 0.0), 60.0), rel=1e-5, abs=1e-6)
-        assert (float(stub._exp_shift) == 0.0) == expect_zero
+        got = DistilBertModel._logit_bound(stub)
+        bound = float((D ** 0.5 * w.abs().max() + b.norm()) * W.norm(dim=1).max()) * (1 + 2 * cfg_w)
+        assert float(got) == pytest.approx(bound, rel=1e-5)
+        c = float(DistilBertModel._shift_from_bound(got))
+        assert c == pytest.approx(min(max(bound - 69.0, 0.0), 60.0), rel=1e-5, abs=1e-6)
+        assert (c == 0.0) == expect_zero
         x = torch.nn.functional.layer_norm(torch.randn(64, D) * 3, (D,), w, b, eps=1e-12)
-        assert float((x @ W.t()).max()) <= bound
-    stub._exp_shift = None
+        y = torch.nn.functional.layer_norm(torch.randn(64, D) * 3, (D,), w, b, eps=1e-12)
+        mix = (1 + cfg_w) * x - cfg_w * y     # CLIP-DDPM.py:313-317
+        assert float((mix @ W.t()).max()) <= bound
+    stub = types.SimpleNamespace(_exp_shift=None, fused_softmax_grad=True)
     DistilBertModel.refresh_exp_shift(stub)   # option off: nothing to do
