@@ -11,7 +11,7 @@
 All compute runs in libclipdlm.so (hand-written CUDA, C-ABI in include/clipdlm.h); importing this package on a machine
 without the built library or without a B200 raises at first use — there is no CPU fallback.
 """
-from .hparams import LOSS_KIND, alpha_cumprod, default_hparams, learning_rates, model_name
+from .hparams import GLOBALS, LOSS_KIND, alpha_cumprod, default_hparams, learning_rates, model_name, set_globals
 from ._lib import ClipdlmError, EXPORTED_SYMBOLS, LIB_PATH
 
 
@@ -19,7 +19,7 @@ def __getattr__(name):  # torch-dependent modules load lazily so that `build` wo
     if name in ("DistilBertModel", "DistilBertConfig", "AdamW"):
         from . import model as _m
         return getattr(_m, name)
-    if name in ("diffuse_t", "generate_diffuse_pair", "loss", "train_func", "validate", "train", "sample"):
+    if name in ("diffuse_t", "generate_diffuse_pair", "loss", "train_func", "validate", "train", "sample", "bind"):
         from . import diffusion as _d
         return getattr(_d, name)
     if name in ("DeviceCaptionDataset", "CaptionSubset", "CaptionLoader", "synthetic_dataset"):

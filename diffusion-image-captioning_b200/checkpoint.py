@@ -155,6 +155,8 @@ def _export_class() -> type:
 def save_reference_pickle(sd: Dict[str, torch.Tensor], hp: dict, path) -> None:
     """Writes what the reference's `torch.save(model.cpu(), f"{MODEL_NAME}.pickle")` writes (CLIP-DDPM.py:551,560): a
     whole-module pickle whose class is recorded as `__main__.DistilBertModel`."""
+    if hasattr(sd, "state_dict"):   # a model (e.g. `model.cpu()`, which returns the module itself) instead of its state dict
+        sd = {k: v.detach().cpu() for k, v in sd.state_dict().items()}
     m = to_reference_module(sd, hp)
     cls = type(m)
     main = sys.modules["__main__"]

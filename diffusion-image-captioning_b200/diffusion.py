@@ -17,6 +17,7 @@ from typing import Dict, Iterable, Optional
 import torch
 
 from . import _lib as L
+from . import hparams as _hparams
 from .hparams import LOSS_KIND, alpha_cumprod, learning_rates
 from .model import AdamW, DistilBertModel
 
@@ -40,10 +41,12 @@ def _need_cuda(t: torch.Tensor):
         raise L.ClipdlmError("clipdlm operates on CUDA tensors only (no CPU fallback)")
 
 
-def diffuse_t(x: torch.Tensor, t: torch.Tensor, hp: dict, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q_sample, CLIP-DDPM.py:347-362. x [B, seq, C]; t [n] int64 -> [n*B, seq, C], row = s*B + b; ONE noise draw of
-    x.shape shared by the n samples (reference semantics)."""
+def diffuse_t(x: torch.Tensor, t: torch.Tensor, hp: Optional[dict] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q_sample, CLIP-DDPM.py:347-362, callable exactly as the reference's `diffuse_t(x, t)`. x [B, seq, C]; t [n] int64 (any shape with n
+    elements) -> [n*B, seq, C], row = s*B + b; ONE noise draw of x.shape shared by the n samples (reference semantics). hp=None reads the
+    active hyperparameters (hparams.GLOBALS - the reference's module globals); noise= pins the draw."""
     _need_cuda(x)
+    hp = _hparams.GLOBALS if hp is None else hp
     B, seq, ch = x.shape
     S = t.numel()
     if noise is None:
@@ -58,11 +61,29 @@ def diffuse_t(x: torch.Tensor, t: torch.Tensor, hp: dict, noise: Optional[torch.
     return out
 
 
-def generate_diffuse_pair(x_0, t, hp: dict, t_next=None):
-    """CLIP-DDPM.py:364-380."""
+def generate_diffuse_pair(x_0, t, t_next=None, hp: Optional[dict] = None):
+    """CLIP-DDPM.py:364-380, same positional form `generate_diffuse_pair(x_0, t, t_next)` (:467). x_0-prediction: (diffuse_t(x_0, t), x_0);
+    otherwise a second, independently drawn noisy target at t_next."""
+    if isinstance(t_next, dict):   # round-1 call form generate_diffuse_pair(x_0, t, hp, t_next)
+        t_next, hp = (hp if not isinstance(hp, dict) else None), t_next
+    hp = _hparams.GLOBALS if hp is None else hp
     if hp["X_0_PREDICTION"]:
         return diffuse_t(x_0, t, hp), x_0
     return diffuse_t(x_0, t, hp), diffuse_t(x_0, t_next, hp)
+
+
+def bind(hp: Optional[dict] = None, val_loader=None, **overrides):
+    """The reference's functions read module globals (hyperparameters :55-114, `val_loader` :221). `bind(hp, val_loader)` sets the active
+    ones and returns the five step functions + the two wrappers, callable exactly as CLIP-DDPM.py:347,364,382,458,488 call them:
+
+        F = clipdlm.bind(hp, val_loader)
+        x_t = F.diffuse_t(x_0, t); pair = F.generate_diffuse_pair(x_0, t, t_next)
+        l, x_t_loss, x_1_loss, prob_loss = F.train_func(model, trainer, x); val_x_t, val_x_1, val_prob = F.validate(model)
+    """
+    import types
+    _hparams.set_globals(hp, val_loader, **overrides)
+    return types.SimpleNamespace(hp=_hparams.GLOBALS, diffuse_t=diffuse_t, generate_diffuse_pair=generate_diffuse_pair, loss=loss,
+                                 train_func=train_func, validate=validate, train=train, sample=sample)
 
 
 def _next_seed() -> int:
@@ -309,8 +330,14 @@ def train_func(model: DistilBertModel, trainer: Optional[AdamW], x: dict, train:
     return l, x_t_loss, x_1_loss, prob_loss
 
 
-def validate(model: DistilBertModel, val_loader: Iterable[dict]):
-    """CLIP-DDPM.py:488-501: eval mode, no grad, mean of the three loss terms over the validation loader."""
+def validate(model: DistilBertModel, val_loader: Optional[Iterable[dict]] = None):
+    """CLIP-DDPM.py:488-501: eval mode, no grad, mean of the three loss terms over the validation loader. Callable as the reference's
+    `validate(model)`: the loader then is `model.val_loader` if set, else the one registered with `bind(hp, val_loader)` (the reference reads
+    the module global `val_loader`, :221,495)."""
+    if val_loader is None:
+        val_loader = getattr(model, "val_loader", None) or _hparams.ACTIVE["val_loader"]
+    if val_loader is None:
+        raise ValueError("validate(model): no validation loader - pass one, set model.val_loader, or register it with clipdlm.bind(hp, val_loader)")
     was_training = model.training
     model.eval()
     x_t_loss = x_1_loss = prob_loss = 0

@@ -34,6 +34,29 @@ def default_hparams(**overrides) -> dict:
     return hp
 
 
+# The reference keeps its hyperparameters (and `val_loader`) as MODULE GLOBALS that `diffuse_t(x, t)`, `generate_diffuse_pair(x_0, t, t_next)`,
+# `validate(model)` read implicitly (CLIP-DDPM.py:55-114,221,347,364,488). GLOBALS plays that role for the verbatim call forms: functions that
+# are not handed a model or an explicit `hp` read it. `bind()` (diffusion.py) sets it.
+GLOBALS: dict = default_hparams()
+ACTIVE = {"val_loader": None}
+
+
+def set_globals(hp: dict = None, val_loader=None, **overrides) -> dict:
+    """Make `hp` (+ overrides) the active hyperparameters / `val_loader` the active validation loader, like editing the constants at the
+    top of CLIP-DDPM.py. Returns the active dict (the same object the functions read)."""
+    if hp is not None:
+        GLOBALS.clear()
+        GLOBALS.update(hp)
+    if overrides:
+        unknown = set(overrides) - set(GLOBALS)
+        if unknown:
+            raise KeyError(f"unknown hyperparameters: {sorted(unknown)}")
+        GLOBALS.update(overrides)
+    if val_loader is not None:
+        ACTIVE["val_loader"] = val_loader
+    return GLOBALS
+
+
 def model_name(hp: dict) -> str:
     """MODEL_NAME f-string of CLIP-DDPM.py:116-118 (file stem of the reference's logs / pickles)."""
     sched = {"linspace": "linspace", "logspace": "logspace", "cosine": "cosine_annealing"}[hp["SCHEDULER"]]

@@ -96,8 +96,11 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
-class DistilBertModel:
-    """Drop-in for the reference's `class DistilBertModel(nn.Module)` (CLIP-DDPM.py:227-323).
+class DistilBertModel(torch.nn.Module):
+    """Drop-in for the reference's `class DistilBertModel(nn.Module)` (CLIP-DDPM.py:227-323). An `nn.Module` like the reference's: `model(x, ...)`,
+    `.train()/.eval()`, `.parameters()` (the reference overrides it to return a list, :258-269; so does this one - `nn.Parameter`s that alias the
+    flat fp32 buffer, `.grad` aliasing the flat gradient buffer), `torch.save(model.cpu(), path)` / `torch.load(path).to(device)` (:551,560,570:
+    the pickle holds the host state dict + hyperparameters; the device buffers are rebuilt on load).
 
     embedding / projection: the pretrained word-embedding and vocab-projector (modules with `.weight`, or tensors
     [VOCAB_SIZE, DIM]); frozen copies are taken (:245-247). None => random N(0, 0.02) tied table (what
@@ -110,9 +113,11 @@ class DistilBertModel:
     def __init__(self, embedding=None, projection=None, config=None, hp: Optional[dict] = None, precision: str = "bf16",
                  device="cuda", seed: Optional[int] = None, chunk_rows: int = 8192, fused_softmax_grad: Optional[bool] = None,
                  gelu_deriv_store: Optional[bool] = None):
+        super().__init__()
         lib = L.load()
         if not torch.cuda.is_available():
             raise L.ClipdlmError("clipdlm needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._ctor = dict(precision=precision, chunk_rows=int(chunk_rows), fused_softmax_grad=fused_softmax_grad, gelu_deriv_store=gelu_deriv_store)
         self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
         with torch.cuda.device(self.device):
             if lib.clipdlm_device_ok() != 1:
@@ -238,6 +243,12 @@ class DistilBertModel:
                 self._gviews[name] = self.grad[o:o + cnt].view(stored)[sl]
             for k, v, g in seg:
                 self._views[k], self._gviews[k] = v, g
+        # what parameters() / named_parameters() hand out: nn.Parameters aliasing the views, .grad aliasing the gradient views
+        self._params: Dict[str, torch.nn.Parameter] = {}
+        for k, v in self._views.items():
+            prm = torch.nn.Parameter(v, requires_grad=False)   # no autograd on this path: the backward is hand-written
+            prm.grad = self._gviews[k]
+            self._params[k] = prm
 
     def _rebind_buffers(self, flat, grad, shadow_hi, shadow_lo):
         """Move the flat parameter / gradient / shadow buffers into caller-provided storage of the same size (symmetric memory for
@@ -284,18 +295,22 @@ class DistilBertModel:
             else:
                 v.copy_(torch.randn(v.shape, generator=g) * 0.02)
 
-    def parameters(self) -> ParamList:
-        out = ParamList(self._views.values())
+    def parameters(self, recurse: bool = True) -> ParamList:
+        out = ParamList(self._params.values())
         out.owner = self
         return out
 
-    def named_parameters(self):
-        return list(self._views.items())
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        return [(prefix + k, v) for k, v in self._params.items()]
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.grad.zero_()
+        self._grads_dirty = False
 
     def named_grads(self) -> Dict[str, torch.Tensor]:
         return dict(self._gviews)
 
-    def state_dict(self) -> Dict[str, torch.Tensor]:
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False) -> Dict[str, torch.Tensor]:
         """Reference-compatible names: trainable tensors + embedding.weight + lm_head.{weight,bias}."""
         sd = {k: v.detach().clone() for k, v in self._views.items()}
         if self.hp["TRAIN_EMBEDDING"]:  # embedding.weight / lm_head.weight are trainable views already; no lm_head bias (:239)
@@ -305,20 +320,32 @@ class DistilBertModel:
         sd["lm_head.bias"] = torch.zeros(self.hp["VOCAB_SIZE"], device=self.device)
         return sd
 
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
-        missing = [k for k in self._views if k not in sd]
-        if strict and missing:
-            raise KeyError(f"missing keys: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True, assign: bool = False):
+        """nn.Module semantics: strict => every key of state_dict() must be present (lm_head.* may be absent: tied to embedding.weight,
+        bias 0) and no unknown key; shapes are checked before anything is copied."""
+        hp = self.hp
+        te = hp["TRAIN_EMBEDDING"]
+        frozen = {} if te else {"embedding.weight": self.embedding_weight, "lm_head.weight": self.lm_head_weight}
+        optional = set() if te else {"lm_head.weight", "lm_head.bias"}
+        known = set(self._views) | set(frozen) | optional
+        missing = [k for k in list(self._views) + list(frozen) if k not in sd and k not in optional]
+        unexpected = [k for k in sd if k not in known]
+        if strict and (missing or unexpected):
+            raise KeyError(f"load_state_dict: missing keys {missing[:4]}{'...' if len(missing) > 4 else ''}, "
+                           f"unexpected keys {unexpected[:4]}{'...' if len(unexpected) > 4 else ''}")
+        for k, v in list(self._views.items()) + list(frozen.items()):
+            if k in sd and tuple(sd[k].shape) != tuple(v.shape):
+                raise ValueError(f"load_state_dict: {k} has shape {tuple(sd[k].shape)}, expected {tuple(v.shape)}")
         for k, v in self._views.items():
             if k in sd:
-                v.copy_(sd[k].to(self.device, torch.float32))
-        if self.hp["TRAIN_EMBEDDING"]:
+                v.copy_(sd[k].detach().to(self.device, torch.float32))
+        if te:
             self.sync_shadow()
             return
         if "embedding.weight" in sd:
-            self.embedding_weight.copy_(sd["embedding.weight"].to(self.device, torch.float32))
+            self.embedding_weight.copy_(sd["embedding.weight"].detach().to(self.device, torch.float32))
         if "lm_head.weight" in sd:
-            self.lm_head_weight.copy_(sd["lm_head.weight"].to(self.device, torch.float32))
+            self.lm_head_weight.copy_(sd["lm_head.weight"].detach().to(self.device, torch.float32))
         elif "embedding.weight" in sd:
             self.lm_head_weight.copy_(self.embedding_weight)
         self.sync_shadow()
@@ -393,17 +420,38 @@ class DistilBertModel:
     def eval(self):
         return self.train(False)
 
-    def to(self, device):
-        if torch.device(device).type != "cuda":
-            raise L.ClipdlmError("clipdlm models live on the GPU; use state_dict() to move weights to the host")
+    def _apply(self, fn, recurse=True):
+        return self   # the module owns device buffers laid out by libclipdlm: dtype / device casts do not apply
+
+    def to(self, *args, **kwargs):
+        """`model.to(device)` (CLIP-DDPM.py:506,552,561,572). The compute buffers never leave the GPU; a CUDA target returns self, a CPU target is
+        what `.cpu()` does."""
+        dev = kwargs.get("device", args[0] if args else None)
+        if isinstance(dev, (str, torch.device)) and torch.device(dev).type == "cpu":
+            return self.cpu()
+        return self
+
+    def cuda(self, device=None):
         return self
 
     def cpu(self):
-        """The reference pickles `model.cpu()` (CLIP-DDPM.py:551,560); here the portable form is the state dict on the host."""
-        return {k: v.cpu() for k, v in self.state_dict().items()}
+        """The reference pickles `model.cpu()` and moves the model back with `.to(device)` (CLIP-DDPM.py:551-552,560-561). Pickling this module
+        always serialises host copies (`__getstate__`), so `.cpu()` has nothing to move: it returns self, `torch.save(model.cpu(), path)` writes
+        a file `torch.load(path).to(device)` turns back into a working model, and training continues on the same device buffers."""
+        return self
 
-    def __call__(self, *a, **kw):
-        return self.forward(*a, **kw)
+    def __getstate__(self):
+        return {"clipdlm_module": 1, "hp": dict(self.hp), "ctor": dict(self._ctor), "training": self.training,
+                "state_dict": {k: v.cpu() for k, v in self.state_dict().items()}}
+
+    def __setstate__(self, st):
+        """Unpickling (torch.load of a whole-module pickle, CLIP-DDPM.py:506,570) rebuilds the device buffers on the current CUDA device."""
+        sd = st["state_dict"]
+        emb = None if st["hp"]["TRAIN_EMBEDDING"] else sd["embedding.weight"]
+        proj = None if st["hp"]["TRAIN_EMBEDDING"] else sd.get("lm_head.weight", emb)
+        DistilBertModel.__init__(self, emb, proj, None, hp=st["hp"], **st["ctor"])
+        self.load_state_dict(sd)
+        self.train(st.get("training", True))
 
     # ---------------------------------------------------------------------------------------------------------- engine plumbing
     def _stream(self):
@@ -514,18 +562,17 @@ class DistilBertModel:
         assert tuple(mask.shape) == (R, ML)
         assert tuple(concat_mask.shape) == (R, 2)
         guidance = concat_mask[:, 1] == 1  # :290
-        n_guided = int(guidance.sum().item())
         w = hp["CLASSIFIER_FREE_WEIGHT"]
         te = hp["TRAIN_EMBEDDING"]
         if te:  # :292-293
             from . import train_embedding as TE
             x = TE.in_proj(self, self._f32(x)).clone()
         x_out = self._encode(x, image_clip[:, 0], text_clip[:, 0], mask, guided=False)
-        mixed = w > 0 and n_guided > 0
-        if mixed:  # :313-317
-            idx = guidance.nonzero().flatten()
-            guided_out = self._encode(x[idx], image_clip[idx, 0], text_clip[idx, 0], mask[idx], guided=True)
-            x_out[idx] = (1 + w) * guided_out - w * x_out[idx]
+        mixed = w > 0
+        if mixed:  # :313-317. The reference gathers the guided rows (a host sync on the row count); here the guided pass runs over every row
+            # and the mix is selected per row on the device - no .item(), same values on the guided rows, untouched elsewhere.
+            guided_out = self._encode(x, image_clip[:, 0], text_clip[:, 0], mask, guided=True)
+            x_out = torch.where(guidance.to(self.device)[:, None, None], (1 + w) * guided_out - w * x_out, x_out)
         if te:  # :319-320,323
             y = TE.out_proj(self, x_out).clone()
             return TE.logits(self, y), y
