@@ -71,7 +71,23 @@ def _normalise(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
-def load_reference_checkpoint(path_or_obj, map_location="cpu") -> Dict[str, torch.Tensor]:
+def _read(path, map_location="cpu", allow_pickle: bool = False):
+    """torch.load with weights_only=True first: plain state dicts and this package's own resume files hold tensors and plain containers only
+    and never need the unpickler. Only the reference's WHOLE-MODULE pickles do (arbitrary code runs on load, as with the reference's own
+    `torch.load`, CLIP-DDPM.py:506,570) - that path is taken only with allow_pickle=True, i.e. for files the caller trusts."""
+    try:
+        return torch.load(path, map_location=map_location, weights_only=True)
+    except Exception as ex:
+        if not allow_pickle:
+            raise pickle.UnpicklingError(
+                f"{path}: not a weights-only file ({type(ex).__name__}). The reference's whole-module pickles execute code on load: "
+                "pass allow_pickle=True for a file you trust") from ex
+        if hasattr(path, "seek"):
+            path.seek(0)
+    return torch.load(path, map_location=map_location, pickle_module=_RemapPickle, weights_only=False)
+
+
+def load_reference_checkpoint(path_or_obj, map_location="cpu", allow_pickle: bool = False) -> Dict[str, torch.Tensor]:
     """Reads a checkpoint and returns a CPU state dict under the reference's names:
     `model.distilbert...`, `model.vocab_transform.*`, `model.vocab_layer_norm.*`, `image_linear.*`, `text_linear.*`,
     `segment_embedding.weight` (concat fusion), `embedding.weight`, `lm_head.weight`, `lm_head.bias`
@@ -81,7 +97,7 @@ def load_reference_checkpoint(path_or_obj, map_location="cpu") -> Dict[str, torc
     (b) a plain `state_dict` file, (c) a `save_checkpoint` file of this package; or the already-loaded object of any of those."""
     obj = path_or_obj
     if not isinstance(obj, (dict, nn.Module)):
-        obj = torch.load(path_or_obj, map_location=map_location, pickle_module=_RemapPickle, weights_only=False)
+        obj = _read(path_or_obj, map_location, allow_pickle)
     if isinstance(obj, nn.Module):
         return _normalise(obj.state_dict())
     if isinstance(obj, dict) and obj.get("format") == FORMAT:
@@ -173,21 +189,31 @@ def save_reference_pickle(sd: Dict[str, torch.Tensor], hp: dict, path) -> None:
 
 
 def save_checkpoint(model, trainer, path, epoch: int = 0, extra: Optional[dict] = None) -> None:
-    """Resume file of this package: reference-named model state dict, AdamW moments / step / param_groups, hyperparameters."""
+    """Resume file of this package: reference-named model state dict, AdamW moments / step / param_groups, hyperparameters. The moments are
+    always stored FULL-size with their `slice` and `n_params`. Under the fused data-parallel step (each rank holds 1/N of the moments) this
+    is a collective: every rank calls it, the slices are gathered, rank 0 writes the file."""
     obj = dict(format=FORMAT, model={k: v.detach().cpu() for k, v in model.state_dict().items()}, hp=dict(model.hp), epoch=int(epoch),
                precision=model.precision, extra=extra or {})
+    writer = True
     if trainer is not None:
-        st = trainer.state_dict()
+        st = trainer.full_state_dict() if hasattr(trainer, "full_state_dict") else trainer.state_dict()
         obj["optimizer"] = dict(m=st["m"].cpu(), v=st["v"].cpu(), t=st["t"], param_groups=st["param_groups"])
-    torch.save(obj, path)
+        for k in ("slice", "n_params"):
+            if k in st:
+                obj["optimizer"][k] = st[k]
+        if getattr(model, "dp_fused", None) is not None:
+            import torch.distributed as dist
+            writer = dist.get_rank(model.dp_group) == 0
+    if writer:
+        torch.save(obj, path)
 
 
-def load_checkpoint(model, path_or_obj, trainer=None, strict: bool = True) -> Tuple[int, dict]:
+def load_checkpoint(model, path_or_obj, trainer=None, strict: bool = True, allow_pickle: bool = False) -> Tuple[int, dict]:
     """Loads any supported checkpoint into `model` (and, for this package's own files, the optimizer state into `trainer`).
-    Returns (epoch, extra)."""
+    Returns (epoch, extra). allow_pickle=True is needed (only) for the reference's whole-module pickles, see _read()."""
     obj = path_or_obj
     if not isinstance(obj, (dict, nn.Module)):
-        obj = torch.load(path_or_obj, map_location="cpu", pickle_module=_RemapPickle, weights_only=False)
+        obj = _read(path_or_obj, "cpu", allow_pickle)
     model.load_state_dict(load_reference_checkpoint(obj), strict=strict)
     if isinstance(obj, dict) and obj.get("format") == FORMAT:
         if trainer is not None and "optimizer" in obj:

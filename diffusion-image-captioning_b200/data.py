@@ -29,6 +29,37 @@ class DeviceCaptionDataset:
         self.text = list(text) if text is not None else None
         self.device = self.input_ids.device
 
+    @classmethod
+    def from_captions(cls, captions: Sequence, images: Optional[Sequence[str]], image_clip: torch.Tensor, text_clip: torch.Tensor, tokenizer,
+                      max_length: int = 16, device=None, chunk: int = 8192) -> "DeviceCaptionDataset":
+        """Tokeniser adapter: what `FlickrCLIPDataset.__getitem__` (CLIP-DDPM.py:179-197) computes per item on every access, done ONCE for
+        the whole caption list.
+
+        * HF tokenizer (anything callable the way the reference calls `PreTrainedTokenizer`, :183):
+          `tokenizer(text=..., return_tensors="pt", padding="max_length", truncation=True, max_length=MAX_LENGTH)` -> input_ids /
+          attention_mask [N, MAX_LENGTH] ([CLS] ... [SEP] [PAD]...), batched `chunk` captions per call.
+        * a vocabulary dict (the reference's `DictTokenizer` branch, :185-189; TRAIN_EMBEDDING): ids = [0] + [vocab.get(x, vocab['UNK']) for x in
+          caption[:MAX_LENGTH-2]] + [1], padded with vocab['UNK'], mask 1 on the ids and 0 on the padding. `caption[:MAX_LENGTH-2]` is taken
+          as the reference takes it: characters of a string, items of a list."""
+        n = len(captions)
+        vocab = tokenizer if isinstance(tokenizer, dict) else getattr(tokenizer, "dictionary", None)
+        if isinstance(vocab, dict):
+            unk = vocab["UNK"]
+            ids = torch.full((n, max_length), unk, dtype=torch.int64)
+            mask = torch.zeros((n, max_length), dtype=torch.int64)
+            for i, cap in enumerate(captions):
+                row = [0] + [vocab.get(x, unk) for x in cap[:max_length - 2]] + [1]
+                ids[i, :len(row)] = torch.tensor(row, dtype=torch.int64)
+                mask[i, :len(row)] = 1
+        else:
+            parts_i, parts_m = [], []
+            for lo in range(0, n, chunk):
+                tok = tokenizer(text=[str(c) for c in captions[lo:lo + chunk]], return_tensors="pt", padding="max_length", truncation=True,
+                                max_length=max_length)
+                parts_i.append(tok["input_ids"].to(torch.int64)); parts_m.append(tok["attention_mask"].to(torch.int64))
+            ids, mask = torch.cat(parts_i), torch.cat(parts_m)
+        return cls(image_clip, text_clip, ids, mask, image=images, text=[str(c) for c in captions], device=device)
+
     def __len__(self) -> int:
         return int(self.input_ids.shape[0])
 

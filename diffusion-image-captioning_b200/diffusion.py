@@ -361,6 +361,16 @@ def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dic
     early_stopped = False
     model.train()
     history = []
+    dp = getattr(model, "dp_group", None) is not None
+
+    def _global_mean(*xs):
+        """Under data parallelism every rank must take the same decisions (rounding weight, early stop): mean of the rank-local values."""
+        if not dp:
+            return xs
+        v = torch.stack([torch.as_tensor(x, dtype=torch.float32, device=model.device) for x in xs])
+        torch.distributed.all_reduce(v, group=model.dp_group)
+        return tuple(v / model.dp_world)
+
     for epoch in range(hp["EPOCH_NUM"]):
         acc_x_t = acc_x_1 = acc_prob = acc_l = 0
         if not hp["END_LEARNING_RATE"] == hp["LEARNING_RATE"]:
@@ -371,15 +381,17 @@ def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dic
             l, x_t_loss, x_1_loss, prob_loss = train_func(model, trainer, x)
             acc_x_t, acc_x_1, acc_prob, acc_l = acc_x_t + x_t_loss, acc_x_1 + x_1_loss, acc_prob + prob_loss, acc_l + l
             n_batches += 1
-            if hp["DYNAMIC_ROUNDING_WEIGHT"] > 0:
-                model.hp["ROUNDING_WEIGHT"] = float(((acc_x_t + acc_x_1) / acc_prob).item() * hp["DYNAMIC_ROUNDING_WEIGHT"])
+            if hp["DYNAMIC_ROUNDING_WEIGHT"] > 0:  # :535-536 (the kernels take the weight by value: one scalar read-back per step in this mode)
+                g_x_t, g_x_1, g_prob = _global_mean(acc_x_t, acc_x_1, acc_prob)
+                model.hp["ROUNDING_WEIGHT"] = float(((g_x_t + g_x_1) / g_prob).item() * hp["DYNAMIC_ROUNDING_WEIGHT"])
             if hp["DEBUG"]:
                 break
         # the reference divides by len(train_loader) (:547,554), also when DEBUG cut the epoch after one batch
         n_batches = max(len(train_loader) if hasattr(train_loader, "__len__") else n_batches, 1)
+        acc_x_t, acc_x_1, acc_prob, acc_l = _global_mean(acc_x_t, acc_x_1, acc_prob, acc_l)
         rec = dict(epoch=epoch, x_t_loss=acc_x_t / n_batches, x_1_loss=acc_x_1 / n_batches, prob_loss=acc_prob / n_batches, lr=trainer.param_groups[0]["lr"])
         if val_loader is not None:
-            val_x_t, val_x_1, val_prob = validate(model, val_loader)
+            val_x_t, val_x_1, val_prob = _global_mean(*validate(model, val_loader))
             rec.update(val_x_t=val_x_t, val_x_1=val_x_1, val_prob=val_prob)
             if val_x_t + val_x_1 + val_prob > hp["EARLY_STOP_RATIO"] * acc_l / n_batches:
                 if not early_stopped:

@@ -30,7 +30,9 @@ def _ngrams(tokens: Sequence[str], n: int) -> Counter:
 
 def bleu_score(candidates: Sequence[str], references: Sequence[Sequence[str]], n_gram: int = 4) -> float:
     """Corpus-level BLEU as torchmetrics.functional.bleu_score computes it: clipped n-gram counts summed over the corpus, geometric
-    mean of the n precisions (0 if any is 0), brevity penalty with the closest reference length (ties -> shorter)."""
+    mean of the n precisions (0 if any is 0), brevity penalty with the closest reference length - ties go to the FIRST such reference in
+    list order, as torchmetrics' `target_len_diff.index(min(target_len_diff))` does. UNPINNED against torchmetrics itself (absent from this
+    image, no network): checked against hand-computed answers and the definition only (tests/test_host_cpu.py)."""
     assert len(candidates) == len(references)
     num = [0] * n_gram
     den = [0] * n_gram
@@ -39,7 +41,9 @@ def bleu_score(candidates: Sequence[str], references: Sequence[Sequence[str]], n
         c = cand.split()
         rs = [r.split() for r in refs]
         c_len += len(c)
-        r_len += min((abs(len(r) - len(c)), len(r)) for r in rs)[1] if rs else 0
+        if rs:
+            diffs = [abs(len(r) - len(c)) for r in rs]
+            r_len += len(rs[diffs.index(min(diffs))])
         for n in range(1, n_gram + 1):
             cc = _ngrams(c, n)
             best: Counter = Counter()

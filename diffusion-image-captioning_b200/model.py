@@ -682,8 +682,50 @@ class AdamW:
         m._grads_dirty = False  # the kernel zeroed them
 
     def state_dict(self):
-        return {"m": self.m.clone(), "v": self.v.clone(), "t": self.t, "param_groups": [dict(g) for g in self.param_groups], "slice": self._slice}
+        """This rank's optimizer state. Under the fused data-parallel step the moments cover only `slice` (ZeRO-1): use full_state_dict()
+        (collective) for a file every rank can resume from."""
+        n = self._slice[1] - self._slice[0]
+        return {"m": self.m[:n].clone(), "v": self.v[:n].clone(), "t": self.t, "param_groups": [dict(g) for g in self.param_groups],
+                "slice": tuple(self._slice), "n_params": self.model.n_params}
+
+    def full_state_dict(self):
+        """Optimizer state with FULL-size moments. Single device / NCCL exchange: same as state_dict(). Fused data-parallel step: COLLECTIVE
+        (every rank of the model's group must call it) - each rank's slice of m / v is broadcast into a full-size tensor."""
+        sd = self.state_dict()
+        mdl = self.model
+        if self._slice == (0, mdl.n_params):
+            return sd
+        import torch.distributed as dist
+        world = dist.get_world_size(mdl.dp_group)
+        m, v = torch.zeros(mdl.n_params, device=mdl.device), torch.zeros(mdl.n_params, device=mdl.device)
+        b, e = C.c_int64(), C.c_int64()
+        for r in range(world):
+            L.check(L.load().clipdlm_dp_slice(mdl.n_params, r, world, C.byref(b), C.byref(e)))
+            lo, hi = int(b.value), int(e.value)
+            if r == dist.get_rank(mdl.dp_group):
+                assert (lo, hi) == tuple(self._slice)
+                m[lo:hi].copy_(self.m[:hi - lo]); v[lo:hi].copy_(self.v[:hi - lo])
+            if hi > lo:
+                dist.broadcast(m[lo:hi], src=dist.get_global_rank(mdl.dp_group, r), group=mdl.dp_group)
+                dist.broadcast(v[lo:hi], src=dist.get_global_rank(mdl.dp_group, r), group=mdl.dp_group)
+        sd.update(m=m, v=v, slice=(0, mdl.n_params))
+        return sd
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+        """Accepts full-size moments (any rank layout: this rank's slice is cut out) or a state saved for exactly this rank's slice; anything
+        else - e.g. rank 0's slice file loaded on rank 1 - raises instead of silently applying moments to the wrong parameter range."""
+        n_params = self.model.n_params
+        lo, hi = self._slice
+        m, v = sd["m"], sd["v"]
+        src = tuple(sd.get("slice", (0, m.numel())))
+        if sd.get("n_params", n_params) != n_params:
+            raise ValueError(f"optimizer state was saved for {sd['n_params']} parameters, this model has {n_params}")
+        if src == (0, n_params) and m.numel() >= n_params:
+            m, v = m[lo:hi], v[lo:hi]
+        elif src != (lo, hi):
+            raise ValueError(f"optimizer state covers parameter slice {src}, this rank owns {(lo, hi)}: save with full_state_dict() "
+                             "(save_checkpoint does) to resume under a different rank layout")
+        if m.numel() < hi - lo or v.numel() < hi - lo:
+            raise ValueError(f"optimizer moments hold {m.numel()} elements, slice {(lo, hi)} needs {hi - lo}")
+        self.m[:hi - lo].copy_(m[:hi - lo]); self.v[:hi - lo].copy_(v[:hi - lo]); self.t = int(sd["t"])
         self.param_groups = [dict(g) for g in sd["param_groups"]]

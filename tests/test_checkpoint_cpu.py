@@ -80,7 +80,9 @@ def test_reference_whole_module_pickle_loads_without_the_reference_script(tmp_pa
     with _as_main(_RefLike):
         torch.save(ref.cpu(), path)  # CLIP-DDPM.py:560
     with _as_main(None):  # a process that does not define the reference's class
-        sd = ck.load_reference_checkpoint(str(path))
+        with pytest.raises(Exception, match="allow_pickle"):
+            ck.load_reference_checkpoint(str(path))          # whole-module pickles run code on load: only on request
+        sd = ck.load_reference_checkpoint(str(path), allow_pickle=True)
     want = {k: v for k, v in ref.state_dict().items() if not k.endswith("position_ids")}
     assert set(sd) == set(want)
     for k in want:
@@ -178,7 +180,7 @@ def test_resume_checkpoint_round_trip(tmp_path):
     path = tmp_path / "resume.pt"
     ck.save_checkpoint(a, ta, str(path), epoch=3, extra=dict(note="x"))
     b, tb = _FakeModel({k: torch.zeros_like(v) for k, v in sd.items()}, hp), _FakeTrainer(11)
-    epoch, extra = ck.load_checkpoint(b, str(path), tb)
+    epoch, extra = ck.load_checkpoint(b, str(path), tb)     # this package's own file: weights_only=True suffices, no unpickler involved
     assert epoch == 3 and extra == dict(note="x")
     assert all(torch.equal(b.sd[k], sd[k]) for k in sd)
     assert torch.equal(tb.m, ta.m) and torch.equal(tb.v, ta.v) and tb.t == 7 and tb.param_groups[0]["lr"] == 3e-5
@@ -197,7 +199,7 @@ def test_real_reference_class_pickle(tmp_path):
     with _as_main(cls):
         torch.save(model.cpu(), str(path))
     with _as_main(None):
-        sd = ck.load_reference_checkpoint(str(path))
+        sd = ck.load_reference_checkpoint(str(path), allow_pickle=True)
         out = tmp_path / "ours.pickle"
         hp2 = dict(hp, MAX_POSITION=512)
         ck.save_reference_pickle(sd, hp2, str(out))
@@ -213,3 +215,33 @@ def test_real_reference_class_pickle(tmp_path):
     with torch.no_grad():
         a, b = model(x, img, txt, mask, cm), back(x, img, txt, mask, cm)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_adamw_state_refuses_a_foreign_slice():
+    """under the fused data-parallel step a rank holds the Adam moments of its parameter slice only. Loading rank 0's slice
+    on rank 1 must raise (equal slice lengths made it silent before); full-size states are cut to the rank's own slice."""
+    from clipdlm.model import AdamW
+    import types
+    n = 64
+    def trainer(lo, hi):
+        tr = AdamW.__new__(AdamW)
+        tr.model = types.SimpleNamespace(n_params=n, device="cpu")
+        tr._slice, tr.m, tr.v, tr.t, tr.param_groups = (lo, hi), torch.zeros(hi - lo), torch.zeros(hi - lo), 0, [dict(lr=1e-4)]
+        return tr
+    r0, r1 = trainer(0, 32), trainer(32, 64)
+    r0.m += 1.0; r0.v += 2.0; r0.t = 5
+    sd0 = r0.state_dict()
+    assert sd0["slice"] == (0, 32) and sd0["n_params"] == n
+    with pytest.raises(ValueError, match="slice"):
+        r1.load_state_dict(sd0)
+    r0b = trainer(0, 32); r0b.load_state_dict(sd0)
+    assert torch.equal(r0b.m, r0.m) and r0b.t == 5
+    full = dict(m=torch.arange(n, dtype=torch.float32), v=torch.arange(n, dtype=torch.float32) * 2, t=9, param_groups=[dict(lr=3e-5)], slice=(0, n), n_params=n)
+    r1.load_state_dict(full)
+    assert torch.equal(r1.m, torch.arange(32, 64, dtype=torch.float32)) and torch.equal(r1.v, 2 * torch.arange(32, 64, dtype=torch.float32)) and r1.t == 9
+    single = trainer(0, n); single.load_state_dict(full)
+    assert torch.equal(single.m, full["m"])
+    with pytest.raises(ValueError, match="parameters"):
+        r1.load_state_dict(dict(full, n_params=n + 1))
+    legacy = dict(m=torch.ones(n), v=torch.ones(n), t=1, param_groups=[dict(lr=1e-4)])   # round-1 files: no slice key, full size
+    single.load_state_dict(legacy); r1.load_state_dict(legacy)

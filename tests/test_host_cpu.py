@@ -311,3 +311,43 @@ def test_exp_shift_bound_formula():
         assert float((mix @ W.t()).max()) <= bound
     stub = types.SimpleNamespace(_exp_shift=None, fused_softmax_grad=True)
     DistilBertModel.refresh_exp_shift(stub)   # option off: nothing to do
+
+
+def test_tokenizer_adapter_matches_per_item_tokenisation(tmp_path):
+    """N2 (CLIP-DDPM.py:179-197): DeviceCaptionDataset.from_captions tokenises the caption list once; every row must equal what the reference's
+    __getitem__ computes for that item - both branches: an HF PreTrainedTokenizer (a DistilBertTokenizer over a small local vocabulary) and the
+    DictTokenizer / vocab_dict branch (characters of the caption string, [0] ... [1], UNK padding)."""
+    import clipdlm
+    from transformers import DistilBertTokenizer
+    words = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "dog", "runs", "on", "the", "grass", "two", "men", "play", "##ing", "ball", ".", ","]
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(words))
+    tok = DistilBertTokenizer(vocab_file=str(vf), do_lower_case=True)
+    caps = ["A dog runs on the grass .", "Two men playing ball , the dog runs on the grass , a dog runs on the grass , two men", "unknownword dog", ""]
+    n = len(caps)
+    img, txt = torch.randn(n, 512), torch.randn(n, 512)
+    ds = clipdlm.DeviceCaptionDataset.from_captions(caps, [f"i{k}.jpg" for k in range(n)], img, txt, tok, max_length=16, chunk=3)
+    assert tuple(ds.input_ids.shape) == (n, 16) and ds.input_ids.dtype == torch.int64
+    for i, c in enumerate(caps):
+        t = tok(text=c, return_tensors="pt", padding="max_length", truncation=True, max_length=16)   # :183
+        assert torch.equal(ds.input_ids[i], t["input_ids"].squeeze()) and torch.equal(ds.attention_mask[i], t["attention_mask"].squeeze()), i
+    b = ds.batch(torch.tensor([1, 0]))
+    assert b["text"] == [caps[1], caps[0]] and b["image"] == ["i1.jpg", "i0.jpg"] and int(b["input_ids"][1, 0]) == words.index("[CLS]")
+    vocab = {"UNK": 2, **{ch: 3 + k for k, ch in enumerate("abcdefghijklmnopqrstuvwxyz ")}}
+    ds2 = clipdlm.DeviceCaptionDataset.from_captions(caps, None, img, txt, vocab, max_length=16)
+    for i, c in enumerate(caps):
+        ids = [0] + [vocab.get(x, vocab["UNK"]) for x in c[:16 - 2]] + [1]                            # :185-189
+        pad = max(0, 16 - len(ids))
+        assert ds2.input_ids[i].tolist() == ids + [vocab["UNK"]] * pad and ds2.attention_mask[i].tolist() == [1] * len(ids) + [0] * pad
+
+
+def test_pinned_staging_loader_yields_the_same_batches():
+    import clipdlm
+    ds = clipdlm.synthetic_dataset(40, seed=2)
+    ds.image = ds.text = None
+    sub = clipdlm.CaptionSubset(ds, torch.arange(40))
+    a = list(sub.loader(8, shuffle=True, generator=torch.Generator().manual_seed(1)))
+    b = [{k: v.clone() for k, v in x.items()} for x in sub.loader(8, shuffle=True, generator=torch.Generator().manual_seed(1), pin_staging=True)]
+    assert len(a) == len(b) == 5
+    for x, y in zip(a, b):
+        assert all(torch.equal(x[k], y[k]) for k in x)
