@@ -178,7 +178,8 @@ def test_logit_bound_out_of_range_falls_back_to_the_inplace_path():
         else:
             losses = pkg.train_func(model, trainer, batch, t=t, noise_t=n_t, noise_1=n_1, dropout_seed=1)
         res[flag] = ([x.item() for x in losses], snap["g"].double())
-    assert res[False][0] == res[True][0] and torch.equal(res[False][1], res[True][1])   # the same kernels ran
+    assert res[False][0] == res[True][0]                                      # the same kernels ran: losses bit-equal,
+    assert rel(res[True][1], res[False][1]) < 1e-4                              # gradients equal up to the fp32 atomics of the split-K weight gradients
     # classifier-free guidance widens the bound: x 4 alone stays inside (bound ~ 66 < 69, c = 0), with w = 0.25 (factor 1.5) c > 0
     hp2 = dict(hp, CLASSIFIER_FREE_WEIGHT=0.25)
     m_plain = pkg.DistilBertModel(E, E * 4.0, None, hp=hp, precision="bf16", seed=0, fused_softmax_grad=True)
