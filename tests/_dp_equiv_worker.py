@@ -51,17 +51,25 @@ def main():
             assert abs(a - b) <= 2e-5 * abs(b), (step, a, b)
     torch.cuda.synchronize()
     ps, pd = dict(single.named_parameters()), dict(dp.named_parameters())
+    worst_u = 0.0
     for k in ps:
         d = float((ps[k] - pd[k]).abs().max())
         assert d <= 2 * 1e-3 * 3 + 1e-6, (k, d)   # bounded by Adam's step size x steps (zero-gradient tensors move on rounding noise)
-        if "k_lin.bias" not in k:
-            e = float((ps[k].double() - pd[k].double()).norm() / ps[k].double().norm().clamp_min(1e-6))
-            worst = max(worst, e)
+        if "k_lin.bias" in k or k.startswith("text_linear"):
+            continue                               # analytically-zero gradients: Adam normalises pure rounding noise there
+        p0 = P[k].to(dev).double()
+        us, ud = ps[k].double() - p0, pd[k].double() - p0
+        e = float((ps[k].double() - pd[k].double()).norm() / ps[k].double().norm().clamp_min(1e-6))
+        eu = float((us - ud).norm() / us.norm().clamp_min(1e-12))     # relative to the UPDATE (biases start at 0: their norm is the update)
+        worst, worst_u = max(worst, e), max(worst_u, eu)
+        tol_u = 1e-2 if precision == "bf16x3" else 5e-2               # Adam's m / sqrt(v) amplifies summation-order noise on small-gradient elements
+        assert eu < tol_u, (k, eu)
+        if float(p0.norm()) > 0:
             assert e < (2e-4 if precision == "bf16x3" else 2e-3), (k, e)
     ref = dp.flat.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, dp.flat), "ranks diverged"
-    print(f"DP_EQUIV_OK rank={rank} world={world} fused={fused} precision={precision} worst_rel_weight_diff={worst:.2e}", flush=True)
+    print(f"DP_EQUIV_OK rank={rank} world={world} fused={fused} precision={precision} worst_rel_weight_diff={worst:.2e} worst_rel_update_diff={worst_u:.2e}", flush=True)
     dist.destroy_process_group()
 
 

@@ -96,7 +96,7 @@ def test_diffuse_t_and_generate_diffuse_pair(pkg):
     try:
         a, tgt = F.generate_diffuse_pair(x_0, zero)
         assert tgt is x_0 and torch.equal(a, x_0.repeat(3, 1, 1))
-        hp["X_0_PREDICTION"] = False   # the active dict is the one the functions read (a module global in the reference)
+        F.hp["X_0_PREDICTION"] = False   # F.hp is the active dict the functions read (a module global in the reference)
         a, b = F.generate_diffuse_pair(x_0, zero, zero)
         assert torch.equal(a, x_0.repeat(3, 1, 1)) and torch.equal(b, a)
         t = torch.tensor([999, 500, 999], device=DEV).reshape(3, 1, 1)
