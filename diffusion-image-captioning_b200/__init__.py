@@ -19,7 +19,7 @@ def __getattr__(name):  # torch-dependent modules load lazily so that `build` wo
     if name in ("DistilBertModel", "DistilBertConfig", "AdamW"):
         from . import model as _m
         return getattr(_m, name)
-    if name in ("diffuse_t", "generate_diffuse_pair", "loss", "train_func", "validate", "train", "sample", "bind"):
+    if name in ("diffuse_t", "generate_diffuse_pair", "loss", "train_func", "validate", "train", "sample", "bind", "SAMPLE_USES_CUDA_GRAPH"):
         from . import diffusion as _d
         return getattr(_d, name)
     if name in ("DeviceCaptionDataset", "CaptionSubset", "CaptionLoader", "synthetic_dataset"):

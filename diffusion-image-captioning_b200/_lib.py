@@ -134,6 +134,7 @@ _SIGS = {
                                         u64, u32, f32, C.POINTER(Bf), u32, f32, C.POINTER(Bf), c_p, c_p]),
     "clipdlm_attn_fwd": (C.c_int, [C.POINTER(Bf), c_p, i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
     "clipdlm_attn_bwd": (C.c_int, [C.POINTER(Bf), c_p, C.POINTER(Bf), i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p]),
+    "clipdlm_attn_bwd_bias": (C.c_int, [C.POINTER(Bf), c_p, C.POINTER(Bf), i32, i32, i32, i32, C.POINTER(Bf), u64, u32, f32, c_p, c_p, c_p]),
     "clipdlm_attn_force_simt": (None, [i32]),
     "clipdlm_colsum": (C.c_int, [C.POINTER(Bf), i64, i32, c_p, c_p]),
     "clipdlm_embed_loss": (C.c_int, [C.POINTER(Bf), c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i64, i32, f32, c_p,

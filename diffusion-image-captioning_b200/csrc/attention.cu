@@ -652,7 +652,13 @@ static inline BfPtr mbf(const clipdlm_bf_t* p) {
   BfPtr r; r.hi = (__nv_bfloat16*)p->hi; r.lo = (__nv_bfloat16*)p->lo; return r;
 }
 
-static int g_force_path = 0;   // 0 = auto (forward: tcgen05 packed tiles, backward: mma.sync TMA ring), 1 = fp32 SIMT, 2 = ring, 3 = tcgen05
+// 0 = auto (L = 16 / 18: back-to-back packed tcgen05 tiles, attention_packed.cu; other L <= 32: forward tcgen05 32-row slots, backward mma.sync
+// TMA ring), 1 = fp32 SIMT, 2 = ring, 3 = tcgen05 with 32-row slots (attention_umma.cu), 4 = as 0
+static int g_force_path = 0;
+bool attn_packed_supported(int L, int D, int H);
+template <bool BWD>
+int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
+                       __nv_bfloat16* out, float* dbias, const DropoutCfg& drop, cudaStream_t st);
 void attn_force_simt(int on) { g_force_path = on; }
 template <bool BWD>
 int launch_attn_umma(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
@@ -709,6 +715,8 @@ int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, i
   CLIPDLM_CHECK(qkv && qkv->hi && ctx && ctx->hi && keymask, "attn_fwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_fwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_fwd: L %d out of range (1..128)", L);
+  if (qkv->lo == nullptr && ctx->lo == nullptr && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H))
+    return launch_attn_packed<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, nullptr, make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && ctx->lo == nullptr && ((L <= 32 && (g_force_path == 0 || g_force_path == 3)) || (L > 32 && g_force_path != 1)))
     return launch_attn_umma<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && g_force_path == 2)
@@ -733,11 +741,19 @@ int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, i
   return 0;
 }
 
+// dbias (nullable): d(qkv bias) [3D] fp32. When the kernel that runs can fold the bias gradients into its epilogue it accumulates d(q bias) and
+// d(v bias) there (d(k bias) is analytically zero) and sets *folded = 1; otherwise *folded = 0 and the caller runs its column-sum pass over dqkv.
 int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int R, int L, int D, int H,
-                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st) {
+                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st, float* dbias, int* folded) {
   CLIPDLM_CHECK(qkv && qkv->hi && dctx && dctx->hi && dqkv && dqkv->hi && keymask, "attn_bwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_bwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_bwd: L %d out of range (1..128)", L);
+  if (folded) *folded = 0;
+  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H)) {
+    if (folded && dbias) *folded = 1;
+    return launch_attn_packed<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
+                                    (folded && dbias) ? dbias : nullptr, make_drop(seed, site, p), st);
+  }
   // 32 < L <= 128 (bert-large / seq_len 64 shapes): tcgen05 tiles with one or two sequences per tile, both directions
   if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && ((L <= 32 && g_force_path == 3) || (L > 32 && g_force_path != 1)))
     return launch_attn_umma<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,

@@ -49,7 +49,7 @@ void attn_force_simt(int on);
 int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, int L, int D, int H, const clipdlm_bf_t* ctx,
                       unsigned long long seed, uint32_t site, float p, cudaStream_t st);
 int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int R, int L, int D, int H,
-                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st);
+                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st, float* dbias, int* folded);
 
 }  // namespace clipdlm
 
@@ -107,7 +107,15 @@ int clipdlm_attn_fwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, int32_t R
 }
 int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int32_t R, int32_t L, int32_t D, int32_t H,
                      const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p, clipdlm_stream stream) {
-  return attn_bwd_dispatch(qkv, keymask, dctx, R, L, D, H, dqkv, drop_seed, drop_site, drop_p, ST);
+  return attn_bwd_dispatch(qkv, keymask, dctx, R, L, D, H, dqkv, drop_seed, drop_site, drop_p, ST, nullptr, nullptr);
+}
+int clipdlm_attn_bwd_bias(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int32_t R, int32_t L, int32_t D, int32_t H,
+                          const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p, float* dbias_qkv, int32_t* bias_folded,
+                          clipdlm_stream stream) {
+  int folded = 0;
+  const int rc = attn_bwd_dispatch(qkv, keymask, dctx, R, L, D, H, dqkv, drop_seed, drop_site, drop_p, ST, dbias_qkv, &folded);
+  if (bias_folded) *bias_folded = folded;
+  return rc;
 }
 void clipdlm_attn_force_simt(int32_t on) { attn_force_simt(on); }
 int clipdlm_colsum(const clipdlm_bf_t* x, int64_t rows, int32_t N, float* out, clipdlm_stream stream) { return colsum_dispatch(x, rows, N, out, ST); }

@@ -42,7 +42,7 @@ int gather_rows_f32_dispatch(const clipdlm_bf_t* x, long long rows_out, int len,
 int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, int L, int D, int H, const clipdlm_bf_t* ctx,
                       unsigned long long seed, uint32_t site, float p, cudaStream_t st);
 int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int R, int L, int D, int H,
-                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st);
+                      const clipdlm_bf_t* dqkv, unsigned long long seed, uint32_t site, float p, cudaStream_t st, float* dbias, int* folded);
 
 // ------------------------------------------------------------------------------------------------------------------
 // flat parameter layout
@@ -441,8 +441,11 @@ static int backward_from_g0(clipdlm_engine* e, cudaStream_t st) {
     RUNG(g);
     g = linear_dgrad(e->g1, shadow(e, lslot(l, CLIPDLM_PL_O_W)), T, D, D, e->g0);
     RUNG(g);
-    RUNP(CLIPDLM_PROF_ATTN_BWD, 10.0 * R * L * L * D, (double)T * 7 * D * (e->pair ? 4.0 : 2.0), attn_bwd_dispatch(&b.qkv, e->keymask, &e->g0, R, L, D, c.n_heads, &e->gq, p.drop_seed, 1 + 2 * l, padrop, st));
-    RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gq, T, 3 * D, grad(e, lslot(l, CLIPDLM_PL_QKV_B)), st));
+    int bias_folded = 0;   // the packed tcgen05 backward (L = 16 / 18, plain bf16) forms d(q bias), d(v bias) in its epilogue; d(k bias) == 0
+    RUNP(CLIPDLM_PROF_ATTN_BWD, 10.0 * R * L * L * D, (double)T * 7 * D * (e->pair ? 4.0 : 2.0),
+         attn_bwd_dispatch(&b.qkv, e->keymask, &e->g0, R, L, D, c.n_heads, &e->gq, p.drop_seed, 1 + 2 * l, padrop, st, grad(e, lslot(l, CLIPDLM_PL_QKV_B)), &bias_folded));
+    if (!bias_folded)
+      RUNP(CLIPDLM_PROF_COLSUM, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), colsum_dispatch(&e->gq, T, 3 * D, grad(e, lslot(l, CLIPDLM_PL_QKV_B)), st));
     g = linear_wgrad(e->gq, hin, T, 3 * D, D, grad(e, lslot(l, CLIPDLM_PL_QKV_W)));
     RUNG(g);
     g = linear_dgrad(e->gq, shadow(e, lslot(l, CLIPDLM_PL_QKV_W)), T, 3 * D, D, e->g0);

@@ -411,15 +411,40 @@ def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dic
     return history
 
 
+SAMPLE_USES_CUDA_GRAPH = True
+_GRAPH_MAX_BATCH = 256     # above this the loop is long kernels back to back and launch latency is hidden anyway
+
+
+def _denoise_steps(model, eng, cur, nxt, img, txt, n_steps: int, return_all: bool):
+    """n_steps x { encoder pass on restored[:, :MAX_LENGTH] } (+ fused lm_head / arg-max where ids are needed). Pure launches on the current
+    stream over caller-owned buffers: this is the body the CUDA graph of the small-batch path captures."""
+    hp = model.hp
+    B = cur.shape[0]
+    Lfull, D = cur.shape[1], cur.shape[2]
+    outs = []
+    for i in range(n_steps):
+        model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=cur,
+                           x_in_stride=Lfull * D, x_out=nxt, reuse_proj=i > 0)  # the CLIP projections do not change across steps
+        cur, nxt = nxt, cur
+        if return_all:
+            outs.append(model.argmax_last(B))
+    indexes = outs[-1] if return_all and outs else model.argmax_last(B)  # softmax is monotone: argmax(softmax(x)) == argmax(x) (:620)
+    return indexes, cur, outs
+
+
 @torch.no_grad()
 def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, return_all: bool = False,
-           restored: Optional[torch.Tensor] = None, unique_consecutive: bool = False):
+           restored: Optional[torch.Tensor] = None, unique_consecutive: bool = False, use_graph: Optional[bool] = None):
     """The reference's reverse "denoise" loop (CLIP-DDPM.py:611-621, COCO_BLEU.py:249-257): restored ~ N(0, I) [B, L, C];
     n_steps x { out, restored = model(restored[:, :MAX_LENGTH], image_clip, 0, ones, [1, 0]) }; ids = argmax over the vocabulary.
 
     Returns ids int64 [B, MAX_LENGTH] (and the final `restored`, and per-step ids if return_all). The lm_head GEMM runs only
     where ids are needed (last step; every step if return_all) with a fused running-argmax epilogue: logits never reach HBM.
-    unique_consecutive=True applies the reference's `indexes.unique_consecutive(dim=-1)` post-processing (:621)."""
+    unique_consecutive=True applies the reference's `indexes.unique_consecutive(dim=-1)` post-processing (:621).
+
+    Small batches (the reference evaluates B = 8 x 5 steps, :613-617) are launch-bound - ~45 kernels of a few microseconds per step - so for
+    B <= 256 the whole loop is captured ONCE per (B, n_steps) into a CUDA graph over static buffers and replayed (use_graph=False opts out;
+    None = on unless profiling)."""
     hp = model.hp
     dev = model.device
     _need_cuda(image_clip)
@@ -428,15 +453,14 @@ def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, r
     Lfull = ML + (2 if hp["CLIP_ADDING_METHOD"] == "concat" else 0)
     if restored is None:
         restored = torch.randn(B, Lfull, D, device=dev)  # :613
-    cur = restored.to(dev, torch.float32).contiguous().clone()
-    nxt = torch.empty_like(cur)
     img = image_clip.to(dev, torch.float32).contiguous()
-    txt = torch.zeros_like(img)  # text_clip = zeros (:617)
     eng = model._engine(B, B, False)
     model._last_eng = eng
     outs = []
     if hp["TRAIN_EMBEDDING"]:  # the loop runs in the IN_CHANNEL-wide space: input_projection -> encoder -> output_projection per step
         from . import train_embedding as TE
+        cur = restored.to(dev, torch.float32).contiguous().clone()
+        txt = torch.zeros_like(img)  # text_clip = zeros (:617)
         xo = torch.empty(B, Lfull, hp["DIM"], device=dev)
         for i in range(n_steps):
             u = TE.in_proj(model, cur[:, :ML].contiguous())
@@ -450,13 +474,41 @@ def sample(model: DistilBertModel, image_clip: torch.Tensor, n_steps: int = 5, r
             indexes = indexes.unique_consecutive(dim=-1)
         cur = cur.clone()
         return (indexes, cur, outs) if return_all else (indexes, cur)
-    for i in range(n_steps):
-        model._run_forward(eng, R=B, B=B, mode=0, guided=False, train=False, image_clip=img, text_clip=txt, attn_mask=None, x_in=cur,
-                           x_in_stride=Lfull * D, x_out=nxt, reuse_proj=i > 0)  # the CLIP projections do not change across steps
-        cur, nxt = nxt, cur
-        if return_all:
-            outs.append(model.argmax_last(B))
-    indexes = outs[-1] if return_all and outs else model.argmax_last(B)  # softmax is monotone: argmax(softmax(x)) == argmax(x) (:620)
+    if use_graph is None:
+        use_graph = SAMPLE_USES_CUDA_GRAPH and B <= _GRAPH_MAX_BATCH and not getattr(model, "_profiling", False)
+    if use_graph:
+        indexes, cur, outs = _sample_graphed(model, eng, restored, img, n_steps, return_all)
+    else:
+        cur = restored.to(dev, torch.float32).contiguous().clone()
+        indexes, cur, outs = _denoise_steps(model, eng, cur, torch.empty_like(cur), img, torch.zeros_like(img), n_steps, return_all)
     if unique_consecutive:
         indexes = indexes.unique_consecutive(dim=-1)
     return (indexes, cur, outs) if return_all else (indexes, cur)
+
+
+def _sample_graphed(model, eng, restored, img, n_steps: int, return_all: bool):
+    """Replay (capture on first use) of the CUDA graph of the denoise loop for this (engine, B, n_steps, return_all)."""
+    dev = model.device
+    B = img.shape[0]
+    cache = model.__dict__.setdefault("_sample_graphs", {})
+    key = (int(eng), B, int(n_steps), bool(return_all), tuple(restored.shape))
+    ent = cache.get(key)
+    if ent is None:
+        for k in [k for k in cache if k[0] != int(eng)]:   # the engine was regrown: its workspace moved, older graphs are stale
+            del cache[k]
+        st_cur = restored.to(dev, torch.float32).contiguous().clone()
+        st_img = img.clone()
+        st_txt = torch.zeros_like(st_img)
+        st_nxt = torch.empty_like(st_cur)
+        keep = st_cur.clone()
+        _denoise_steps(model, eng, st_cur, st_nxt, st_img, st_txt, min(n_steps, 2), return_all)   # un-captured warm-up: lazy one-time initialisation
+        torch.cuda.synchronize(dev)
+        st_cur.copy_(keep)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ids, cur, outs = _denoise_steps(model, eng, st_cur, st_nxt, st_img, st_txt, n_steps, return_all)
+        ent = cache[key] = dict(graph=graph, cur_in=st_cur, img=st_img, ids=ids, cur_out=cur, outs=outs, keep=(st_nxt, st_txt))
+    ent["cur_in"].copy_(restored.to(dev, torch.float32))
+    ent["img"].copy_(img)
+    ent["graph"].replay()
+    return ent["ids"].clone(), ent["cur_out"].clone(), [o.clone() for o in ent["outs"]]

@@ -158,8 +158,17 @@ int clipdlm_attn_bwd(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cli
                      int32_t H, const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p,
                      clipdlm_stream stream);
 
-/* Test hook: attention path for plain bf16, L <= 32: 0 = default (forward: tcgen05 packed tiles, backward: mma.sync TMA ring),
- * 1 = fp32 SIMT kernels, 2 = mma.sync TMA-ring kernels, 3 = tcgen05 packed tiles for both directions. */
+/* clipdlm_attn_bwd that may also form the bias gradients of the q|k|v projection (the column sums of dqkv the caller would otherwise compute
+ * with clipdlm_colsum; autograd of the Linear at modeling_distilbert.py:187-189): dbias_qkv [3*D] fp32 (+=). *bias_folded = 1 when the kernel
+ * that ran accumulated d(q bias) and d(v bias) there (plain bf16, L = 16 / 18: the packed tcgen05 kernel; d(k bias) is analytically zero -
+ * every row of dS sums to zero - and is left untouched), 0 when the caller still has to run clipdlm_colsum over dqkv. */
+int clipdlm_attn_bwd_bias(const clipdlm_bf_t* qkv, const uint32_t* keymask, const clipdlm_bf_t* dctx, int32_t R, int32_t L, int32_t D,
+                          int32_t H, const clipdlm_bf_t* dqkv, uint64_t drop_seed, uint32_t drop_site, float drop_p, float* dbias_qkv,
+                          int32_t* bias_folded, clipdlm_stream stream);
+
+/* Test hook: attention path for plain bf16, L <= 32: 0 = default (L = 16 / 18: tcgen05 tiles of back-to-back packed sequences in both
+ * directions; other L: forward tcgen05 with 32-row slots, backward mma.sync TMA ring), 1 = fp32 SIMT kernels, 2 = mma.sync TMA-ring
+ * kernels, 3 = tcgen05 with 32-row slots for both directions. */
 void clipdlm_attn_force_simt(int32_t on);
 
 /* Column sums (bias gradients): out[n] += sum_m x[m, n]. */

@@ -144,6 +144,17 @@ def make_real_width(name: str = "real_width_6L", steps: int = 2):
             ids_steps.append(torch.softmax(o, -1).argmax(-1).numpy())
             t2 = o.topk(2, dim=-1).values
             gaps.append((t2[..., 0] - t2[..., 1]).numpy())
+    # the reference ITSELF under torch.autocast(bfloat16) on the same inputs: how far plain-bf16 arithmetic moves its own arg-max ids
+    # (the yardstick for the speed mode's agreement gate; this fixture's untrained, closed-form weights give nearly flat logits)
+    r16 = restored.clone()
+    ids16 = []
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        for _ in range(5):
+            o16, r16 = model(r16[:, :ML, :].float(), batch["image_clip"].unsqueeze(1), torch.zeros_like(batch["image_clip"]).unsqueeze(1),
+                             torch.ones(B, ML), torch.tensor([1, 0]).repeat(B, 1))
+            r16 = r16.float()
+            ids16.append(torch.softmax(o16.float(), -1).argmax(-1).numpy())
+    out["autocast_bf16_ids_steps"] = np.stack(ids16)
     out["sample_ids_steps"] = np.stack(ids_steps)
     out["sample_top2_gap_steps"] = np.stack(gaps)
     out["sample_restored_slice"] = r[:, :, ::16].numpy()

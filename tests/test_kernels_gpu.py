@@ -310,7 +310,7 @@ def test_attention_mma_path_matches_simt_with_dropout(G):
     words = words.to(torch.int32).contiguous()
     lib, Lb = G.lib(), G.L
     outs = {}
-    for simt in (0, 1, 2, 3):  # default mix, fp32 SIMT, mma.sync TMA ring, tcgen05 packed tiles
+    for simt in (0, 1, 2, 3):  # default (packed tcgen05 tiles), fp32 SIMT, mma.sync TMA ring, tcgen05 with 32-row slots
         lib.clipdlm_attn_force_simt(simt)
         ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
         dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
@@ -323,6 +323,54 @@ def test_attention_mma_path_matches_simt_with_dropout(G):
     for path in (0, 2, 3):
         assert rel(outs[path][0], outs[1][0]) < 1e-2 and rel(outs[path][1], outs[1][1]) < 1.5e-2, path
     # a differing mask would change ~10 % of the probabilities by 100 %: far outside these bounds
+
+
+@pytest.mark.parametrize("L,R", [(18, 2500), (18, 6), (16, 1031), (18, 7 * 296 + 3)])
+def test_attention_packed_tiles_and_folded_bias_gradients(G, L, R):
+    """attention_packed.cu (the default for L = 16 / 18, plain bf16): 7 back-to-back sequences per 128-row tcgen05 tile. Many tiles per CTA
+    (R = 2500: 358 tiles over 24 CTAs per head), a ragged last tile, dropout on; against the fp32 SIMT kernels (same dropout masks), and the
+    bias gradients folded into the backward's epilogue (clipdlm_attn_bwd_bias) against the column sums of its own dqkv: d(q bias) from the
+    per-thread accumulators, d(v bias) from the row-sum column of P' on the tensor core, d(k bias) left untouched (analytically zero)."""
+    D, H, p = 768, 12, 0.1
+    qkv = torch.randn(R * L, 3 * D, device=G.DEV).bfloat16()
+    dctx = torch.randn(R * L, D, device=G.DEV).bfloat16()
+    km = torch.rand(R, L, device=G.DEV) > 0.2
+    km[:, 1] = True
+    words = torch.zeros(R, 1, device=G.DEV, dtype=torch.int64)
+    for j in range(L):
+        words[:, 0] |= km[:, j].long() << j
+    words = words.to(torch.int32).contiguous()
+    lib, Lb = G.lib(), G.L
+    outs = {}
+    for path in (0, 1):
+        lib.clipdlm_attn_force_simt(path)
+        ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
+        dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
+        dbias = torch.full((3 * D,), 0.25, device=G.DEV)
+        folded = torch.zeros(1, dtype=torch.int32)
+        Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx, None)), 4242, 9, p, G.st()))
+        Lb.check(lib.clipdlm_attn_bwd_bias(C.byref(G.bfp(qkv, None)), words.data_ptr(), C.byref(G.bfp(dctx, None)), R, L, D, H, C.byref(G.bfp(dq, None)),
+                                           4242, 9, p, dbias.data_ptr(), folded.data_ptr(), G.st()))
+        torch.cuda.synchronize()
+        outs[path] = (ctx.float(), dq.float(), dbias.clone(), int(folded))
+    lib.clipdlm_attn_force_simt(0)
+    assert outs[0][3] == 1 and outs[1][3] == 0            # the SIMT path leaves the bias gradients to the caller's colsum
+    assert torch.equal(outs[1][2], torch.full((3 * D,), 0.25, device=G.DEV))
+    assert rel(outs[0][0], outs[1][0]) < 1e-2 and rel(outs[0][1], outs[1][1]) < 1.5e-2
+    got = outs[0][2] - 0.25                                # += semantics
+    want = outs[1][1].double().sum(0)                      # column sums of the fp32-SIMT dqkv
+    own = outs[0][1].double().sum(0)
+    assert rel(got[:D], want[:D]) < 1e-2 and rel(got[2 * D:], want[2 * D:]) < 1e-2
+    assert rel(got[:D], own[:D]) < 5e-3 and rel(got[2 * D:], own[2 * D:]) < 5e-3
+    assert float(got[D:2 * D].abs().max()) == 0.0 and float(want[D:2 * D].abs().max()) < 1e-2 * float(want[:D].abs().max())
+    # without the dropout, and repeated launches on the persistent P / dS tiles: against fp64 torch
+    qr = qkv.double().requires_grad_(True)
+    ref = _attn_ref(qr, km, R, L, D, H)
+    ref.backward(dctx.double())
+    ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16); dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
+    Lb.check(lib.clipdlm_attn_fwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), R, L, D, H, C.byref(G.bfp(ctx, None)), 0, 0, 0.0, G.st()))
+    Lb.check(lib.clipdlm_attn_bwd(C.byref(G.bfp(qkv, None)), words.data_ptr(), C.byref(G.bfp(dctx, None)), R, L, D, H, C.byref(G.bfp(dq, None)), 0, 0, 0.0, G.st()))
+    assert rel(ctx, ref) < 5e-3 and rel(dq, qr.grad) < 6e-3
 
 
 @pytest.mark.parametrize("L,R", [(40, 7), (66, 5), (128, 3)])

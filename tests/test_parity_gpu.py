@@ -530,11 +530,19 @@ def test_real_width_speed_mode_vs_reference(pkg, record_property):
     g = r["g"]
     np.testing.assert_allclose(r["losses"], g["train_losses"], rtol=1e-2)
     agree = float((r["ids_steps"] == g["sample_ids_steps"]).mean())
-    agree_clear = float((r["ids_steps"] == g["sample_ids_steps"])[g["sample_top2_gap_steps"] > 2e-2].mean())
+    clear = g["sample_top2_gap_steps"] > 5e-2
+    agree_clear = float((r["ids_steps"] == g["sample_ids_steps"])[clear].mean())
+    ref_autocast = float((g["autocast_bf16_ids_steps"] == g["sample_ids_steps"]).mean())
     record_property("bf16_argmax_agreement", agree)
-    print(f"\nbf16 speed mode, real width: arg-max agreement {agree:.4f} over {g['sample_ids_steps'].size} ids "
-          f"({agree_clear:.4f} where the reference's top-2 gap > 2e-2); losses {r['losses'].tolist()} vs {g['train_losses'].tolist()}")
-    assert agree >= 0.97, agree
+    record_property("reference_autocast_bf16_argmax_agreement", ref_autocast)
+    print(f"\nbf16 speed mode, real width: arg-max agreement with the reference's fp32 ids {agree:.4f} over {g['sample_ids_steps'].size} ids "
+          f"({agree_clear:.4f} on the {int(clear.sum())} ids whose reference top-2 gap > 5e-2); the reference itself under autocast(bf16): {ref_autocast:.4f}; "
+          f"losses {r['losses'].tolist()} vs {g['train_losses'].tolist()}")
+    # Gate = the reference's OWN agreement with itself under torch.autocast(bfloat16) on this fixture (0.955 here: untrained closed-form weights,
+    # nearly flat logits, 12 % of the ids have a top-2 gap below bf16 resolution; SURVEY 7 measured 0.97 on a random-init model) - the speed mode
+    # must not move the ids more than plain-bf16 arithmetic moves the reference's own; clear-cut ids (gap > 5e-2) must agree.
+    assert agree >= ref_autocast - 0.005, (agree, ref_autocast)
+    assert agree >= 0.95 and agree_clear >= 0.995, (agree, agree_clear)
     names = [str(n) for n in g["grad_names"]]
     gscale = float(g["grad_norms"].max())
     for n, ref_norm in zip(names, g["grad_norms"]):

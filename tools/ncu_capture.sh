@@ -17,11 +17,11 @@ full() {  # name, kernel regex (demangled), launches to capture, launches to ski
       $BENCH --steps 1 --warmup 0 --samples 16 > /dev/null 2> gpurun_out/${TAG}_full_$1.err
   ncu -i gpurun_out/${TAG}_full_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_$1.csv 2>/dev/null
 }
-full gemm_fwd   'gemm_kernel<0, 0, (0|6),' 12 13
-full gemm_lse   'gemm_kernel<0, 0, (2|4),' 2 0
-full gemm_dgrad 'gemm_kernel<0, 1, ' 8 2
-full gemm_wgrad 'gemm_kernel<1, 1, ' 5 0
-full attn       'attn_' 4 10
+full gemm_fwd   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(0|6),' 12 13
+full gemm_lse   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(2|4),' 2 0
+full gemm_dgrad 'gemm_kernel<(\(int\))?0, (\(int\))?1, ' 8 2
+full gemm_wgrad 'gemm_kernel<(\(int\))?1, (\(int\))?1, ' 5 0
+full attn       'attn_' 4 4
 full ln         'layernorm_' 6 12
 python tools/ncu_full_summary.py gpurun_out ${TAG} > gpurun_out/${TAG}_ncu_full_summary.csv 2> gpurun_out/${TAG}_ncu_full_summary.err
 ls -la gpurun_out | head -40
