@@ -121,9 +121,11 @@ __device__ __forceinline__ void ap_store_block(uint32_t tile, int row, int s, co
   }
 }
 __device__ __forceinline__ void ap_zero_row_chunk(uint32_t tile_chunk, int row) {   // 128 B of one row of one 64-key chunk
+  // 16-byte units visited in swizzled order: the 32 rows of a warp are 128 B apart (the same banks), the XOR spreads each store over 8 bank
+  // groups (4-way instead of 32-way conflicts)
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_chunk + (uint32_t)row * 128u + (uint32_t)(c << 4)), "r"(0u) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile_chunk + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4)), "r"(0u) : "memory");
 }
 
 // 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (128 contiguous bytes) in global memory; ACC: also added into acc[]

@@ -357,6 +357,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): issued one work item ahead, so that the real load hits L2.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
+
 // 1-D bulk copy global -> shared (contiguous bytes, multiple of 16, both addresses 16-byte aligned), completing on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
