@@ -404,6 +404,24 @@ __device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* tm
       : "memory");
 }
 
+// L2 cache-policy operands for TMA loads (.L2::cache_hint): the fixed encodings createpolicy.fractional.L2::evict_{first,last} (fraction 1.0)
+// produces. evict_last keeps a small, heavily re-read operand (the 47 MB embedding table of the lm_head GEMMs) resident while gigabytes of
+// logits stream through L2; evict_first marks an operand that is read exactly once.
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------

@@ -71,6 +71,7 @@ struct GemmArgs {
   int tgt_period;
   const float* lse;          // SMGRAD: lse[M];  LSE_EXP: the exponent shift (device scalar, may be NULL);  STORE_ROWSCALE: row_scale[M]
   float grad_scale;          // (one slot for the three: GemmArgs keeps its layout, so the other instantiations compile to the same SASS)
+  uint64_t pol_a, pol_b;     // L2 cache-policy operands of the plain 2-D TMA loads of A / B (0 = default policy)
 };
 
 __device__ __forceinline__ long long map_row(const GemmArgs& g, int m) {
@@ -405,13 +406,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
               if (AMAJ == 0) {
                 if (g.gather_len > 0) tma_load_3d(sa, ta, &full_bar[stage], kb * BK, 0, m0 / g.gather_len);
+                else if (g.pol_a != 0) tma_load_2d_hint(sa, ta, &full_bar[stage], kb * BK, m0, g.pol_a);
                 else tma_load_2d(sa, ta, &full_bar[stage], kb * BK, m0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ta, &full_bar[stage], m0 + j * 64, kb * BK);
               }
               if (BMAJ == 0) {
-                tma_load_2d(sb, tb, &full_bar[stage], kb * BK, n0);
+                if (g.pol_b != 0) tma_load_2d_hint(sb, tb, &full_bar[stage], kb * BK, n0, g.pol_b);
+                else tma_load_2d(sb, tb, &full_bar[stage], kb * BK, n0);
+              } else if (g.pol_b != 0) {
+#pragma unroll
+                for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d_hint(sb + j * 8192, tb, &full_bar[stage], n0 + j * 64, kb * BK, g.pol_b);
               } else {
 #pragma unroll
                 for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d(sb + j * 8192, tb, &full_bar[stage], n0 + j * 64, kb * BK);
@@ -422,13 +428,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               else mbar_arrive_cluster(fb);
               if (AMAJ == 0) {
                 if (g.gather_len > 0) tma_load_3d_cg2(sa, ta, fb, kb * BK, 0, m0 / g.gather_len);
+                else if (g.pol_a != 0) tma_load_2d_cg2_hint(sa, ta, fb, kb * BK, m0, g.pol_a);
                 else tma_load_2d_cg2(sa, ta, fb, kb * BK, m0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sa + j * 8192, ta, fb, m0 + j * 64, kb * BK);
               }
               if (BMAJ == 0) {
-                tma_load_2d_cg2(sb, tb, fb, kb * BK, n0);
+                if (g.pol_b != 0) tma_load_2d_cg2_hint(sb, tb, fb, kb * BK, n0, g.pol_b);
+                else tma_load_2d_cg2(sb, tb, fb, kb * BK, n0);
+              } else if (g.pol_b != 0) {
+#pragma unroll
+                for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d_cg2_hint(sb + j * 8192, tb, fb, n0 + j * 64, kb * BK, g.pol_b);
               } else {
 #pragma unroll
                 for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d_cg2(sb + j * 8192, tb, fb, n0 + j * 64, kb * BK);
@@ -1101,6 +1112,10 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   if (g->a_lo) { ga.part_a[ga.nparts] = 1; ga.part_b[ga.nparts] = 0; ga.nparts++; }
   if (g->b_lo) { ga.part_a[ga.nparts] = 0; ga.part_b[ga.nparts] = 1; ga.nparts++; }
   ga.gather_len = g->gather_len;
+  // lm_head GEMMs (A gathered from x_out[:, :16] / output scattered back): B is the embedding table, re-read by every row tile while the
+  // logits (written, or read exactly once as the A operand of the gradient GEMM) stream through L2 - keep the table, let the logits go
+  ga.pol_a = g->scatter_len > 0 ? L2_EVICT_FIRST : 0ull;
+  ga.pol_b = (g->gather_len > 0 || g->scatter_len > 0) ? L2_EVICT_LAST : 0ull;
   ga.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192;
   ga.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
   ga.out_hi = (__nv_bfloat16*)g->out_hi; ga.out_lo = (__nv_bfloat16*)g->out_lo;
