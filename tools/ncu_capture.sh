@@ -16,9 +16,11 @@ full() {  # name, kernel regex (demangled), launches to capture, launches to ski
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $4 -c $3 -f -o gpurun_out/${TAG}_full_$1 \
       $BENCH --steps 1 --warmup 0 --samples 16 > /dev/null 2> gpurun_out/${TAG}_full_$1.err
   ncu -i gpurun_out/${TAG}_full_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_$1.csv 2>/dev/null
+  if [ "${5:-}" = "source" ]; then ncu -i gpurun_out/${TAG}_full_$1.ncu-rep --page source --csv > gpurun_out/${TAG}_full_$1_source.csv 2>/dev/null; fi
+  rm -f gpurun_out/${TAG}_full_$1.ncu-rep      # gpurun brings back at most 64 MiB: keep the CSV exports, not the reports
 }
-full gemm_fwd   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(0|6),' 12 13
-full gemm_lse   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(2|4),' 2 0
+full gemm_fwd   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(0|6),' 12 13 source
+full gemm_lse   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(2|4),' 2 0 source
 full gemm_dgrad 'gemm_kernel<(\(int\))?0, (\(int\))?1, ' 8 2
 full gemm_wgrad 'gemm_kernel<(\(int\))?1, (\(int\))?1, ' 5 0
 full attn       'attn_' 4 4
