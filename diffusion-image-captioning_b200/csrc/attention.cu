@@ -657,8 +657,9 @@ static inline BfPtr mbf(const clipdlm_bf_t* p) {
 static int g_force_path = 0;
 bool attn_packed_supported(int L, int D, int H);
 template <bool BWD>
-int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
-                       __nv_bfloat16* out, float* dbias, const DropoutCfg& drop, cudaStream_t st);
+int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo,
+                       const uint32_t* keymask, int R, int L, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias,
+                       const DropoutCfg& drop, cudaStream_t st);
 void attn_force_simt(int on) { g_force_path = on; }
 template <bool BWD>
 int launch_attn_umma(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
@@ -715,8 +716,9 @@ int attn_fwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, int R, i
   CLIPDLM_CHECK(qkv && qkv->hi && ctx && ctx->hi && keymask, "attn_fwd: null pointer");
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_fwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_fwd: L %d out of range (1..128)", L);
-  if (qkv->lo == nullptr && ctx->lo == nullptr && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H))
-    return launch_attn_packed<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, nullptr, make_drop(seed, site, p), st);
+  if ((qkv->lo == nullptr) == (ctx->lo == nullptr) && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H))
+    return launch_attn_packed<false>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)qkv->lo, nullptr, nullptr, keymask, R, L, D, H,
+                                     (__nv_bfloat16*)ctx->hi, (__nv_bfloat16*)ctx->lo, nullptr, make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && ctx->lo == nullptr && ((L <= 32 && (g_force_path == 0 || g_force_path == 3)) || (L > 32 && g_force_path != 1)))
     return launch_attn_umma<false>((const __nv_bfloat16*)qkv->hi, nullptr, keymask, R, L, D, H, (__nv_bfloat16*)ctx->hi, make_drop(seed, site, p), st);
   if (qkv->lo == nullptr && ctx->lo == nullptr && L <= 32 && g_force_path == 2)
@@ -749,10 +751,13 @@ int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cl
   CLIPDLM_CHECK(H > 0 && D == H * DH, "attn_bwd: head dim must be 64 (D %d, H %d)", D, H);
   CLIPDLM_CHECK(L >= 1 && L <= 128, "attn_bwd: L %d out of range (1..128)", L);
   if (folded) *folded = 0;
-  if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H)) {
-    if (folded && dbias) *folded = 1;
-    return launch_attn_packed<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)dctx->hi, keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi,
-                                    (folded && dbias) ? dbias : nullptr, make_drop(seed, site, p), st);
+  const bool all_pair = qkv->lo != nullptr && dctx->lo != nullptr && dqkv->lo != nullptr;
+  const bool all_plain = qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr;
+  if ((all_plain || all_pair) && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H)) {
+    const bool fold = all_plain && folded && dbias;
+    if (fold) *folded = 1;
+    return launch_attn_packed<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)qkv->lo, (const __nv_bfloat16*)dctx->hi, (const __nv_bfloat16*)dctx->lo,
+                                    keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi, (__nv_bfloat16*)dqkv->lo, fold ? dbias : nullptr, make_drop(seed, site, p), st);
   }
   // 32 < L <= 128 (bert-large / seq_len 64 shapes): tcgen05 tiles with one or two sequences per tile, both directions
   if (qkv->lo == nullptr && dctx->lo == nullptr && dqkv->lo == nullptr && ((L <= 32 && g_force_path == 3) || (L > 32 && g_force_path != 1)))

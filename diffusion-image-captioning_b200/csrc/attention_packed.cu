@@ -19,6 +19,12 @@
 //            shared-memory reduction + 64 atomics per CTA at the end;
 //   d(b_k) = sum_j dK_j = sum_i q_i (sum_j dS_ij) = 0 exactly (softmax is shift invariant: every dS row sums to zero) - not formed; the
 //            reference's autograd produces rounding noise there.
+//
+// PAIR = split precision ("bf16x3", the parity mode): q|k|v, dO and the outputs are (hi, lo) bf16 pairs. Every product X Y runs as the three
+// tensor-core passes Xh Yh + Xl Yh + Xh Yl into one fp32 TMEM accumulator (the dropped Xl Yl term is 2^-16 relative), the probabilities
+// and dS are split the same way when they are written to shared memory, so the [tile set] simply exists twice (hi set, lo set): forward
+// 6 tiles (96 KB, 2 CTAs per SM), backward 14 tiles (224 KB, 1 CTA per SM). Replaces the fp32 SIMT kernels of attention.cu for L = 16 / 18
+// (they took 370 of the 1306 ms of a parity-mode step). The bias-gradient fold stays off in this mode (the engine's colsum runs).
 #include "common.cuh"
 #include "../../include/clipdlm.h"
 #include <cudaTypedefs.h>
@@ -63,6 +69,7 @@ __device__ __forceinline__ uint32_t ap_row_keep_bits(const DropoutCfg& d, unsign
 struct AttPArgs {
   const uint32_t* keymask;
   __nv_bfloat16* out;       // ctx [T, D] (forward) or dqkv [T, 3D] (backward)
+  __nv_bfloat16* out_lo;    // PAIR: the lo halves of the output
   float* dbias;             // backward: d(qkv bias) [3D] (fp32, accumulated with atomics) or nullptr
   int R, L, D, H;
   int tiles;                // ceil(R / NS): 128-row tiles per head
@@ -120,6 +127,15 @@ __device__ __forceinline__ void ap_store_block(uint32_t tile, int row, int s, co
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(x[2 * jj], x[2 * jj + 1])) : "memory");
   }
 }
+// PAIR: x -> (bf16(x), bf16(x - bf16(x))) into the hi tile and its twin `lo_off` bytes further
+template <int SLOT>
+__device__ __forceinline__ void ap_store_block_pair(uint32_t tile, uint32_t lo_off, int row, int s, const float (&x)[SLOT]) {
+  float lo[SLOT];
+#pragma unroll
+  for (int j = 0; j < SLOT; ++j) lo[j] = x[j] - bf16_round(x[j]);
+  ap_store_block<SLOT>(tile, row, s, x);
+  ap_store_block<SLOT>(tile + lo_off, row, s, lo);
+}
 __device__ __forceinline__ void ap_zero_row_chunk(uint32_t tile_chunk, int row) {   // 128 B of one row of one 64-key chunk
   // 16-byte units visited in swizzled order: the 32 rows of a warp are 128 B apart (the same banks), the XOR spreads each store over 8 bank
   // groups (4-way instead of 32-way conflicts)
@@ -130,7 +146,8 @@ __device__ __forceinline__ void ap_zero_row_chunk(uint32_t tile_chunk, int row) 
 
 // 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (128 contiguous bytes) in global memory; ACC: also added into acc[]
 template <bool ACC, int NACC>
-__device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* dst, bool store, bool accumulate, float (&acc)[NACC]) {
+__device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* dst, bool store, bool accumulate, float (&acc)[NACC],
+                                               __nv_bfloat16* dst_lo = nullptr) {
   static_assert(!ACC || NACC == 64, "accumulator size");
   float v[32];
 #pragma unroll
@@ -142,6 +159,15 @@ __device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* ds
         *reinterpret_cast<uint4*>(dst + half * 32 + c * 8) =
             make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]), pack_bf16x2(v[8 * c + 4], v[8 * c + 5]),
                        pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+      if (dst_lo != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] -= bf16_round(v[j]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(dst_lo + half * 32 + c * 8) =
+              make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]), pack_bf16x2(v[8 * c + 4], v[8 * c + 5]),
+                         pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+      }
     }
     if (ACC) {
       if (accumulate) {
@@ -152,17 +178,20 @@ __device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* ds
   }
 }
 
-template <bool BWD, int SLOT>
-__global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                                                                               const AttPArgs a) {
+template <bool BWD, int SLOT, bool PAIR>
+__global__ void __launch_bounds__(AP_THREADS, (BWD ? 2 : 4) / (PAIR ? 2 : 1))
+attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_qkv_lo,
+                   const __grid_constant__ CUtensorMap tm_do_lo, const AttPArgs a) {
   extern __shared__ __align__(1024) uint8_t ap_smem[];
   // forward : Q | K | V, P (2 tiles) overlays Q | K once S is done      = 3 tiles (48 KB), 128 TMEM columns: 4 CTAs per SM
   // backward: Q | K | dO | V + P (P chunk 0 overlays V) | dS(2)           = 7 tiles (112 KB), 256 TMEM columns: 2 CTAs per SM
   constexpr int OFF_Q = 0, OFF_K = 1, OFF_DO = 2, OFF_V = BWD ? 3 : 2, OFF_P = BWD ? 3 : 0, OFF_DS = 5;
-  constexpr int NTILES_SMEM = BWD ? 7 : 3;
+  constexpr int NSET = BWD ? 7 : 3;                         // tiles of one precision set
+  constexpr int NTILES_SMEM = NSET * (PAIR ? 2 : 1);        // PAIR: the lo set follows the hi set, same layout
+  constexpr uint32_t LO = NSET * AP_TILE;                   // byte offset hi tile -> its lo twin
   constexpr uint32_t TMEM_COLS = BWD ? 256 : 128;
   constexpr uint32_t COL_O = BWD ? 128 : 0;
-  constexpr int NLOADS = BWD ? 4 : 3;
+  constexpr int NLOADS = (BWD ? 4 : 3) * (PAIR ? 2 : 1);
   constexpr int NS = 127 / SLOT;
   constexpr int ROWS = NS * SLOT;      // live rows of a tile (<= 127)
   uint8_t* smem = ap_smem;
@@ -176,9 +205,11 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
   // backward: the dS tile and key chunk 1 of P are dedicated; each row only ever writes its own diagonal block there (+ column 127 of P),
   // everything else stays zero for the life of the CTA. (Chunk 0 of P is where TMA lands V: its rows are rewritten for every group.)
   if (BWD) {
-    uint8_t* z0 = smem + (OFF_P + 1) * AP_TILE;
     const uint32_t zbytes = 3u * AP_TILE;
-    for (uint32_t off = threadIdx.x * 16; off < zbytes; off += AP_THREADS * 16) *reinterpret_cast<uint4*>(z0 + off) = make_uint4(0u, 0u, 0u, 0u);
+    for (int set = 0; set < (PAIR ? 2 : 1); ++set) {
+      uint8_t* z0 = smem + set * LO + (OFF_P + 1) * AP_TILE;
+      for (uint32_t off = threadIdx.x * 16; off < zbytes; off += AP_THREADS * 16) *reinterpret_cast<uint4*>(z0 + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (threadIdx.x == 0) {
     pdl_launch_dependents();
@@ -186,6 +217,7 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
     fence_mbar_init();
     tma_prefetch_desc(&tm_qkv);
     if (BWD) tma_prefetch_desc(&tm_do);
+    if (PAIR) { tma_prefetch_desc(&tm_qkv_lo); if (BWD) tma_prefetch_desc(&tm_do_lo); }
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -210,6 +242,12 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
         tma_load_2d(smem + OFF_K * AP_TILE, &tm_qkv, in_full, a.D + h * AP_DH, row0);
         tma_load_2d(smem + OFF_V * AP_TILE, &tm_qkv, in_full, 2 * a.D + h * AP_DH, row0);
         if (BWD) tma_load_2d(smem + OFF_DO * AP_TILE, &tm_do, in_full, h * AP_DH, row0);
+        if (PAIR) {
+          tma_load_2d(smem + LO + OFF_Q * AP_TILE, &tm_qkv_lo, in_full, h * AP_DH, row0);
+          tma_load_2d(smem + LO + OFF_K * AP_TILE, &tm_qkv_lo, in_full, a.D + h * AP_DH, row0);
+          tma_load_2d(smem + LO + OFF_V * AP_TILE, &tm_qkv_lo, in_full, 2 * a.D + h * AP_DH, row0);
+          if (BWD) tma_load_2d(smem + LO + OFF_DO * AP_TILE, &tm_do_lo, in_full, h * AP_DH, row0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -220,6 +258,15 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
       constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q: both MN-major
       const uint32_t sq = smem_u32(smem + OFF_Q * AP_TILE), sk = smem_u32(smem + OFF_K * AP_TILE), sv = smem_u32(smem + OFF_V * AP_TILE);
       const uint32_t sdo = smem_u32(smem + OFF_DO * AP_TILE), sp = smem_u32(smem + OFF_P * AP_TILE), sds = smem_u32(smem + OFF_DS * AP_TILE);
+      // X Y = Xh Yh (+ Xl Yh + Xh Yl in split precision): A / B descriptors of the hi tiles, the lo twins sit LO bytes further
+      constexpr uint64_t LO_DESC = (uint64_t)(LO >> 4);
+      auto mm = [&](uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        umma_bf16(d, adesc, bdesc, idesc, acc);
+        if (PAIR) {
+          umma_bf16(d, adesc + LO_DESC, bdesc, idesc, 1u);
+          umma_bf16(d, adesc, bdesc + LO_DESC, idesc, 1u);
+        }
+      };
       for (int n = 0; n < my_tiles; ++n) {
         const uint32_t par = (uint32_t)n & 1u;
         mbar_wait(in_full, par);
@@ -227,13 +274,13 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S = Q K^T
-          umma_bf16(tmem_base, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2),
-                    idesc_s, k > 0 ? 1u : 0u);
+          mm(tmem_base, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2),
+             idesc_s, k > 0 ? 1u : 0u);
         if (BWD) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // dP = dO V^T
-            umma_bf16(tmem_base + 128, make_smem_desc_sw128(sdo, 16, 1024) + (uint64_t)(k * 2),
-                      make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+            mm(tmem_base + 128, make_smem_desc_sw128(sdo, 16, 1024) + (uint64_t)(k * 2),
+               make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(s_full);
         mbar_wait(p_full, par);
@@ -241,21 +288,21 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
         if (!BWD) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // O = P V  (keys in blocks of 16: P chunk k / 4, 32 B per step; V rows 16 k)
-            umma_bf16(tmem_base + COL_O, make_smem_desc_sw128(sp + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
-                      make_smem_desc_sw128(sv, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
+            mm(tmem_base + COL_O, make_smem_desc_sw128(sp + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
+               make_smem_desc_sw128(sv, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // dV = P^T dO   (queries in blocks of 16: rows 16 k of P and dO)
-            umma_bf16(tmem_base, make_smem_desc_sw128(sp, AP_TILE, 1024) + (uint64_t)(k * 128),
-                      make_smem_desc_sw128(sdo, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
+            mm(tmem_base, make_smem_desc_sw128(sp, AP_TILE, 1024) + (uint64_t)(k * 128),
+               make_smem_desc_sw128(sdo, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // dK = dS^T Q
-            umma_bf16(tmem_base + 64, make_smem_desc_sw128(sds, AP_TILE, 1024) + (uint64_t)(k * 128),
-                      make_smem_desc_sw128(sq, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
+            mm(tmem_base + 64, make_smem_desc_sw128(sds, AP_TILE, 1024) + (uint64_t)(k * 128),
+               make_smem_desc_sw128(sq, 8192, 1024) + (uint64_t)(k * 128), idesc_tv, k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // dQ = dS K
-            umma_bf16(tmem_base + 128, make_smem_desc_sw128(sds + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
-                      make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
+            mm(tmem_base + 128, make_smem_desc_sw128(sds + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
+               make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(in_empty);   // every operand tile of this group has been consumed
@@ -270,9 +317,9 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
     const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t sp = smem_u32(smem + OFF_P * AP_TILE), sds = smem_u32(smem + OFF_DS * AP_TILE);
     const int k_slot = s - (32 * quad) / SLOT;   // 0, 1 or 2: which block of the warp's column window is this thread's
-    float acc[BWD ? 64 : 1];
+    float acc[(BWD && !PAIR) ? 64 : 1];
 #pragma unroll
-    for (int j = 0; j < (BWD ? 64 : 1); ++j) acc[j] = 0.f;
+    for (int j = 0; j < ((BWD && !PAIR) ? 64 : 1); ++j) acc[j] = 0.f;
     const bool dropping = a.drop.thresh16 != 0;
     const float sl = a.scale * AP_LOG2E;
     for (int n = 0; n < my_tiles; ++n) {
@@ -316,7 +363,13 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
         // P lives where TMA landed Q / K: rewrite this row of both key chunks completely (zeros off the diagonal block)
         ap_zero_row_chunk(sp, row);
         ap_zero_row_chunk(sp + AP_TILE, row);
-        if (live) ap_store_block<SLOT>(sp, row, s, p);
+        if (PAIR) {
+          ap_zero_row_chunk(sp + LO, row);
+          ap_zero_row_chunk(sp + LO + AP_TILE, row);
+          if (live) ap_store_block_pair<SLOT>(sp, LO, row, s, p);
+        } else if (live) {
+          ap_store_block<SLOT>(sp, row, s, p);
+        }
       } else {
         float dp[SLOT];
 #pragma unroll
@@ -342,7 +395,13 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
         }
         // key chunk 0 of P is where TMA landed V: rewrite this row of it completely
         ap_zero_row_chunk(sp, row);
-        if (row < ROWS) {
+        if (PAIR) ap_zero_row_chunk(sp + LO, row);
+        if (PAIR) {
+          if (row < ROWS) {
+            ap_store_block_pair<SLOT>(sp, LO, row, s, p);
+            ap_store_block_pair<SLOT>(sds, LO, row, s, dp);
+          }
+        } else if (row < ROWS) {
           ap_store_block<SLOT>(sp, row, s, p);
           ap_store_block<SLOT>(sds, row, s, dp);
           if (a.dbias != nullptr) {   // P'[i, 127] = rho_i  (word 63 of the row: keys 126 | 127; key 126 is dead as well)
@@ -359,7 +418,13 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
       tc_fence_after();
       const size_t tok = (size_t)tile * ROWS + row;   // == r * L + i on live rows
       if constexpr (!BWD) {
-        ap_store_out64<false>(tq + COL_O, a.out + tok * a.D + h * AP_DH, live, false, acc);
+        ap_store_out64<false>(tq + COL_O, a.out + tok * a.D + h * AP_DH, live, false, acc, PAIR ? a.out_lo + tok * a.D + h * AP_DH : nullptr);
+      } else if constexpr (PAIR) {
+        __nv_bfloat16* o = a.out + tok * 3 * a.D + h * AP_DH;
+        __nv_bfloat16* ol = a.out_lo + tok * 3 * a.D + h * AP_DH;
+        ap_store_out64<false>(tq + 128, o, live, false, acc, ol);                      // dQ
+        ap_store_out64<false>(tq + 64, o + a.D, live, false, acc, ol + a.D);           // dK (row = key i)
+        ap_store_out64<false>(tq, o + 2 * a.D, live, false, acc, ol + 2 * a.D);        // dV
       } else {
         __nv_bfloat16* o = a.out + tok * 3 * a.D + h * AP_DH;
         const bool fold = a.dbias != nullptr;
@@ -371,7 +436,7 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty);
     }
-    if constexpr (BWD) if (a.dbias != nullptr && my_tiles > 0) {
+    if constexpr (BWD && !PAIR) if (a.dbias != nullptr && my_tiles > 0) {
       // d(b_q)[h] = sum over the 127 query lanes of acc; d(b_v)[h] = lane 127's acc.  Every MMA of this CTA has completed (the last o_full
       // wait), so the operand tiles are free: [128 rows][64] fp32 staging over Q | K.
       float* stage = reinterpret_cast<float*>(smem);
@@ -394,31 +459,37 @@ __global__ void __launch_bounds__(AP_THREADS, BWD ? 2 : 4) attn_packed_kernel(co
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <bool BWD, int SLOT>
-int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int D, int H, __nv_bfloat16* out,
-                  float* dbias, const DropoutCfg& drop, cudaStream_t st) {
+template <bool BWD, int SLOT, bool PAIR>
+int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo, const uint32_t* keymask,
+                  int R, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias, const DropoutCfg& drop, cudaStream_t st) {
   constexpr int NS = 127 / SLOT;
   const unsigned long long T = (unsigned long long)R * SLOT;
-  CUtensorMap tm_qkv, tm_do;
+  CUtensorMap tm_qkv, tm_do, tm_qkv_lo, tm_do_lo;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tm_qkv, qkv, 3ull * D, T, 3ull * D * 2, AP_DH, 128))) return rc;
-  tm_do = tm_qkv;
+  tm_do = tm_qkv; tm_qkv_lo = tm_qkv; tm_do_lo = tm_qkv;
   if (BWD && (rc = make_tmap_2d_bf16(&tm_do, dctx, (unsigned long long)D, T, (unsigned long long)D * 2, AP_DH, 128))) return rc;
+  if (PAIR) {
+    if ((rc = make_tmap_2d_bf16(&tm_qkv_lo, qkv_lo, 3ull * D, T, 3ull * D * 2, AP_DH, 128))) return rc;
+    tm_do_lo = tm_qkv_lo;
+    if (BWD && (rc = make_tmap_2d_bf16(&tm_do_lo, dctx_lo, (unsigned long long)D, T, (unsigned long long)D * 2, AP_DH, 128))) return rc;
+  }
   AttPArgs a;
-  a.keymask = keymask; a.out = out; a.dbias = dbias; a.R = R; a.L = SLOT; a.D = D; a.H = H; a.drop = drop; a.scale = 0.125f;  // 1 / sqrt(64)
+  a.keymask = keymask; a.out = out; a.out_lo = out_lo; a.dbias = PAIR ? nullptr : dbias; a.R = R; a.L = SLOT; a.D = D; a.H = H; a.drop = drop;
+  a.scale = 0.125f;  // 1 / sqrt(64)
   a.tiles = (R + NS - 1) / NS;
-  const size_t smem = (size_t)(BWD ? 7 : 3) * AP_TILE + 64;
+  const size_t smem = (size_t)(BWD ? 7 : 3) * (PAIR ? 2 : 1) * AP_TILE + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_packed_kernel<BWD, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_packed_kernel<BWD, SLOT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  // grid: a multiple of H (every CTA keeps one head), at most (2 | 4) CTAs per SM, at most one CTA per (tile, head)
-  long long per_head = ((BWD ? 2LL : 4LL) * num_sms()) / H;
+  // grid: a multiple of H (every CTA keeps one head), at most (2 | 4) CTAs per SM (half that in split precision), at most one CTA per (tile, head)
+  long long per_head = (((BWD ? 2LL : 4LL) / (PAIR ? 2 : 1)) * num_sms()) / H;
   if (per_head < 1) per_head = 1;
   if (per_head > a.tiles) per_head = a.tiles;
   const int grid = (int)(per_head * H);
-  CLIPDLM_CUDA_OK(launch_pdl(attn_packed_kernel<BWD, SLOT>, dim3(grid), dim3(AP_THREADS), smem, st, tm_qkv, tm_do, a));
+  CLIPDLM_CUDA_OK(launch_pdl(attn_packed_kernel<BWD, SLOT, PAIR>, dim3(grid), dim3(AP_THREADS), smem, st, tm_qkv, tm_do, tm_qkv_lo, tm_do_lo, a));
   return 0;
 }
 
@@ -426,17 +497,25 @@ int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uin
 
 bool attn_packed_supported(int L, int D, int H) { return (L == 16 || L == 18) && D == H * AP_DH && H <= 64; }
 
-// forward: dctx / dbias unused.  backward: dbias (nullable) receives d(q bias) and d(v bias) (+= ; d(k bias) = 0 is not touched).
+// forward: dctx / dbias unused.  backward: dbias (nullable, plain bf16 only) receives d(q bias) and d(v bias) (+= ; d(k bias) = 0 is not touched).
+// qkv_lo != nullptr selects split precision (dctx_lo / out_lo are then required as well).
 template <bool BWD>
-int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int L, int D, int H,
-                       __nv_bfloat16* out, float* dbias, const DropoutCfg& drop, cudaStream_t st) {
+int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo,
+                       const uint32_t* keymask, int R, int L, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias,
+                       const DropoutCfg& drop, cudaStream_t st) {
   CLIPDLM_CHECK(attn_packed_supported(L, D, H), "packed attention: unsupported shape L %d D %d H %d", L, D, H);
-  if (L == 16) return launch_packed<BWD, 16>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
-  return launch_packed<BWD, 18>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
+  const bool pair = qkv_lo != nullptr;
+  CLIPDLM_CHECK(!pair || (out_lo != nullptr && (!BWD || dctx_lo != nullptr)), "packed attention: split precision needs every lo operand");
+  if (pair) {
+    if (L == 16) return launch_packed<BWD, 16, true>(qkv, qkv_lo, dctx, dctx_lo, keymask, R, D, H, out, out_lo, dbias, drop, st);
+    return launch_packed<BWD, 18, true>(qkv, qkv_lo, dctx, dctx_lo, keymask, R, D, H, out, out_lo, dbias, drop, st);
+  }
+  if (L == 16) return launch_packed<BWD, 16, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
+  return launch_packed<BWD, 18, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
 }
-template int launch_attn_packed<false>(const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int, int, __nv_bfloat16*, float*,
-                                       const DropoutCfg&, cudaStream_t);
-template int launch_attn_packed<true>(const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int, int, __nv_bfloat16*, float*,
-                                      const DropoutCfg&, cudaStream_t);
+template int launch_attn_packed<false>(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int,
+                                       int, __nv_bfloat16*, __nv_bfloat16*, float*, const DropoutCfg&, cudaStream_t);
+template int launch_attn_packed<true>(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const uint32_t*, int, int, int,
+                                      int, __nv_bfloat16*, __nv_bfloat16*, float*, const DropoutCfg&, cudaStream_t);
 
 }  // namespace clipdlm
