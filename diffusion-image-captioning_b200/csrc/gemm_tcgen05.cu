@@ -72,7 +72,22 @@ struct GemmArgs {
   const float* lse;          // SMGRAD: lse[M];  LSE_EXP: the exponent shift (device scalar, may be NULL);  STORE_ROWSCALE: row_scale[M]
   float grad_scale;          // (one slot for the three: GemmArgs keeps its layout, so the other instantiations compile to the same SASS)
   uint64_t pol_a, pol_b;     // L2 cache-policy operands of the plain 2-D TMA loads of A / B (0 = default policy)
+  int band;                  // > 0: tile order in bands of `band` row tiles, column tile outer / row tile inner within a band (tile_mn)
 };
+
+// Work item -> (row tile, column tile). Default: column tile fastest - the CTA pairs that run concurrently share a few A row tiles and
+// sweep all of B, right when B (a weight matrix) is small. Band order (lm_head passes: 120 column tiles of a 47 MB table, gigabytes of
+// output streaming through L2): the `band` pairs that run concurrently take `band` DIFFERENT row tiles of the SAME column tile, step by step -
+// a B tile is fetched once per band (7 x 47 MB per pass) and the band's A tiles (29 MB) stay L2-resident over the sweep, instead of B being
+// re-fetched whenever the output stream has pushed it out.
+__device__ __forceinline__ void tile_mn(const GemmArgs& g, int tile, int& m_blk, int& n_blk) {
+  if (g.band <= 0) { n_blk = tile % g.num_n_tiles; m_blk = tile / g.num_n_tiles; return; }
+  const int per_band = g.band * g.num_n_tiles;
+  const int b = tile / per_band, r = tile - b * per_band;
+  const int rows = min(g.band, g.num_m_tiles - b * g.band);
+  n_blk = r / rows;
+  m_blk = b * g.band + (r - n_blk * rows);
+}
 
 __device__ __forceinline__ long long map_row(const GemmArgs& g, int m) {
   return g.scatter_len > 0 ? (long long)(m / g.scatter_len) * g.scatter_stride + (m % g.scatter_len) : (long long)m;
@@ -387,7 +402,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       for (int w = unit0; w < total_items; w += unit_stride) {
         const int split = w % g.k_splits;
         const int tile = w / g.k_splits;
-        const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
+        int n_blk, m_blk;
+        tile_mn(g, tile, m_blk, n_blk);
         const int m0 = (m_blk * CG + cta_rank) * BM;           // first A row of this CTA
         const int n0 = n_blk * BN + cta_rank * G::BN_CTA;      // first B row this CTA stages
         const int kb0 = split * g.kb_per_split;
@@ -499,7 +515,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const uint32_t tempty0_leader = CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
     for (int w = unit0; w < total_items; w += unit_stride) {
       const int tile = w / g.k_splits;
-      const int n_blk = tile % g.num_n_tiles, m_blk = tile / g.num_n_tiles;
+      int n_blk, m_blk;
+      tile_mn(g, tile, m_blk, n_blk);
       const int row_base = (m_blk * CG + cta_rank) * BM + q * 32;
       const int m = row_base + lane;
 
@@ -1114,8 +1131,11 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   ga.gather_len = g->gather_len;
   // lm_head GEMMs (A gathered from x_out[:, :16] / output scattered back): B is the embedding table, re-read by every row tile while the
   // logits (written, or read exactly once as the A operand of the gradient GEMM) stream through L2 - keep the table, let the logits go
-  ga.pol_a = g->scatter_len > 0 ? L2_EVICT_FIRST : 0ull;
-  ga.pol_b = (g->gather_len > 0 || g->scatter_len > 0) ? L2_EVICT_LAST : 0ull;
+  // (measured, profiles/r02_ncu_launches_train_step.csv: evict_last on the table + evict_first on the streamed operand made the DRAM reads of the
+  // lm_head passes WORSE - 4.3 GB instead of 2.4 GB (LSE), 21 GB instead of 8 GB (gradient GEMM: its three column tiles re-read every A tile from
+  // L2, which evict_first defeats). The hints stay plumbed but off; the tile order below is what keeps the table resident.)
+  ga.pol_a = 0ull;
+  ga.pol_b = 0ull;
   ga.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192;
   ga.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
   ga.out_hi = (__nv_bfloat16*)g->out_hi; ga.out_lo = (__nv_bfloat16*)g->out_lo;
@@ -1198,6 +1218,11 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
 
   const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
   const int grid = total < units_max ? total : units_max;   // work units: CTAs (cg = 1) or CTA pairs (cg = 2)
+  // band order for the vocabulary-wide passes (LSE / LSE_EXP / SMGRAD: N = 120 column tiles): one band = the row tiles one wave of units takes
+  ga.band = 0;
+  if ((g->epilogue == CLIPDLM_EPI_LSE || g->epilogue == CLIPDLM_EPI_LSE_EXP || g->epilogue == CLIPDLM_EPI_SMGRAD) && ga.k_splits == 1 &&
+      ga.num_n_tiles >= 16 && ga.num_m_tiles > 1 && !(g_dbg_flags & 64u))
+    ga.band = grid < ga.num_m_tiles ? grid : ga.num_m_tiles;
 
   switch (g->epilogue) {
     case CLIPDLM_EPI_STORE:

@@ -18,9 +18,11 @@ def category(name: str) -> str:
     m = re.search(r"gemm_kernel<\(?(?:int\))?(\d), \(?(?:int\))?(\d), \(?(?:int\))?(\d)", name)
     if m:
         amaj, bmaj, epi = (int(x) for x in m.groups())
-        return {1: "gemm_wgrad", 2: "gemm_lse", 3: "gemm_smgrad"}.get(epi, "gemm_dgrad" if bmaj else "gemm_fwd")
+        return {1: "gemm_wgrad", 2: "gemm_lse", 3: "gemm_smgrad", 4: "gemm_lse"}.get(epi, "gemm_dgrad" if bmaj else "gemm_fwd")
     name = name.replace("(bool)", "")
-    for key, cat in (("softmax_grad_inplace", "gemm_smgrad"), ("attn_umma_kernel<0", "attn_fwd"), ("attn_umma_kernel<1", "attn_bwd"),
+    name = name.replace("(int)", "")
+    for key, cat in (("softmax_grad_inplace", "gemm_smgrad"), ("attn_packed_kernel<0", "attn_fwd"), ("attn_packed_kernel<1", "attn_bwd"),
+                     ("ce_row_terms", "loss"), ("attn_umma_kernel<0", "attn_fwd"), ("attn_umma_kernel<1", "attn_bwd"),
                      ("attn_ring_kernel<0", "attn_fwd"), ("attn_ring_kernel<1", "attn_bwd"), ("attn_fwd", "attn_fwd"),
                      ("attn_bwd", "attn_bwd"), ("layernorm_fwd", "ln_fwd"), ("layernorm_bwd", "ln_bwd"), ("embed_fwd", "embed"),
                      ("embed_loss", "loss"), ("lse_combine", "loss"), ("colsum", "colsum"), ("adamw", "adamw")):
@@ -34,6 +36,11 @@ def main():
     lines = [l for l in open(src) if not l.startswith("==")]
     per = collections.defaultdict(lambda: dict(n=0, ms=0.0, rd=0.0, wr=0.0))
     launches = collections.defaultdict(dict)
+    if lines and lines[0].startswith("id,kernel,time_us"):   # the compact per-launch table kept under profiles/ (one row per launch)
+        for row in csv.DictReader(lines):
+            launches[row["id"]] = {"name": row["kernel"], "gpu__time_duration.sum": float(row["time_us"]) * 1e-3,
+                                   "dram__bytes_read.sum": float(row["dram_read_mb"]) * 1e6, "dram__bytes_write.sum": float(row["dram_write_mb"]) * 1e6}
+        lines = []
     for row in csv.DictReader(lines):
         launches[row["ID"]]["name"] = row["Kernel Name"]
         v = float(row["Metric Value"].replace(",", ""))
