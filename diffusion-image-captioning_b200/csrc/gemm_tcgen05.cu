@@ -657,10 +657,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         const float nb = -shift * LOG2E;
         const int tgt = (m < g.M && g.targets != nullptr) ? g.targets[m % g.tgt_period] : -1;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, tl = 0.f; bool has_t = false;
+        // The 8 GB of bf16 exponentials per chunk leave through shared memory + TMA stores (two alternating [32 rows][64 columns] swizzled
+        // staging tiles per warp, as in epi_store_fast): the row-wise 64-byte stores of row_store_pair cost one L1 transaction per sector and
+        // kept this pass store-bound at ~1065 TFLOP/s whatever the tile order.
+        const bool tma = g.tma_out != 0;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           const int n0 = n_blk * BN + c * 32;
-          if (n0 >= g.N) break;
+          const int cc = c - c_lo;
+          if (n0 >= g.N && (!tma || (cc & 1) == 0)) break;   // (a staged pair is always completed: its second half is written as zeros)
           float v[32];
           tmem_ld32(taddr + c * 32, v);
           if ((unsigned)(tgt - n0) < 32u) {
@@ -674,7 +679,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (n0 + j) < g.N ? v[j] : 0.f;
           }
-          if (m < g.M) row_store_pair(g.out_hi + (long long)m * g.ldo + n0, nullptr, g.al32 != 0, v);
+          if (tma) {
+            const uint32_t buf = smem_u32(stg) + (uint32_t)((cc >> 1) * 4096);
+            if ((cc & 1) == 0) {
+              if (lane == 0) bulk_wait_read<1>();   // the store that last read this buffer (two commits ago) has drained it
+              __syncwarp();
+            }
+            stage_row32(buf, lane, cc & 1, v);
+            if (cc & 1) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tmO, buf, n_blk * BN + (c - 1) * 32, row_base); bulk_commit(); }   // rows >= M are clipped by the map
+            }
+          } else if (m < g.M) {
+            row_store_pair(g.out_hi + (long long)m * g.ldo + n0, nullptr, g.al32 != 0, v);
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
         }
@@ -1207,6 +1226,14 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   // bf16 outputs through TMA stores (box 64 columns x 32 rows out of the epilogue warps' swizzled staging tiles)
   CUtensorMap o0 = a0, o1 = a0;
   ga.tma_out = 0;
+  if (g->epilogue == CLIPDLM_EPI_LSE_EXP && g->out_hi && !(g_dbg_flags & 1024u) && g->ldo % 8 == 0 && g->ldo >= (long long)ga.num_n_tiles * BN) {
+    // the exponentials of the factored softmax gradient: [M][ldo] with the padding columns of the last vocabulary tile written as zeros
+    uint64_t dims[2] = {(uint64_t)ga.num_n_tiles * BN, (uint64_t)g->M};
+    uint64_t str[1] = {(uint64_t)g->ldo * 2};
+    uint32_t box[2] = {64, 32};
+    if ((rc = encode_map(&o0, g->out_hi, 2, dims, str, box))) return rc;
+    ga.tma_out = 1;
+  }
   if (ga.fast_mode >= 0 && g->scatter_len == 0 && !(g_dbg_flags & 1024u)) {
     uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
     uint64_t str[1] = {(uint64_t)g->ldo * 2};
@@ -1218,9 +1245,11 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
 
   const int total = ga.num_m_tiles * ga.num_n_tiles * ga.k_splits;
   const int grid = total < units_max ? total : units_max;   // work units: CTAs (cg = 1) or CTA pairs (cg = 2)
-  // band order for the vocabulary-wide passes (LSE / LSE_EXP / SMGRAD: N = 120 column tiles): one band = the row tiles one wave of units takes
+  // band order for the vocabulary-wide passes (LSE / LSE_EXP: N = 120 column tiles): one band = the row tiles one wave of units takes
   ga.band = 0;
-  if ((g->epilogue == CLIPDLM_EPI_LSE || g->epilogue == CLIPDLM_EPI_LSE_EXP || g->epilogue == CLIPDLM_EPI_SMGRAD) && ga.k_splits == 1 &&
+  // (measured on one box, tools/gemm_perf.py --flags 0,64 at 8192 rows: LSE 4.51 vs 4.95 ms, LSE_EXP with its 8 GB output 5.63 vs 5.71 ms; the
+  // split-precision SMGRAD recompute pass was 10 % SLOWER in band order - three operand passes per tile - and keeps the default order)
+  if ((g->epilogue == CLIPDLM_EPI_LSE || g->epilogue == CLIPDLM_EPI_LSE_EXP) && ga.k_splits == 1 &&
       ga.num_n_tiles >= 16 && ga.num_m_tiles > 1 && !(g_dbg_flags & 64u))
     ga.band = grid < ga.num_m_tiles ? grid : ga.num_m_tiles;
 

@@ -2,7 +2,7 @@
 """Micro-benchmark of the GEMM shapes one train chunk launches (T = 4096 rows x 18 positions = 73 728 tokens), through the C-ABI,
 next to torch.matmul (cuBLAS) on the bare shape. Triage tool, not a bench line:  python tools/gemm_perf.py [--flags 0,1,2,4] [--rows 4096]
 
-flags: clipdlm_gemm_debug_flags bits (1 = no epilogue stores, 2 = no aux loads, 4 = TMEM drain only)."""
+flags: clipdlm_gemm_debug_flags bits (1 = no epilogue stores, 2 = no aux loads, 4 = TMEM drain only, 64 = no band tile order in the lm_head passes)."""
 import argparse
 import ctypes as C
 import os
@@ -90,6 +90,7 @@ def main():
         ("wgrad qkv", 2 * T * 3 * D * D, dict(a_hi=x2304, b_hi=x768, lda=3 * D, ldb=D, M=3 * D, N=D, K=T, a_major=1, b_major=1, epilogue=1, acc_f32=accs["qkv"], ldo=D), (x2304.t(), x768)),
         ("wgrad o", 2 * T * D * D, dict(a_hi=x768, b_hi=x768, lda=D, ldb=D, M=D, N=D, K=T, a_major=1, b_major=1, epilogue=1, acc_f32=accs["o"], ldo=D), (x768.t(), x768)),
         ("lm_head LSE", 2 * M16 * V * D, dict(a_hi=x768, b_hi=E, lda=D, ldb=D, M=M16, N=V, K=D, gather_len=16, gather_stride=18, epilogue=2, part_max=pm, part_sum=ps, part_arg=pa, tgt_logit=tl, targets=tgt, tgt_period=512 * 16), None),
+        ("lm_head LSE_EXP + bf16 exp out", 2 * M16 * V * D, dict(a_hi=x768, b_hi=E, lda=D, ldb=D, M=M16, N=V, K=D, gather_len=16, gather_stride=18, epilogue=4, part_max=pm, part_sum=ps, tgt_logit=tl, targets=tgt, tgt_period=512 * 16, out_hi=dlog, ldo=VP), None),
         ("lm_head SMGRAD", 2 * M16 * V * D, dict(a_hi=x768, b_hi=E, lda=D, ldb=D, M=M16, N=V, K=D, gather_len=16, gather_stride=18, epilogue=3, out_hi=dlog, ldo=VP, lse=lse, targets=tgt, tgt_period=512 * 16, grad_scale=1e-3), None),
         ("lm_head dgrad scatter+res", 2 * M16 * V * D, dict(a_hi=dlog, b_hi=E, lda=VP, ldb=D, M=M16, N=D, K=V, b_major=1, out_hi=o768, ldo=D, res_hi=o768, ldr=D, scatter_len=16, scatter_stride=18), None),
     ]
