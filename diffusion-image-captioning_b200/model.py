@@ -258,6 +258,7 @@ class DistilBertModel(torch.nn.Module):
             self._launches_retired += int(lib.clipdlm_engine_launch_count(e[0]))
             lib.clipdlm_engine_destroy(e[0])
         self._engines = {}
+        self.__dict__.pop("_sample_graphs", None)
         flat.copy_(self.flat); grad.copy_(self.grad); shadow_hi.copy_(self.shadow_hi)
         if self.shadow_lo is not None:
             shadow_lo.copy_(self.shadow_lo)
@@ -486,6 +487,7 @@ class DistilBertModel(torch.nn.Module):
         h = lib.clipdlm_engine_create(C.byref(self._cfg), C.byref(bufs), rows, batch, 1 if training else 0)
         if not h:
             raise L.ClipdlmError("engine_create failed: " + lib.clipdlm_last_error().decode())
+        self.__dict__.pop("_sample_graphs", None)   # CUDA graphs of sample() hold raw pointers into engine workspaces: a new engine invalidates them
         self._engines[key] = (h, rows, batch, ws)
         if self.fused_softmax_grad and self._exp_shift is None:
             self._exp_shift = torch.zeros(1, device=self.device)

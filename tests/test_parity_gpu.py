@@ -555,3 +555,26 @@ def test_real_width_speed_mode_vs_reference(pkg, record_property):
         if float(ref.norm()) > 1e-3 * ref_norm:
             cos = float((mine * ref).sum() / (mine.norm() * ref.norm()))
             assert cos > 0.99, (n, cos)
+
+
+def test_sample_cuda_graph_replay_matches_eager_launches(pkg):
+    """sample() replays one CUDA graph per (B, n_steps) for small batches (the reference's evaluation shape is B = 8 x 5 steps, :613-617): same
+    ids / restored as the plain launch sequence, on fresh inputs at every replay, per-step ids with return_all, and after the engine has been
+    regrown by a larger batch in between (a stale graph would read a freed workspace)."""
+    hp = golden_hp(BATCH_SIZE=8)
+    model = make_model(pkg, hp, precision="bf16").eval()
+    g = torch.Generator().manual_seed(3)
+    for rep in range(3):
+        img = torch.nn.functional.normalize(torch.randn(8, 512, generator=g), dim=-1).to(DEV)
+        restored = torch.randn(8, 18, 768, generator=g).to(DEV)
+        ids_g, cur_g, outs_g = pkg.sample(model, img, n_steps=5, restored=restored, return_all=True, use_graph=True)
+        ids_e, cur_e, outs_e = pkg.sample(model, img, n_steps=5, restored=restored, return_all=True, use_graph=False)
+        assert torch.equal(ids_g, ids_e) and torch.equal(cur_g, cur_e) and len(outs_g) == 5
+        assert all(torch.equal(a, b) for a, b in zip(outs_g, outs_e))
+        if rep == 1:   # regrow the inference engine, then come back to the small batch
+            big = torch.nn.functional.normalize(torch.randn(40, 512, generator=g), dim=-1).to(DEV)
+            a, _ = pkg.sample(model, big, n_steps=2, restored=torch.zeros(40, 18, 768, device=DEV) + 0.1)
+            b, _ = pkg.sample(model, big, n_steps=2, restored=torch.zeros(40, 18, 768, device=DEV) + 0.1, use_graph=False)
+            assert torch.equal(a, b)
+    ids_d, _ = pkg.sample(model, img, n_steps=5, restored=restored)   # default: graph on for B <= 256
+    assert torch.equal(ids_d, ids_g) and len(model._sample_graphs) >= 1
