@@ -88,6 +88,12 @@ int main(void) {
   clipdlm_buffers_t bufs = {params, grads, shadow, NULL, emb, emb_bf, NULL, ws, ws_bytes};
   clipdlm_engine_t* eng = clipdlm_engine_create(&cfg, &bufs, R, B, 1);
   if (!eng) { fprintf(stderr, "engine_create: %s\n", clipdlm_last_error()); return 1; }
+  if (getenv("C_HOST_FUSED") && atoi(getenv("C_HOST_FUSED"))) {
+    /* the options the Python host switches on by default in plain bf16: factored softmax-CE gradient of the lm_head (exponent shift 0 without
+       CLIPDLM_OPT_EXP_SHIFT_PTR) and gelu'(u) stored by lin1's epilogue + lin1's bias gradient summed in the lin2 gradient GEMM */
+    LK(clipdlm_engine_set_option(eng, CLIPDLM_OPT_FUSED_SOFTMAX_GRAD, 1));
+    LK(clipdlm_engine_set_option(eng, CLIPDLM_OPT_GELU_DERIV_STORE, 2));
+  }
   clipdlm_pass_t pass;
   memset(&pass, 0, sizeof(pass));
   pass.R = R; pass.B = B; pass.mode = 1; pass.train = 1;

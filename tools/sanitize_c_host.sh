@@ -15,11 +15,13 @@ rc=0
 : > "$LOG"
 for tool in ${SANITIZE_TOOLS:-memcheck}; do
   for p in ${SANITIZE_DROPOUTS:-0.1 0}; do
-    echo "===== $tool, dropout $p =====" >> "$LOG"
-    C_HOST_DROPOUT=$p timeout "${SANITIZE_TIMEOUT:-30}" "$CUDA/bin/compute-sanitizer" --tool "$tool" --error-exitcode 9 --print-limit 10 /tmp/c_host_sanitize >> "$LOG" 2>&1
+   for fused in ${SANITIZE_FUSED:-1 0}; do   # 1 = the fused lm_head / gelu' options of the Python host's default path, 0 = the C-ABI defaults
+    echo "===== $tool, dropout $p, fused options $fused =====" >> "$LOG"
+    C_HOST_FUSED=$fused C_HOST_DROPOUT=$p timeout "${SANITIZE_TIMEOUT:-30}" "$CUDA/bin/compute-sanitizer" --tool "$tool" --error-exitcode 9 --print-limit 10 /tmp/c_host_sanitize >> "$LOG" 2>&1
     r=$?
     echo "exit code $r" >> "$LOG"
     [ $r -ne 0 ] && rc=$r
+   done
   done
 done
 grep -v "^=========     \|^=========$" "$LOG" | tail -n 60
