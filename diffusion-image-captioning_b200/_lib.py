@@ -91,6 +91,7 @@ class LossCfg(C.Structure):
         ("rounding_weight", f32), ("backward", i32),
         ("target", c_p), ("target_rows", i32),
         ("row_scale_self", c_p), ("row_scale_export", c_p), ("export_engine", c_p),
+        ("rounding_weight_dev", c_p),
     ]
 
 

@@ -20,7 +20,8 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st);
 int lse_combine_dispatch(const float* pmax, const float* psum, const int* parg, int n_tiles, int M, const float* tgt_logit, float* lse,
                          int* argmax, double* loss_acc, double scale, cudaStream_t st);
 int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
-                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st);
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st,
+                          const float* scale_mul);
 void gemm_debug_mn_desc(uint32_t lbo, uint32_t sbo);
 void gemm_debug_flags(uint32_t flags);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
@@ -81,7 +82,7 @@ int clipdlm_ce_row_terms(const float* lse, const float* exp_shift, const int32_t
                          const void* w_bf16, int64_t ldw, void* dx_bf16, int64_t ldx, int32_t scatter_len, int32_t scatter_stride, int32_t D,
                          float* row_scale, clipdlm_stream stream) {
   return ce_row_terms_dispatch(lse, exp_shift, targets, tgt_period, scale, M, w_bf16, ldw, dx_bf16, ldx, scatter_len, scatter_stride, D, row_scale,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, nullptr);
 }
 
 #define ST ((cudaStream_t)stream)

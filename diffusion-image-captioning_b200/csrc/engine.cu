@@ -18,7 +18,7 @@ int cfg_mix_dispatch(const clipdlm_bf_t* xu, const clipdlm_bf_t* xg, const int* 
 int row_scale_dispatch(const clipdlm_bf_t* g, const float* s_self, const clipdlm_bf_t* ex, const float* s_ex, int R, int L, int D,
                        cudaStream_t st);
 int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, const float* lse, const int* targets, int tgt_period, float scale,
-                                  cudaStream_t st);
+                                  cudaStream_t st, const float* scale_mul);
 int embed_fwd_dispatch(const clipdlm_embed_t* e, cudaStream_t st);
 int embed_bwd_dispatch(const clipdlm_bf_t* dz, int R, int B, int Ltxt, int L, int D, int fusion, int guided, float* d_pos, float* d_seg,
                        float* d_img, float* d_txt, cudaStream_t st);
@@ -30,7 +30,8 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
                            cudaStream_t st);
 int colsum_dispatch(const clipdlm_bf_t* x, long long rows, int N, float* out, cudaStream_t st);
 int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
-                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st);
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st,
+                          const float* scale_mul);
 int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* ids, const float* tgt, int tgt_rows, int R, int B, int Ltxt,
                         int L, int D, int kind, long long R_total, int batch_size, float weight, double* loss_acc, const clipdlm_bf_t* dx,
                         cudaStream_t st);
@@ -501,7 +502,8 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
       const float gs = (float)(lc->rounding_weight * ce_scale);
       // row factors into the (now free) target-logit buffer; one-hot term folded into d(x_out) rows, which already hold the embedding-loss gradient
       RUNP(CLIPDLM_PROF_LOSS, 0, (double)M16 * D * 6.0,
-           ce_row_terms_dispatch(e->lse, e->exp_shift, p.ids, B * Ltxt, gs, M16, e->bufs.emb_hi, D, e->g0.hi, D, Ltxt, L, D, e->tgt_logit, st));
+           ce_row_terms_dispatch(e->lse, e->exp_shift, p.ids, B * Ltxt, gs, M16, e->bufs.emb_hi, D, e->g0.hi, D, Ltxt, L, D, e->tgt_logit, st,
+                                 lc->rounding_weight_dev));
       Act emb{e->bufs.emb_hi, nullptr};
       clipdlm_gemm_t g = gemm_desc(e->dlog, e->ldl, 0, emb, D, 1, M16, D, c.vocab);
       g.epilogue = CLIPDLM_EPI_STORE_ROWSCALE;
@@ -515,7 +517,8 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
       clipdlm_gemm_t g;
       if (store_logits) {
         RUNP(CLIPDLM_PROF_GEMM_SMGRAD, 0, 4.0 * M16 * (double)e->ldl,
-             softmax_grad_inplace_dispatch(e->dlog.hi, e->ldl, M16, c.vocab, e->lse, p.ids, B * Ltxt, (float)(lc->rounding_weight * ce_scale), st));
+             softmax_grad_inplace_dispatch(e->dlog.hi, e->ldl, M16, c.vocab, e->lse, p.ids, B * Ltxt, (float)(lc->rounding_weight * ce_scale), st,
+                                           lc->rounding_weight_dev));
       } else {
         g = gemm_desc(e->xo, D, 0, emb, D, 0, M16, c.vocab, D);
         g.gather_len = Ltxt; g.gather_stride = L;
@@ -523,6 +526,7 @@ static int loss_backward_impl(clipdlm_engine* e, const clipdlm_loss_cfg_t* lc, d
         g.out_hi = e->dlog.hi; g.out_lo = e->dlog.lo; g.ldo = e->ldl;
         g.lse = e->lse; g.targets = p.ids; g.tgt_period = B * Ltxt;
         g.grad_scale = (float)(lc->rounding_weight * ce_scale);
+        g.part_max = const_cast<float*>(lc->rounding_weight_dev);   // SMGRAD: optional device scalar multiplying grad_scale (clipdlm.h)
         RUNG(g);
       }
       // d x_out[:, :Ltxt] += dlogits[M16, V] E[V, D]

@@ -717,7 +717,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             constexpr float LOG2E = 1.4426950408889634f;
             const int tgt = (m < g.M) ? g.targets[m % g.tgt_period] : -1;
             const float l = (m < g.M) ? g.lse[m] : 0.f;
-            const float nb = g.grad_scale > 0.f ? fmaf(-l, LOG2E, __log2f(g.grad_scale)) : -INFINITY;
+            const float gsc = g.part_max != nullptr ? g.grad_scale * *g.part_max : g.grad_scale;   // optional device-resident multiplier
+            const float nb = gsc > 0.f ? fmaf(-l, LOG2E, __log2f(gsc)) : -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ex2_ftz(fmaf(v[j], LOG2E, nb));
             if (n0 + 32 > g.N) {   // zero the padding columns of the vocabulary tail
@@ -726,7 +727,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             }
             if ((unsigned)(tgt - n0) < 32u) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (n0 + j == tgt) v[j] -= g.grad_scale;
+              for (int j = 0; j < 32; ++j) if (n0 + j == tgt) v[j] -= gsc;
             }
             if (valid) row_store_pair(g.out_hi + mr * g.ldo + n0, g.out_lo ? g.out_lo + mr * g.ldo + n0 : nullptr, al32, v);
           } else {  // STORE
@@ -863,7 +864,12 @@ __global__ void lse_combine_kernel(const float* __restrict__ pmax, const float* 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_grad_inplace_kernel(__nv_bfloat16* __restrict__ x, long long ld, int M, int N,
                                                                    const float* __restrict__ lse, const int* __restrict__ targets, int tgt_period,
-                                                                   float scale, float log2_scale) {
+                                                                   float scale, float log2_scale, const float* __restrict__ scale_mul) {
+  if (scale_mul != nullptr) {   // device-resident multiplier of the gradient scale (dynamic rounding weight)
+    const float mul = *scale_mul;
+    scale *= mul;
+    log2_scale = mul > 0.f ? log2_scale + __log2f(mul) : -INFINITY;
+  }
   constexpr float LOG2E = 1.4426950408889634f;
   constexpr int U = 5;   // 16-byte vectors in flight per thread (5 x 2048 threads x 16 B = 160 KB per SM outstanding)
   const int vec_per_row = (int)(ld >> 3);
@@ -904,7 +910,7 @@ __global__ void __launch_bounds__(256) softmax_grad_inplace_kernel(__nv_bfloat16
 }
 
 int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, const float* lse, const int* targets, int tgt_period, float scale,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const float* scale_mul) {
   CLIPDLM_CHECK(logits && lse && targets && M > 0 && N > 0 && ld >= N && ld % 8 == 0 && tgt_period > 0, "softmax_grad_inplace: bad arguments");
   CLIPDLM_CHECK((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "softmax_grad_inplace: buffer must be 16-byte aligned");
   int sms = 148;
@@ -912,7 +918,7 @@ int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, cons
   long long blocks = M;
   if (blocks > 8LL * sms) blocks = 8LL * sms;
   softmax_grad_inplace_kernel<<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)logits, ld, M, N, lse, targets, tgt_period, scale,
-                                                                scale > 0.f ? log2f(scale) : -INFINITY);
+                                                                scale > 0.f ? log2f(scale) : -INFINITY, scale_mul);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -924,7 +930,9 @@ int softmax_grad_inplace_dispatch(void* logits, long long ld, int M, int N, cons
 __global__ void __launch_bounds__(128) ce_row_terms_kernel(const float* __restrict__ lse, const float* __restrict__ exp_shift,
                                                            const int* __restrict__ targets, int tgt_period, float scale, int M,
                                                            const __nv_bfloat16* __restrict__ W, long long ldw, __nv_bfloat16* __restrict__ dx,
-                                                           long long ldx, int scatter_len, int scatter_stride, int D, float* __restrict__ row_scale) {
+                                                           long long ldx, int scatter_len, int scatter_stride, int D, float* __restrict__ row_scale,
+                                                           const float* __restrict__ scale_mul) {
+  if (scale_mul != nullptr) scale *= *scale_mul;   // device-resident multiplier of the gradient scale (dynamic rounding weight)
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -951,13 +959,14 @@ __global__ void __launch_bounds__(128) ce_row_terms_kernel(const float* __restri
 }
 
 int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
-                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st) {
+                          long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st,
+                          const float* scale_mul) {
   CLIPDLM_CHECK(lse && targets && w && dx && row_scale && M > 0 && tgt_period > 0 && D > 0, "ce_row_terms: bad arguments");
   CLIPDLM_CHECK(D % 8 == 0 && ldw % 8 == 0 && ldx % 8 == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
                 "ce_row_terms: rows must be 16-byte aligned (D, pitches multiples of 8 elements)");
   CLIPDLM_CHECK(scatter_len >= 0 && (scatter_len == 0 || scatter_stride >= scatter_len), "ce_row_terms: bad scatter %d / %d", scatter_len, scatter_stride);
   ce_row_terms_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(lse, exp_shift, targets, tgt_period, scale, M, (const __nv_bfloat16*)w, ldw,
-                                                              (__nv_bfloat16*)dx, ldx, scatter_len, scatter_stride, D, row_scale);
+                                                              (__nv_bfloat16*)dx, ldx, scatter_len, scatter_stride, D, row_scale, scale_mul);
   CLIPDLM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1226,7 +1235,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   // bf16 outputs through TMA stores (box 64 columns x 32 rows out of the epilogue warps' swizzled staging tiles)
   CUtensorMap o0 = a0, o1 = a0;
   ga.tma_out = 0;
-  if (g->epilogue == CLIPDLM_EPI_LSE_EXP && g->out_hi && !(g_dbg_flags & 1024u) && g->ldo % 8 == 0 && g->ldo >= (long long)ga.num_n_tiles * BN) {
+  if (g->epilogue == CLIPDLM_EPI_LSE_EXP && g->out_hi && !(g_dbg_flags & (1024u | 2048u)) && g->ldo % 8 == 0 && g->ldo >= (long long)ga.num_n_tiles * BN) {
     // the exponentials of the factored softmax gradient: [M][ldo] with the padding columns of the last vocabulary tile written as zeros
     uint64_t dims[2] = {(uint64_t)ga.num_n_tiles * BN, (uint64_t)g->M};
     uint64_t str[1] = {(uint64_t)g->ldo * 2};
@@ -1250,7 +1259,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   // (measured on one box, tools/gemm_perf.py --flags 0,64 at 8192 rows: LSE 4.51 vs 4.95 ms, LSE_EXP with its 8 GB output 5.63 vs 5.71 ms; the
   // split-precision SMGRAD recompute pass was 10 % SLOWER in band order - three operand passes per tile - and keeps the default order)
   if ((g->epilogue == CLIPDLM_EPI_LSE || g->epilogue == CLIPDLM_EPI_LSE_EXP) && ga.k_splits == 1 &&
-      ga.num_n_tiles >= 16 && ga.num_m_tiles > 1 && !(g_dbg_flags & 64u))
+      ga.num_n_tiles >= 16 && ga.num_m_tiles > 1 && !(g_dbg_flags & 4096u))
     ga.band = grid < ga.num_m_tiles ? grid : ga.num_m_tiles;
 
   switch (g->epilogue) {

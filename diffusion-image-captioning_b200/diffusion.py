@@ -113,9 +113,10 @@ def _loss_pass(model: DistilBertModel, eng, losses: torch.Tensor, slot: int, *, 
             gm = cfg_rows.to(torch.float32)
             s_self = (1.0 - (1.0 + w) * gm).contiguous()   # unguided pass: 1 on plain rows, -w on guided rows
             s_exp = ((1.0 + w) * gm).contiguous()          # guided pass: (1 + w) on guided rows, 0 elsewhere
+    rw_host, rw_dev = model.rounding_weight()
     lc = L.LossCfg(LOSS_KIND[hp["LOSS_FUNC"]], 1 if use_embed else 0, 1 if hp["USE_PROB_LOSS"] else 0, hp["BATCH_SIZE"], R_total,
-                   float(hp["ROUNDING_WEIGHT"]), 1 if backward else 0, L.ptr(target), target_rows,
-                   L.ptr(s_self), L.ptr(s_exp), eng_guided if (cfg_rows is not None and backward) else None)
+                   rw_host, 1 if backward else 0, L.ptr(target), target_rows,
+                   L.ptr(s_self), L.ptr(s_exp), eng_guided if (cfg_rows is not None and backward) else None, L.ptr(rw_dev))
     with torch.cuda.device(model.device):
         L.check(lib.clipdlm_engine_loss_backward(eng, C.byref(lc), losses.data_ptr() + 8 * slot, model._stream()))
         if cfg_rows is not None and backward:
@@ -128,7 +129,8 @@ def _finish(model, losses):
     hp = model.hp
     lf = losses.float()
     x_t_loss, x_1_loss = lf[0], lf[2]
-    prob_loss = float(hp["ROUNDING_WEIGHT"]) * (lf[1] + lf[3])  # CLIP-DDPM.py:445
+    rw_host, rw_dev = model.rounding_weight()
+    prob_loss = (rw_host if rw_dev is None else rw_dev.reshape(())) * (lf[1] + lf[3])  # CLIP-DDPM.py:445
     return x_t_loss, x_1_loss, prob_loss
 
 
@@ -381,9 +383,17 @@ def train(model: DistilBertModel, trainer: AdamW, train_loader, hp: Optional[dic
             l, x_t_loss, x_1_loss, prob_loss = train_func(model, trainer, x)
             acc_x_t, acc_x_1, acc_prob, acc_l = acc_x_t + x_t_loss, acc_x_1 + x_1_loss, acc_prob + prob_loss, acc_l + l
             n_batches += 1
-            if hp["DYNAMIC_ROUNDING_WEIGHT"] > 0:  # :535-536 (the kernels take the weight by value: one scalar read-back per step in this mode)
+            if hp["DYNAMIC_ROUNDING_WEIGHT"] > 0:  # :535-536: a device tensor in the reference, a device tensor here - no read-back, the kernels multiply by it
                 g_x_t, g_x_1, g_prob = _global_mean(acc_x_t, acc_x_1, acc_prob)
-                model.hp["ROUNDING_WEIGHT"] = float(((g_x_t + g_x_1) / g_prob).item() * hp["DYNAMIC_ROUNDING_WEIGHT"])
+                rw = ((g_x_t + g_x_1) / g_prob).detach() * hp["DYNAMIC_ROUNDING_WEIGHT"]
+                if torch.is_tensor(rw) and rw.is_cuda:
+                    buf = model.__dict__.get("_rw_dev")
+                    if buf is None:
+                        buf = model.__dict__["_rw_dev"] = torch.empty(1, device=rw.device)   # one address for the life of the model
+                    buf.copy_(rw.float().reshape(1))
+                    model.hp["ROUNDING_WEIGHT"] = buf
+                else:   # host-side stand-ins (tests of the loop logic)
+                    model.hp["ROUNDING_WEIGHT"] = float(rw)
             if hp["DEBUG"]:
                 break
         # the reference divides by len(train_loader) (:547,554), also when DEBUG cut the epoch after one batch

@@ -442,7 +442,8 @@ class DistilBertModel(torch.nn.Module):
         return self
 
     def __getstate__(self):
-        return {"clipdlm_module": 1, "hp": dict(self.hp), "ctor": dict(self._ctor), "training": self.training,
+        hp = {k: (float(v) if torch.is_tensor(v) else v) for k, v in self.hp.items()}   # a device-resident dynamic ROUNDING_WEIGHT pickles as its value
+        return {"clipdlm_module": 1, "hp": hp, "ctor": dict(self._ctor), "training": self.training,
                 "state_dict": {k: v.cpu() for k, v in self.state_dict().items()}}
 
     def __setstate__(self, st):
@@ -509,6 +510,14 @@ class DistilBertModel(torch.nn.Module):
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._scr[name] = t
         return t[:n].view(shape)
+
+    def rounding_weight(self):
+        """ROUNDING_WEIGHT as (host factor, device scalar or None). A float (the reference's default, CLIP-DDPM.py:75) goes to the kernels by value; a
+        tensor - what the reference's dynamic rounding weight is (:535-536) - stays on the device: the kernels multiply by it, nothing is read back."""
+        rw = self.hp["ROUNDING_WEIGHT"]
+        if torch.is_tensor(rw):
+            return 1.0, rw.detach().to(self.device, torch.float32).reshape(1)
+        return float(rw), None
 
     def launch_count(self) -> int:
         """Kernel launches issued by this model's engines so far (bench `gpu_launches`)."""

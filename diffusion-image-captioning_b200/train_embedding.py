@@ -190,8 +190,10 @@ def loss_pass(model, eng, losses: torch.Tensor, slot: int, *, x16, R, B, R_total
             d_hi = model._scratch("te_dlog_hi", (T16, ldl), torch.bfloat16)
             d_lo = model._scratch("te_dlog_lo", (T16, ldl), torch.bfloat16) if model.precision == "bf16x3" else None
             w_hi, w_lo = _lm_shadow(model)
+            rw_host, rw_dev = model.rounding_weight()   # (a device-resident dynamic weight multiplies grad_scale inside the epilogue)
             _gemm(model, a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, lda=CH_PAD, ldb=CH_PAD, M=T16, N=V, K=CH_PAD, epilogue=L.EPI_SMGRAD,
-                  out_hi=d_hi, out_lo=d_lo, ldo=ldl, lse=lse, targets=ids32, tgt_period=B * ML, grad_scale=float(hp["ROUNDING_WEIGHT"]) * ce_scale)
+                  out_hi=d_hi, out_lo=d_lo, ldo=ldl, lse=lse, targets=ids32, tgt_period=B * ML, grad_scale=rw_host * ce_scale,
+                  **({"part_max": rw_dev} if rw_dev is not None else {}))
             dce = model._scratch("te_dce", (T16, CH_PAD), torch.float32)
             # d y[:, :ML] = dlogits [T16, V] W [V, ch]   (W read in place as an MN-major operand)
             _gemm(model, a_hi=d_hi, a_lo=d_lo, b_hi=w_hi, b_lo=w_lo, lda=ldl, ldb=CH_PAD, M=T16, N=CH_PAD, K=V, a_major=0, b_major=1,

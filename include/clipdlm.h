@@ -79,7 +79,7 @@ typedef struct clipdlm_gemm {
   float* tgt_logit;               /* [M] */
   const int32_t* targets; int32_t tgt_period; /* target of row m = targets[m % tgt_period] */
   const float* lse;               /* [M] (SMGRAD) */
-  float grad_scale;               /* SMGRAD */
+  float grad_scale;               /* SMGRAD (part_max, unused by this epilogue otherwise, may point to ONE device float multiplying it: NULL = 1) */
   const float* exp_shift;         /* LSE_EXP: device scalar c (natural-log units), NULL = 0 */
   const float* row_scale;         /* STORE_ROWSCALE: [M] fp32, indexed by the GEMM row m (before scatter) */
 } clipdlm_gemm_t;
@@ -342,6 +342,10 @@ typedef struct clipdlm_loss_cfg {
   const float* row_scale_self;    /* [R] device, or NULL */
   const float* row_scale_export;  /* [R] device, or NULL */
   clipdlm_engine_t* export_engine;
+  /* Optional DEVICE scalar multiplying rounding_weight in the cross-entropy gradient (NULL = 1): the reference's dynamic rounding weight
+   * (CLIP-DDPM.py:535-536) is a tensor recomputed every step from the running loss sums; with it on the device no step ever reads a
+   * scalar back to the host. (The loss VALUES are returned unweighted either way.) */
+  const float* rounding_weight_dev;
 } clipdlm_loss_cfg_t;
 int clipdlm_engine_loss_backward(clipdlm_engine_t* e, const clipdlm_loss_cfg_t* lc, double* losses, clipdlm_stream stream);
 /* x_out(e_unguided)[r] <- guided[r] ? (1 + w) * x_out(e_guided)[r] - w * x_out(e_unguided)[r] : unchanged, over the R rows of the two

@@ -578,3 +578,56 @@ def test_sample_cuda_graph_replay_matches_eager_launches(pkg):
             assert torch.equal(a, b)
     ids_d, _ = pkg.sample(model, img, n_steps=5, restored=restored)   # default: graph on for B <= 256
     assert torch.equal(ids_d, ids_g) and len(model._sample_graphs) >= 1
+
+
+@pytest.mark.parametrize("mode", ["bf16-factored", "bf16-inplace", "bf16x3", "bf16x3-train-embedding"])
+def test_device_resident_rounding_weight_matches_the_host_value(pkg, mode):
+    """the reference's dynamic ROUNDING_WEIGHT is a tensor (CLIP-DDPM.py:535-536). A device-resident weight must give the losses
+    and gradients of the same value passed as a Python float, on every softmax-gradient path (factored, in-place, split-precision recompute,
+    TRAIN_EMBEDDING's own lm_head) - the kernels multiply by the device scalar, no step reads it back."""
+    te = mode.endswith("train-embedding")
+    hp = golden_hp(**(dict(TRAIN_EMBEDDING=True, IN_CHANNEL=16) if te else {}))
+    P = O.init_params(hp, seed=0, closed_form=True)
+    inp = golden_inputs(hp)
+    res = {}
+    for kind in ("float", "tensor"):
+        cfg = pkg.DistilBertConfig(n_layers=hp["N_LAYERS"], dropout=0.0, attention_dropout=0.0)
+        emb = None if te else P["embedding.weight"]
+        model = pkg.DistilBertModel(emb, emb, cfg, hp=hp, precision=mode.split("-")[0], chunk_rows=6,
+                                    fused_softmax_grad=(mode == "bf16-factored")).train()
+        model.load_state_dict({k: v.detach() for k, v in P.items()})
+        model.hp["ROUNDING_WEIGHT"] = 0.37 if kind == "float" else torch.tensor([0.37], device=DEV)
+        trainer = pkg.AdamW(model.parameters(), lr=1e-4)
+        snap = {}
+        trainer.step = lambda m=model, s=snap: s.update(g=m.grad.clone())
+        losses = pkg.train_func(model, trainer, to_dev(inp["batch"]), t=inp["t"], noise_t=inp["noise_t"], noise_1=inp["noise_1"], dropout_seed=3)
+        res[kind] = ([x.item() for x in losses], snap["g"].double())
+    for a, b in zip(res["float"][0], res["tensor"][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), (res["float"][0], res["tensor"][0])
+    assert rel(res["tensor"][1], res["float"][1]) < (2e-3 if mode.startswith("bf16-") else 1e-5)   # (bf16: the weight enters before a bf16 rounding)
+    assert float(res["float"][1].norm()) > 0
+
+
+def test_epoch_loop_keeps_the_dynamic_rounding_weight_on_the_device(pkg):
+    """train() with DYNAMIC_ROUNDING_WEIGHT > 0 (:535-536): after every step ROUNDING_WEIGHT = (sum x_t + sum x_1) / sum prob * C, held in ONE device
+    buffer the loss kernels read."""
+    hp = golden_hp(DYNAMIC_ROUNDING_WEIGHT=0.3, EPOCH_NUM=1, BATCH_SIZE=3, SAMPLE_SIZE=4)
+    P = O.init_params(hp, seed=0, closed_form=True)
+    model = make_model(pkg, hp, precision="bf16").train()
+    trainer = pkg.AdamW(model.parameters(), lr=1e-4)
+    batches = [to_dev(O.closed_form_batch(hp, k)) for k in range(3)]
+    seen = []
+    orig = pkg.train_func
+    import clipdlm.diffusion as D
+    def spy(m, tr, x, *a, **kw):
+        seen.append(m.hp["ROUNDING_WEIGHT"])
+        return orig(m, tr, x, *a, **kw)
+    D.train_func, keep = spy, D.train_func
+    try:
+        hist = pkg.train(model, trainer, batches)
+    finally:
+        D.train_func = keep
+    assert isinstance(seen[0], float) and torch.is_tensor(seen[1]) and seen[1].is_cuda and seen[1].data_ptr() == seen[2].data_ptr()
+    rec = hist[0]
+    want = (rec["x_t_loss"] + rec["x_1_loss"]) / rec["prob_loss"] * 0.3   # the epoch averages share the 1 / n_batches factor
+    assert abs(float(model.hp["ROUNDING_WEIGHT"]) - float(want)) < 1e-5 * abs(float(want))

@@ -2,7 +2,7 @@
 """Micro-benchmark of the GEMM shapes one train chunk launches (T = 4096 rows x 18 positions = 73 728 tokens), through the C-ABI,
 next to torch.matmul (cuBLAS) on the bare shape. Triage tool, not a bench line:  python tools/gemm_perf.py [--flags 0,1,2,4] [--rows 4096]
 
-flags: clipdlm_gemm_debug_flags bits (1 = no epilogue stores, 2 = no aux loads, 4 = TMEM drain only, 64 = no band tile order in the lm_head passes)."""
+flags: clipdlm_gemm_debug_flags bits (1 = no epilogue stores, 2 = no aux loads, 4 = TMEM drain only, 4096 = no band tile order in the lm_head passes)."""
 import argparse
 import ctypes as C
 import os
