@@ -516,6 +516,9 @@ def run_ours(args):
     if args.gemm_debug_flags:
         from clipdlm import _lib
         _lib.load().clipdlm_gemm_debug_flags(args.gemm_debug_flags)
+    if args.attn_path:
+        from clipdlm import _lib
+        _lib.load().clipdlm_attn_force_simt(args.attn_path)
     ctx = Ctx(args)
     rank, world = ctx.rank, ctx.world
     pk = peaks()
@@ -701,6 +704,8 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-time bound; past it the loop stops once 5 timed steps exist")
     ap.add_argument("--gemm-debug-flags", type=int, default=0, help="triage: clipdlm_gemm_debug_flags bits (4096 = no band tile order in the lm_head passes, "
                                                                     "2048 = LSE_EXP output through row stores instead of TMA stores)")
+    ap.add_argument("--attn-path", type=int, default=0, help="triage: clipdlm_attn_force_simt (0 default, 4 = packed attention without the pipelined backward, "
+                                                             "3 = 32-row-slot tcgen05, 2 = mma.sync ring)")
     ap.add_argument("--profile-mode", action="store_true", help="for runs under ncu: no forced warm-up, no e2e leg, no sub-benchmarks, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

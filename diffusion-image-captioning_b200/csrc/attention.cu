@@ -653,9 +653,10 @@ static inline BfPtr mbf(const clipdlm_bf_t* p) {
 }
 
 // 0 = auto (L = 16 / 18: back-to-back packed tcgen05 tiles, attention_packed.cu; other L <= 32: forward tcgen05 32-row slots, backward mma.sync
-// TMA ring), 1 = fp32 SIMT, 2 = ring, 3 = tcgen05 with 32-row slots (attention_umma.cu), 4 = as 0
+// TMA ring), 1 = fp32 SIMT, 2 = ring, 3 = tcgen05 with 32-row slots (attention_umma.cu), 4 = as 0 but the backward without software pipelining
 static int g_force_path = 0;
 bool attn_packed_supported(int L, int D, int H);
+void attn_packed_bwd_pipeline(int on);
 template <bool BWD>
 int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo,
                        const uint32_t* keymask, int R, int L, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias,
@@ -756,6 +757,7 @@ int attn_bwd_dispatch(const clipdlm_bf_t* qkv, const uint32_t* keymask, const cl
   if ((all_plain || all_pair) && (g_force_path == 0 || g_force_path == 4) && attn_packed_supported(L, D, H)) {
     const bool fold = all_plain && folded && dbias;
     if (fold) *folded = 1;
+    attn_packed_bwd_pipeline(g_force_path == 4 ? 0 : 1);   // 4: the non-pipelined packed backward (two CTAs per SM), kept for A/B
     return launch_attn_packed<true>((const __nv_bfloat16*)qkv->hi, (const __nv_bfloat16*)qkv->lo, (const __nv_bfloat16*)dctx->hi, (const __nv_bfloat16*)dctx->lo,
                                     keymask, R, L, D, H, (__nv_bfloat16*)dqkv->hi, (__nv_bfloat16*)dqkv->lo, fold ? dbias : nullptr, make_drop(seed, site, p), st);
   }

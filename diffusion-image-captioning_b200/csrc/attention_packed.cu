@@ -115,6 +115,58 @@ __device__ __forceinline__ void ap_load_row(uint32_t tlane, int k, float (&out)[
   ap_pick<SLOT, Q, 32>(win, k, out);
 }
 
+// 64 consecutive fp32 TMEM columns of this warp's 32 lanes, WITHOUT waiting: the caller issues several and waits once (tmem_ld_wait) - every
+// tcgen05.wait::ld exposes a full TMEM round trip, and the softmax threads sit on exactly that chain.
+__device__ __forceinline__ void tmem_ld64_nowait(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]),
+        "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+        "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// out[j] = win[D(k) + j] for the slot index k of this thread (64-column window)
+template <int SLOT, int Q>
+__device__ __forceinline__ void ap_pick64(const uint32_t (&win)[64], int k, float (&out)[SLOT]) {
+  using W = ApWin<SLOT, Q>;
+#pragma unroll
+  for (int j = 0; j < SLOT; ++j) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      if (!W::valid(kk)) continue;
+      v = (k == kk) ? win[W::D(kk) + j] : v;
+    }
+    out[j] = __uint_as_float(v);
+  }
+}
+// S row and dP row of this thread with ONE TMEM round trip: both 64-column windows in flight, one wait
+template <int SLOT, int Q>
+__device__ __forceinline__ void ap_load_rows2(uint32_t tlane_s, uint32_t tlane_d, int k, float (&p)[SLOT], float (&dp)[SLOT]) {
+  using W = ApWin<SLOT, Q>;
+  uint32_t ws[64], wd[64];
+  tmem_ld64_nowait(tlane_s + W::C0, ws);
+  tmem_ld64_nowait(tlane_d + W::C0, wd);
+  tmem_ld_wait();
+  ap_pick64<SLOT, Q>(ws, k, p);
+  ap_pick64<SLOT, Q>(wd, k, dp);
+}
+template <int SLOT, int Q>
+__device__ __forceinline__ void ap_load_row64(uint32_t tlane, int k, float (&out)[SLOT]) {
+  using W = ApWin<SLOT, Q>;
+  uint32_t w[64];
+  tmem_ld64_nowait(tlane + W::C0, w);
+  tmem_ld_wait();
+  ap_pick64<SLOT, Q>(w, k, out);
+}
+
 // SLOT fp32 values -> bf16 pairs at keys [SLOT s, SLOT s + SLOT) of row `row` of a K-major [2 chunks][128 rows][128 B] tile (128-byte swizzle)
 template <int SLOT>
 __device__ __forceinline__ void ap_store_block(uint32_t tile, int row, int s, const float (&x)[SLOT]) {
@@ -145,6 +197,30 @@ __device__ __forceinline__ void ap_zero_row_chunk(uint32_t tile_chunk, int row) 
 }
 
 // 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (128 contiguous bytes) in global memory; ACC: also added into acc[]
+// 64 accumulator columns of this thread's TMEM lane with ONE tcgen05.ld (x64) and one wait -> 64 bf16 in global memory; ACC: also added into acc[].
+// (10 warps per CTA = 3 warps on two of the four register-file partitions: 168 registers per thread is the hard cap, so the pipelined
+// backward's epilogue takes its three outputs one after the other - three TMEM round trips instead of six.)
+template <bool ACC, int NACC>
+__device__ __forceinline__ void ap_store_out64x(uint32_t taddr, __nv_bfloat16* dst, bool store, bool accumulate, float (&acc)[NACC]) {
+  static_assert(!ACC || NACC == 64, "accumulator size");
+  uint32_t q[64];
+  tmem_ld64_nowait(taddr, q);
+  tmem_ld_wait();
+  if (store) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(dst + c * 8) =
+          make_uint4(pack_bf16x2(__uint_as_float(q[8 * c]), __uint_as_float(q[8 * c + 1])), pack_bf16x2(__uint_as_float(q[8 * c + 2]), __uint_as_float(q[8 * c + 3])),
+                     pack_bf16x2(__uint_as_float(q[8 * c + 4]), __uint_as_float(q[8 * c + 5])), pack_bf16x2(__uint_as_float(q[8 * c + 6]), __uint_as_float(q[8 * c + 7])));
+  }
+  if (ACC) {
+    if (accumulate) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j % NACC] += __uint_as_float(q[j]);
+    }
+  }
+}
+
 template <bool ACC, int NACC>
 __device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* dst, bool store, bool accumulate, float (&acc)[NACC],
                                                __nv_bfloat16* dst_lo = nullptr) {
@@ -334,11 +410,20 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       float p[SLOT];
 #pragma unroll
       for (int j = 0; j < SLOT; ++j) p[j] = 0.f;
-      switch (quad) {
-        case 0: ap_load_row<SLOT, 0>(tq, k_slot, p); break;
-        case 1: ap_load_row<SLOT, 1>(tq, k_slot, p); break;
-        case 2: ap_load_row<SLOT, 2>(tq, k_slot, p); break;
-        default: ap_load_row<SLOT, 3>(tq, k_slot, p); break;
+      if constexpr (BWD && !PAIR) {   // (2 CTAs x 192 threads: 170 registers - room for the 64-register window; forward / split precision keep the 32-register one)
+        switch (quad) {
+          case 0: ap_load_row64<SLOT, 0>(tq, k_slot, p); break;
+          case 1: ap_load_row64<SLOT, 1>(tq, k_slot, p); break;
+          case 2: ap_load_row64<SLOT, 2>(tq, k_slot, p); break;
+          default: ap_load_row64<SLOT, 3>(tq, k_slot, p); break;
+        }
+      } else {
+        switch (quad) {
+          case 0: ap_load_row<SLOT, 0>(tq, k_slot, p); break;
+          case 1: ap_load_row<SLOT, 1>(tq, k_slot, p); break;
+          case 2: ap_load_row<SLOT, 2>(tq, k_slot, p); break;
+          default: ap_load_row<SLOT, 3>(tq, k_slot, p); break;
+        }
       }
       {
         float mx = -INFINITY;
@@ -459,6 +544,279 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Software-pipelined backward (plain bf16): ONE CTA per SM that keeps TWO groups in flight in two smem / TMEM slots, with the per-group
+// work split over two warp sets that run concurrently on different groups -
+//   warps 2..5 "softmax": S, dP (TMEM) -> P', dS (smem)          of group n
+//   warps 6..9 "epilogue": dQ, dK, dV (TMEM) -> global, bias sums  of group n - 1
+// while the MMA warp alternates [S, dP of n] / [dV, dK, dQ of n - 1] and the TMA warp loads group n + 1. attn_packed_kernel<true> runs these
+// phases back to back in one warp set (two CTAs per SM give two chains of ~10 us per group); here a group leaves the SM every
+// max(softmax, epilogue) time. Same arithmetic, same smem tiles (one 7-tile set per slot), same folded bias gradients.
+// ------------------------------------------------------------------------------------------------------------------------------------
+constexpr int APP_THREADS = 320;   // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 softmax, warps 6..9 epilogue
+
+template <int SLOT>
+__global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                                                                               const AttPArgs a) {
+  extern __shared__ __align__(1024) uint8_t ap_smem[];
+  constexpr int OFF_Q = 0, OFF_K = 1, OFF_DO = 2, OFF_V = 3, OFF_P = 3, OFF_DS = 5, NSET = 7;
+  constexpr uint32_t SLOT_BYTES = NSET * AP_TILE;      // 112 KB per group slot
+  constexpr int NS = 127 / SLOT;
+  constexpr int ROWS = NS * SLOT;
+  uint8_t* smem = ap_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * SLOT_BYTES);
+  uint64_t* in_full = bars + 0; uint64_t* in_empty = bars + 2; uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 6; uint64_t* o_full = bars + 8; uint64_t* t_empty = bars + 10;      // [2] each: one per slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("clipdlm: attention smem base not 1024-byte aligned\n"); __trap(); }
+  for (int slot = 0; slot < 2; ++slot) {   // dedicated tiles (P chunk 1, dS): zero for the life of the CTA outside the rows' own blocks
+    uint8_t* z0 = smem + slot * SLOT_BYTES + (OFF_P + 1) * AP_TILE;
+    for (uint32_t off = threadIdx.x * 16; off < 3u * AP_TILE; off += APP_THREADS * 16) *reinterpret_cast<uint4*>(z0 + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    pdl_launch_dependents();
+    for (int s2 = 0; s2 < 2; ++s2) {
+      mbar_init(in_full + s2, 1); mbar_init(in_empty + s2, 1); mbar_init(s_full + s2, 1);
+      mbar_init(p_full + s2, 4); mbar_init(o_full + s2, 1); mbar_init(t_empty + s2, 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int h = (int)(blockIdx.x % a.H);
+  const int tile0 = (int)(blockIdx.x / a.H), tstride = (int)(gridDim.x / a.H);
+  const int my_tiles = a.tiles > tile0 ? (a.tiles - tile0 + tstride - 1) / tstride : 0;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      for (int n = 0; n < my_tiles; ++n) {
+        const int sl = n & 1;
+        const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+        uint8_t* base = smem + sl * SLOT_BYTES;
+        const int row0 = (tile0 + n * tstride) * ROWS;
+        mbar_wait(in_empty + sl, ph ^ 1u);
+        mbar_arrive_expect_tx(in_full + sl, 4 * AP_TILE);
+        tma_load_2d(base + OFF_Q * AP_TILE, &tm_qkv, in_full + sl, h * AP_DH, row0);
+        tma_load_2d(base + OFF_K * AP_TILE, &tm_qkv, in_full + sl, a.D + h * AP_DH, row0);
+        tma_load_2d(base + OFF_V * AP_TILE, &tm_qkv, in_full + sl, 2 * a.D + h * AP_DH, row0);
+        tma_load_2d(base + OFF_DO * AP_TILE, &tm_do, in_full + sl, h * AP_DH, row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer: [S, dP of n] then [dV, dK, dQ of n - 1] =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);
+      for (int n = 0; n <= my_tiles; ++n) {
+        if (n < my_tiles) {
+          const int sl = n & 1;
+          const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+          const uint32_t b0 = smem_u32(smem + sl * SLOT_BYTES), tb = tmem_base + (uint32_t)sl * 256u;
+          const uint32_t sq = b0 + OFF_Q * AP_TILE, sk = b0 + OFF_K * AP_TILE, sv = b0 + OFF_V * AP_TILE, sdo = b0 + OFF_DO * AP_TILE;
+          mbar_wait(in_full + sl, ph);
+          mbar_wait(t_empty + sl, ph ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // S = Q K^T
+            umma_bf16(tb, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dP = dO V^T
+            umma_bf16(tb + 128, make_smem_desc_sw128(sdo, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s,
+                      k > 0 ? 1u : 0u);
+          umma_commit(s_full + sl);
+        }
+        if (n >= 1) {
+          const int m = n - 1, sl = m & 1;
+          const uint32_t ph = (uint32_t)(m >> 1) & 1u;
+          const uint32_t b0 = smem_u32(smem + sl * SLOT_BYTES), tb = tmem_base + (uint32_t)sl * 256u;
+          const uint32_t sq = b0 + OFF_Q * AP_TILE, sk = b0 + OFF_K * AP_TILE, sdo = b0 + OFF_DO * AP_TILE, sp = b0 + OFF_P * AP_TILE, sds = b0 + OFF_DS * AP_TILE;
+          mbar_wait(p_full + sl, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dV = P^T dO
+            umma_bf16(tb, make_smem_desc_sw128(sp, AP_TILE, 1024) + (uint64_t)(k * 128), make_smem_desc_sw128(sdo, 8192, 1024) + (uint64_t)(k * 128), idesc_tv,
+                      k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dK = dS^T Q
+            umma_bf16(tb + 64, make_smem_desc_sw128(sds, AP_TILE, 1024) + (uint64_t)(k * 128), make_smem_desc_sw128(sq, 8192, 1024) + (uint64_t)(k * 128), idesc_tv,
+                      k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dQ = dS K
+            umma_bf16(tb + 128, make_smem_desc_sw128(sds + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
+                      make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
+          umma_commit(o_full + sl);
+          umma_commit(in_empty + sl);
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int s = row / SLOT;
+    const int i = row - s * SLOT;
+    const bool dropping = a.drop.thresh16 != 0;
+    if (warp < 6) {
+      // ===================================== softmax warps: S, dP -> P', dS =====================================
+      const int k_slot = s - (32 * quad) / SLOT;
+      const float sl2 = a.scale * AP_LOG2E;
+      for (int n = 0; n < my_tiles; ++n) {
+        const int sl = n & 1;
+        const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+        const uint32_t tq = tmem_base + (uint32_t)sl * 256u + ((uint32_t)(quad * 32) << 16);
+        const uint32_t b0 = smem_u32(smem + sl * SLOT_BYTES);
+        const uint32_t sp = b0 + OFF_P * AP_TILE, sds = b0 + OFF_DS * AP_TILE;
+        const int tile = tile0 + n * tstride;
+        const int r = tile * NS + s;
+        const bool live = row < ROWS && r < a.R;
+        const unsigned long long rh = (unsigned long long)r * a.H + h;
+        const uint32_t keybits = live ? (a.keymask[r] & (SLOT >= 32 ? 0xffffffffu : ((1u << SLOT) - 1u))) : 0u;
+        mbar_wait(s_full + sl, ph);
+        tc_fence_after();
+        float p[SLOT], dp[SLOT];
+#pragma unroll
+        for (int j = 0; j < SLOT; ++j) { p[j] = 0.f; dp[j] = 0.f; }
+        // S row (one x64 load), then the dP window is requested BEFORE the softmax arithmetic on p and awaited after it: its TMEM round trip hides
+        // behind the exponentials
+        uint32_t wd[64];
+        switch (quad) {
+          case 0: ap_load_row64<SLOT, 0>(tq, k_slot, p); tmem_ld64_nowait(tq + 128 + ApWin<SLOT, 0>::C0, wd); break;
+          case 1: ap_load_row64<SLOT, 1>(tq, k_slot, p); tmem_ld64_nowait(tq + 128 + ApWin<SLOT, 1>::C0, wd); break;
+          case 2: ap_load_row64<SLOT, 2>(tq, k_slot, p); tmem_ld64_nowait(tq + 128 + ApWin<SLOT, 2>::C0, wd); break;
+          default: ap_load_row64<SLOT, 3>(tq, k_slot, p); tmem_ld64_nowait(tq + 128 + ApWin<SLOT, 3>::C0, wd); break;
+        }
+        {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < SLOT; ++j) {
+            p[j] = (keybits & (1u << j)) ? p[j] * sl2 : -INFINITY;
+            mx = fmaxf(mx, p[j]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < SLOT; ++j) { p[j] = ex2_ftz(p[j] - mx); sum += p[j]; }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int j = 0; j < SLOT; ++j) p[j] = live ? p[j] * inv : 0.f;
+        }
+        const uint32_t kb = dropping ? ap_row_keep_bits<SLOT>(a.drop, rh, i) : 0xffffffffu;
+        tmem_ld_wait();
+        switch (quad) {
+          case 0: ap_pick64<SLOT, 0>(wd, k_slot, dp); break;
+          case 1: ap_pick64<SLOT, 1>(wd, k_slot, dp); break;
+          case 2: ap_pick64<SLOT, 2>(wd, k_slot, dp); break;
+          default: ap_pick64<SLOT, 3>(wd, k_slot, dp); break;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < SLOT; ++j) {
+          if (dropping) dp[j] = (kb & (1u << j)) ? dp[j] * a.drop.scale : 0.f;
+          dot = fmaf(dp[j], p[j], dot);
+        }
+        float rho = 0.f;
+#pragma unroll
+        for (int j = 0; j < SLOT; ++j) {
+          dp[j] = live ? p[j] * (dp[j] - dot) * a.scale : 0.f;
+          if (dropping) p[j] = (kb & (1u << j)) ? p[j] * a.drop.scale : 0.f;
+          rho += p[j];
+        }
+        ap_zero_row_chunk(sp, row);   // key chunk 0 of P is where TMA landed V
+        if (row < ROWS) {
+          ap_store_block<SLOT>(sp, row, s, p);
+          ap_store_block<SLOT>(sds, row, s, dp);
+          if (a.dbias != nullptr) {
+            const uint32_t addr = sp + AP_TILE + (uint32_t)row * 128u + ((7u ^ (uint32_t)(row & 7)) << 4) + 12u;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(0.f, rho)) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + sl);
+      }
+    } else {
+      // ===================================== epilogue warps: dQ, dK, dV -> global (+ bias sums) =====================================
+      float acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      const bool fold = a.dbias != nullptr;
+      for (int n = 0; n < my_tiles; ++n) {
+        const int sl = n & 1;
+        const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+        const uint32_t tq = tmem_base + (uint32_t)sl * 256u + ((uint32_t)(quad * 32) << 16);
+        const int tile = tile0 + n * tstride;
+        const int r = tile * NS + s;
+        const bool live = row < ROWS && r < a.R;
+        mbar_wait(o_full + sl, ph);
+        tc_fence_after();
+        const size_t tok = (size_t)tile * ROWS + row;
+        __nv_bfloat16* o = a.out + tok * 3 * a.D + h * AP_DH;
+        ap_store_out64x<true>(tq + 128, o, live, fold && live, acc);                    // dQ (+ this thread's share of d(b_q))
+        ap_store_out64x<false>(tq + 64, o + a.D, live, false, acc);                     // dK
+        ap_store_out64x<true>(tq, o + 2 * a.D, live, fold && row == 127, acc);          // dV; row 127 of dV is the group's d(b_v)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + sl);
+      }
+      if (fold && my_tiles > 0) {
+        float* stage = reinterpret_cast<float*>(smem);   // every MMA of this CTA has completed: [128 rows][64] fp32 over slot 0's Q | K
+#pragma unroll
+        for (int j = 0; j < 64; ++j) stage[row * 64 + ((j + row) & 63)] = acc[j];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x - 192;    // 0..127
+        if (t < 64) {
+          float sq2 = 0.f;
+          for (int rr = 0; rr < 127; ++rr) sq2 += stage[rr * 64 + ((t + rr) & 63)];
+          atomicAdd(a.dbias + h * AP_DH + t, sq2);
+        } else {
+          const int c = t - 64;
+          atomicAdd(a.dbias + 2 * a.D + h * AP_DH + c, stage[127 * 64 + ((c + 127) & 63)]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int g_packed_bwd_pipe = 1;   // 1 = software-pipelined backward (default), 0 = attn_packed_kernel<true> (two CTAs per SM)
+
+template <int SLOT>
+int launch_packed_bwd_pipe(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const uint32_t* keymask, int R, int D, int H, __nv_bfloat16* out,
+                           float* dbias, const DropoutCfg& drop, cudaStream_t st) {
+  constexpr int NS = 127 / SLOT;
+  const unsigned long long T = (unsigned long long)R * SLOT;
+  CUtensorMap tm_qkv, tm_do;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tm_qkv, qkv, 3ull * D, T, 3ull * D * 2, AP_DH, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_do, dctx, (unsigned long long)D, T, (unsigned long long)D * 2, AP_DH, 128))) return rc;
+  AttPArgs a;
+  a.keymask = keymask; a.out = out; a.out_lo = nullptr; a.dbias = dbias; a.R = R; a.L = SLOT; a.D = D; a.H = H; a.drop = drop; a.scale = 0.125f;
+  a.tiles = (R + NS - 1) / NS;
+  const size_t smem = (size_t)14 * AP_TILE + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_packed_bwd_pipe_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  long long per_head = num_sms() / H;   // one CTA per SM, every CTA on one head
+  if (per_head < 1) per_head = 1;
+  if (per_head > a.tiles) per_head = a.tiles;
+  const int grid = (int)(per_head * H);
+  CLIPDLM_CUDA_OK(launch_pdl(attn_packed_bwd_pipe_kernel<SLOT>, dim3(grid), dim3(APP_THREADS), smem, st, tm_qkv, tm_do, a));
+  return 0;
+}
+
 template <bool BWD, int SLOT, bool PAIR>
 int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo, const uint32_t* keymask,
                   int R, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias, const DropoutCfg& drop, cudaStream_t st) {
@@ -496,6 +854,7 @@ int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const _
 }  // namespace
 
 bool attn_packed_supported(int L, int D, int H) { return (L == 16 || L == 18) && D == H * AP_DH && H <= 64; }
+void attn_packed_bwd_pipeline(int on) { g_packed_bwd_pipe = on; }
 
 // forward: dctx / dbias unused.  backward: dbias (nullable, plain bf16 only) receives d(q bias) and d(v bias) (+= ; d(k bias) = 0 is not touched).
 // qkv_lo != nullptr selects split precision (dctx_lo / out_lo are then required as well).
@@ -509,6 +868,10 @@ int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, co
   if (pair) {
     if (L == 16) return launch_packed<BWD, 16, true>(qkv, qkv_lo, dctx, dctx_lo, keymask, R, D, H, out, out_lo, dbias, drop, st);
     return launch_packed<BWD, 18, true>(qkv, qkv_lo, dctx, dctx_lo, keymask, R, D, H, out, out_lo, dbias, drop, st);
+  }
+  if (BWD && g_packed_bwd_pipe && H <= num_sms()) {
+    if (L == 16) return launch_packed_bwd_pipe<16>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
+    return launch_packed_bwd_pipe<18>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
   }
   if (L == 16) return launch_packed<BWD, 16, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
   return launch_packed<BWD, 18, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);

@@ -168,7 +168,7 @@ int clipdlm_attn_bwd_bias(const clipdlm_bf_t* qkv, const uint32_t* keymask, cons
 
 /* Test hook: attention path for plain bf16, L <= 32: 0 = default (L = 16 / 18: tcgen05 tiles of back-to-back packed sequences in both
  * directions; other L: forward tcgen05 with 32-row slots, backward mma.sync TMA ring), 1 = fp32 SIMT kernels, 2 = mma.sync TMA-ring
- * kernels, 3 = tcgen05 with 32-row slots for both directions. */
+ * kernels, 3 = tcgen05 with 32-row slots for both directions, 4 = as 0 with the non-pipelined packed backward (A/B of the software pipeline). */
 void clipdlm_attn_force_simt(int32_t on);
 
 /* Column sums (bias gradients): out[n] += sum_m x[m, n]. */

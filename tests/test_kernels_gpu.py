@@ -342,7 +342,7 @@ def test_attention_packed_tiles_and_folded_bias_gradients(G, L, R):
     words = words.to(torch.int32).contiguous()
     lib, Lb = G.lib(), G.L
     outs = {}
-    for path in (0, 1):
+    for path in (0, 1, 4):   # packed + software-pipelined backward (default), fp32 SIMT, packed without the pipeline
         lib.clipdlm_attn_force_simt(path)
         ctx = torch.zeros(R * L, D, device=G.DEV, dtype=torch.bfloat16)
         dq = torch.zeros(R * L, 3 * D, device=G.DEV, dtype=torch.bfloat16)
@@ -354,7 +354,8 @@ def test_attention_packed_tiles_and_folded_bias_gradients(G, L, R):
         torch.cuda.synchronize()
         outs[path] = (ctx.float(), dq.float(), dbias.clone(), int(folded))
     lib.clipdlm_attn_force_simt(0)
-    assert outs[0][3] == 1 and outs[1][3] == 0            # the SIMT path leaves the bias gradients to the caller's colsum
+    assert outs[0][3] == 1 and outs[1][3] == 0 and outs[4][3] == 1   # the SIMT path leaves the bias gradients to the caller's colsum
+    assert rel(outs[4][1], outs[0][1]) < 1e-6 and rel(outs[4][2], outs[0][2]) < 1e-4   # same arithmetic with and without the pipeline
     assert torch.equal(outs[1][2], torch.full((3 * D,), 0.25, device=G.DEV))
     assert rel(outs[0][0], outs[1][0]) < 1e-2 and rel(outs[0][1], outs[1][1]) < 1.5e-2
     got = outs[0][2] - 0.25                                # += semantics

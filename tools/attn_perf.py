@@ -46,13 +46,13 @@ def timeit(fn, iters=20):
 fwd_bytes, bwd_bytes = R * Ls * D * 2 * 4, R * Ls * D * 2 * 7
 dbias = torch.zeros(3 * D, device=DEV)
 folded = (C.c_int32 * 1)()
-for path in ((0, 3, 2) if Ls <= 32 else (0,)):
+for path in ((0, 4, 3, 2) if Ls <= 32 else (0,)):
     lib.clipdlm_attn_force_simt(path)
     for p in (0.0, 0.1):
         f = timeit(lambda: L.check(lib.clipdlm_attn_fwd(C.byref(bq), km.data_ptr(), R, Ls, D, H, C.byref(bc), 1, 1, p, st)))
         b = timeit(lambda: L.check(lib.clipdlm_attn_bwd(C.byref(bq), km.data_ptr(), C.byref(bd), R, Ls, D, H, C.byref(bg), 1, 1, p, st)))
         extra = ""
-        if path == 0 and Ls <= 32:
+        if path in (0, 4) and Ls <= 32:
             bb = timeit(lambda: L.check(lib.clipdlm_attn_bwd_bias(C.byref(bq), km.data_ptr(), C.byref(bd), R, Ls, D, H, C.byref(bg), 1, 1, p, dbias.data_ptr(),
                                                                   C.cast(folded, C.c_void_p), st)))
             extra = f"   bwd + folded bias gradients {bb:7.1f} us (folded = {folded[0]})"
