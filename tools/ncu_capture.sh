@@ -23,7 +23,7 @@ full gemm_fwd   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(0|6),' 12 13 s
 full gemm_lse   'gemm_kernel<(\(int\))?0, (\(int\))?0, (\(int\))?(2|4),' 2 0 source
 full gemm_dgrad 'gemm_kernel<(\(int\))?0, (\(int\))?1, ' 8 2
 full gemm_wgrad 'gemm_kernel<(\(int\))?1, (\(int\))?1, ' 5 0
-full attn       'attn_' 4 4
+full attn       'attn_packed' 4 4
 full ln         'layernorm_' 6 12
 python tools/ncu_full_summary.py gpurun_out ${TAG} > gpurun_out/${TAG}_ncu_full_summary.csv 2> gpurun_out/${TAG}_ncu_full_summary.err
 ls -la gpurun_out | head -40
