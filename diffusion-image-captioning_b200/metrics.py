@@ -31,8 +31,10 @@ def _ngrams(tokens: Sequence[str], n: int) -> Counter:
 def bleu_score(candidates: Sequence[str], references: Sequence[Sequence[str]], n_gram: int = 4) -> float:
     """Corpus-level BLEU as torchmetrics.functional.bleu_score computes it: clipped n-gram counts summed over the corpus, geometric
     mean of the n precisions (0 if any is 0), brevity penalty with the closest reference length - ties go to the FIRST such reference in
-    list order, as torchmetrics' `target_len_diff.index(min(target_len_diff))` does. UNPINNED against torchmetrics itself (absent from this
-    image, no network): checked against hand-computed answers and the definition only (tests/test_host_cpu.py)."""
+    list order, as torchmetrics' `target_len_diff.index(min(target_len_diff))` does. torchmetrics itself is absent from this image (no
+    network); the function is pinned on the published doc-test vectors of torchmetrics.functional.bleu_score (0.7598) and of
+    nltk's sentence_bleu / corpus_bleu (0.5045666840058485, 0.5920778868801042), reproduced to 1e-12
+    (tests/test_host_cpu.py::test_bleu_published_known_answers), besides hand-computed answers."""
     assert len(candidates) == len(references)
     num = [0] * n_gram
     den = [0] * n_gram

@@ -154,6 +154,28 @@ def test_postprocess_and_bleu():
     assert abs(s - 1.0) < 1e-12
 
 
+def test_bleu_published_known_answers():
+    """Pins bleu_score() on the doc-test vectors two independent BLEU implementations publish (neither package is in this image, the
+    expected values are the ones printed in their docstrings): torchmetrics.functional.bleu_score - the function the reference calls
+    through `BLEUScore()` (CLIP-DDPM.py:604-606,629) - and nltk.translate.bleu_score sentence_bleu / corpus_bleu (same definition:
+    clipped counts summed over the corpus, uniform 4-gram weights, no smoothing, closest-reference brevity penalty)."""
+    import clipdlm
+    # torchmetrics/functional/text/bleu.py docstring: tensor(0.7598); analytically (5/6 * 4/5 * 3/4 * 2/3) ** 0.25 = 3 ** -0.25, BP = 1
+    s = clipdlm.bleu_score(["the cat is on the mat"], [["there is a cat on the mat", "a cat is on the mat"]])
+    assert round(s, 4) == 0.7598 and abs(s - 3.0 ** -0.25) < 1e-12
+    h1 = "It is a guide to action which ensures that the military always obeys the commands of the party"
+    r1a = "It is a guide to action that ensures that the military will forever heed Party commands"
+    r1b = "It is the guiding principle which guarantees the military forces always being under the command of the Party"
+    r1c = "It is the practical guide for the army always to heed the directions of the party"
+    h2 = "he read the book because he was interested in world history"
+    r2a = "he was interested in world history because he read the book"
+    # nltk.translate.bleu_score.sentence_bleu docstring: 0.5045666840058485; corpus_bleu docstring: 0.5920778868801042
+    assert abs(clipdlm.bleu_score([h1], [[r1a, r1b, r1c]]) - 0.5045666840058485) < 1e-12
+    assert abs(clipdlm.bleu_score([h1, h2], [[r1a, r1b, r1c], [r2a]]) - 0.5920778868801042) < 1e-12
+    # the reference averages per-batch corpus scores (CLIP-DDPM.py:629-631); a batch with no 4-gram match scores 0, not NaN
+    assert clipdlm.bleu_score([h2], [[r1a]]) == 0.0
+
+
 def _build_c_host(out):
     from clipdlm import _lib as L
     if not os.path.exists(L.LIB_PATH):
