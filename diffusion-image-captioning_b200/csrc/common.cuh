@@ -38,6 +38,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// One lane of a converged warp (elect.sync always names the same lane for the same member mask): ptxas keeps the operands of single-thread
+// instructions (tcgen05.mma / commit, TMA) on the uniform datapath under this predicate, where `lane == 0` costs an ELECT / R2UR waterfall each.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,6 +23,11 @@ namespace clipdlm {
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16384
 constexpr int EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quadrant, each owning 128 of the 256 tile columns
+// (Round 2 measured a 16-warp variant of the math-heavy K = 768 epilogues - four warps per quadrant, 64 columns each, 16-column TMEM pieces,
+// 64B-swizzled 32-column TMA-store boxes, 92 registers: parity-green but SLOWER, STORE_GELU_DERIV 0.713 vs 0.691 ms, STORE_MULAUX 0.694 vs
+// 0.599 ms per 8192-row chunk. Both layouts issue ~0.5 instructions per cycle and scheduler: FFMA2 / FMNMX / F2FP / LOP3 take two dispatch
+// cycles each and MUFU.EX2 eight, so ~15 instructions per element cost about what the 6144 MMA cycles of a tile offer whatever the warp
+// count, and the narrower stores and auxiliary loads cost more than the extra latency hiding bought. Removed)
 constexpr int STG_PITCH = 80;                       // fp32 staging (WGRAD): bytes per staged row (64 B payload = 16 fp32, + 16 B pad)
 constexpr int STG_WARP_BYTES = 8192;                // per epilogue warp: two [32 rows][128 B] swizzled tiles feeding TMA stores (or the fp32 staging)
 constexpr int TMEM_COLS = 512;
@@ -396,7 +401,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues: see the MMA issuer below)
+    {
       int stage = 0; uint32_t phase = 0;
       const uint32_t full0_cluster = CG == 2 ? mapa_u32(&full_bar[0], 0) : 0u;  // leader's full barriers (shared::cluster)
       for (int w = unit0; w < total_items; w += unit_stride) {
@@ -415,7 +421,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stages + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            if (g.dbg & 32u) {   // triage: no loads at all, the MMAs run on whatever is in shared memory
+            if (!elect_one()) {
+            } else if (g.dbg & 32u) {   // triage: no loads at all, the MMAs run on whatever is in shared memory
               if (CG == 1 || cta_rank == 0) mbar_arrive(&full_bar[stage]);
               else mbar_arrive_cluster(full0_cluster + stage * 8);
             } else if (CG == 1) {
@@ -461,6 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 for (int j = 0; j < G::BN_CTA / 64; ++j) tma_load_2d_cg2(sb + j * 8192, tb, fb, n0 + j * 64, kb * BK);
               }
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -468,8 +476,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA of the pair only) =====================================
-    if (lane == 0 && cta_rank == 0) {
+    // The WHOLE warp walks the loop and lane 0 issues: under an enclosing `if (lane == 0)` every descriptor lives in vector registers and each
+    // tcgen05 instruction is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall - ~130 dependent instructions per 64-wide k-block
+    // against the 512 cycles its four MMAs take (ncu source view, round 2: the issuer's samples are flat over that loop, and with four epilogue
+    // warps on its scheduler it, not the epilogue, bounded the K = 768 GEMMs). Uniform control flow keeps the loop state on the uniform datapath.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, AMAJ, BMAJ);
+      constexpr uint32_t a_step = (AMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;  // K advance per MMA, 16-byte units
+      constexpr uint32_t b_step = (BMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+      const uint32_t stages_u32 = smem_u32(stages);
+      const uint32_t a_lbo = AMAJ == 0 ? 16u : g.mn_lbo, a_sbo = AMAJ == 0 ? 1024u : g.mn_sbo;
+      const uint32_t b_lbo = BMAJ == 0 ? 16u : g.mn_lbo, b_sbo = BMAJ == 0 ? 1024u : g.mn_sbo;
+      const uint64_t adesc0 = make_smem_desc_sw128(0u, a_lbo, a_sbo), bdesc0 = make_smem_desc_sw128(0u, b_lbo, b_sbo);   // start address added per stage
+      const bool no_mma = (g.dbg & 16u) != 0;   // triage: no MMAs, the commits below fire immediately
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int w = unit0; w < total_items; w += unit_stride) {
@@ -483,24 +502,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stages + stage * STAGE_BYTES);
+          const uint32_t sa = stages_u32 + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t adesc = AMAJ == 0 ? make_smem_desc_sw128(sa, 16, 1024) : make_smem_desc_sw128(sa, g.mn_lbo, g.mn_sbo);
-          const uint64_t bdesc = BMAJ == 0 ? make_smem_desc_sw128(sb, 16, 1024) : make_smem_desc_sw128(sb, g.mn_lbo, g.mn_sbo);
-          constexpr uint32_t a_step = (AMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;  // K advance per MMA, 16-byte units
-          constexpr uint32_t b_step = (BMAJ == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+          const uint64_t adesc = adesc0 | static_cast<uint64_t>((sa >> 4) & 0x3fffu);
+          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((sb >> 4) & 0x3fffu);
+          if (elect_one()) {
+            if (!no_mma) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            if (g.dbg & 16u) continue;   // triage: no MMAs, the commits below fire immediately
-            if (CG == 2) umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (CG == 2) umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(d_tmem, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc, (it > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // last k-block: accumulator ready for the epilogue warps (of both CTAs). Same thread as the MMAs by construction - tcgen05.commit
+            // tracks the issuing thread's operations, so it must not depend on a second election naming the same lane
+            if (it == iters - 1) { if (CG == 2) umma_commit_cg2(&tfull_bar[as]); else umma_commit(&tfull_bar[as]); }
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator ready for the epilogue warps (of both CTAs)
-        if (CG == 2) umma_commit_cg2(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }

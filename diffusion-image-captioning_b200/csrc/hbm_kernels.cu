@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_fwd_fast_kernel(const __nv_b
       }
     }
     __syncwarp();
-    if (lane == 0 && row + LNF_STAGES * row_step < rows) {
+    if (row + LNF_STAGES * row_step < rows && elect_one()) {   // (elect.sync, not lane == 0: no ELECT / R2UR waterfall around the bulk copy)
       mbar_arrive_expect_tx(&bars[stage], row_bytes);
       bulk_load_1d(ring + (size_t)stage * row_bytes, z + (size_t)(row + LNF_STAGES * row_step) * D, row_bytes, &bars[stage]);
     }
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a
       }
     }
     __syncwarp();   // every lane has consumed the stage: refill it with the row LNB_STAGES ahead
-    if (lane == 0 && row + LNB_STAGES * row_step < a.rows) issue(stage, row + LNB_STAGES * row_step);
+    if (row + LNB_STAGES * row_step < a.rows && elect_one()) issue(stage, row + LNB_STAGES * row_step);
     if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
     if (a.drop_out.thresh16 != 0) {
 #pragma unroll
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128, NV <= 3 ? 3 : 2) layernorm_bwd_fast_kerne
       }
     }
     __syncwarp();
-    if (lane == 0 && row + LNB_STAGES * row_step < a.rows) issue(stage, row + LNB_STAGES * row_step);
+    if (row + LNB_STAGES * row_step < a.rows && elect_one()) issue(stage, row + LNB_STAGES * row_step);
     if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
     if (DROP_OUT) {   // the dropout that followed this LN's output masks dy
 #pragma unroll

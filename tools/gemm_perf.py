@@ -82,6 +82,9 @@ def main():
         ("fwd ffn2 bias+drop+res", 2 * T * F * D, dict(a_hi=x3072, b_hi=w2, lda=F, ldb=F, M=T, N=D, K=F, out_hi=o768, ldo=D, bias=bias, res_hi=x768, ldr=D, drop_seed=7, drop_site=3, drop_p=0.1), (x3072, w2.t())),
         ("fwd vt   bias+gelu dual", 2 * T * D * D, dict(a_hi=x768, b_hi=wo, lda=D, ldb=D, M=T, N=D, K=D, out_hi=o768, out2_hi=bf(T, D), ldo=D, bias=bias), None),
         ("dgrad ffn2 *gelu'(u)", 2 * T * F * D, dict(a_hi=x768, b_hi=w2, lda=D, ldb=F, M=T, N=F, K=D, b_major=1, out_hi=o3072, ldo=F, u_hi=x3072, ldu=F), (x768, w2)),
+        ("EPI6 fwd ffn1 gelu'+gelu", 2 * T * F * D, dict(a_hi=x768, b_hi=w1, lda=D, ldb=D, M=T, N=F, K=D, epilogue=6, out_hi=o3072, out2_hi=o3072b, ldo=F, bias=bias), None),
+        ("EPI7 dgrad ffn2 *stored gelu'", 2 * T * F * D, dict(a_hi=x768, b_hi=w2, lda=D, ldb=F, M=T, N=F, K=D, b_major=1, epilogue=7, out_hi=o3072, ldo=F, u_hi=x3072, ldu=F), None),
+        ("EPI7 ... + bias colsum", 2 * T * F * D, dict(a_hi=x768, b_hi=w2, lda=D, ldb=F, M=T, N=F, K=D, b_major=1, epilogue=7, out_hi=o3072, ldo=F, u_hi=x3072, ldu=F, acc_f32=torch.zeros(F, device=DEV)), None),
         ("dgrad ffn1 +res", 2 * T * F * D, dict(a_hi=x3072, b_hi=w1, lda=F, ldb=D, M=T, N=D, K=F, b_major=1, out_hi=o768, ldo=D, res_hi=x768, ldr=D), (x3072, w1)),
         ("dgrad qkv +res", 2 * T * 3 * D * D, dict(a_hi=x2304, b_hi=wqkv, lda=3 * D, ldb=D, M=T, N=D, K=3 * D, b_major=1, out_hi=o768, ldo=D, res_hi=x768, ldr=D), (x2304, wqkv)),
         ("dgrad o", 2 * T * D * D, dict(a_hi=x768, b_hi=wo, lda=D, ldb=D, M=T, N=D, K=D, b_major=1, out_hi=o768, ldo=D), (x768, wo)),
