@@ -241,11 +241,16 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       for (int j = 0; j < 16; ++j) upk2(mul2(pk2(v[2 * j], v[2 * j + 1]), rs2), v[2 * j], v[2 * j + 1]);
     }
     if (BIAS) {
+      // bias of this chunk's 32 columns. Default: straight from global memory - every lane reads the same 16 bytes (one L1 wavefront per
+      // load, the tile's 1 KB stays L1-resident), so the per-tile fill of a shared bias array and its two epilogue-wide bar.syncs go away
+      // (ncu source view: 8 % of the epilogue warps' samples on the lin1 forward GEMM sat at those barriers). Debug bit 13: the shared array.
       const uint32_t sb = sbias_u32 + cc * 128;
+      const float* gb = g.bias + col0 + cc * 32;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 b4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
+        if (g.dbg & 8192u) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
+        else asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "l"(gb + j * 4));
         upk2(add2(pk2(v[4 * j], v[4 * j + 1]), pk2(b4.x, b4.y)), v[4 * j], v[4 * j + 1]);
         upk2(add2(pk2(v[4 * j + 2], v[4 * j + 3]), pk2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
       }
@@ -542,7 +547,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int row_base = (m_blk * CG + cta_rank) * BM + q * 32;
       const int m = row_base + lane;
 
-      if ((EPI == CLIPDLM_EPI_STORE || EPI == CLIPDLM_EPI_STORE_GELU_DERIV) && g.bias != nullptr) {
+      // shared bias array: generic STORE epilogue only (the specialised ones read the bias from global memory, N % 256 == 0 there)
+      if ((EPI == CLIPDLM_EPI_STORE || EPI == CLIPDLM_EPI_STORE_GELU_DERIV) && g.bias != nullptr && (g.fast_mode < 0 || (g.dbg & 8192u))) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's readers done
         for (int i = threadIdx.x - 128; i < BN; i += 32 * EPI_WARPS) {
           const int n = n_blk * BN + i;
@@ -1216,6 +1222,7 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   if (g->epilogue == CLIPDLM_EPI_LSE_EXP) ga.lse = g->exp_shift;
   if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) ga.lse = g->row_scale;
   ga.dbg = g_dbg_flags;
+  if (g->bias != nullptr && (reinterpret_cast<uintptr_t>(g->bias) & 15) != 0) ga.dbg |= 8192u;   // 16-byte bias loads need an aligned bias vector: else the shared array
   ga.fast_mode = -1;
   if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) {
     CLIPDLM_CHECK(g->row_scale && g->out_hi && g->res_hi && !g->bias && !g->u_hi && !g->out2_hi && !g->out_f32 && !g->out_lo && !g->res_lo &&
