@@ -362,7 +362,7 @@ def roofline_block(prof, steps, ms_prof, pk):
     dom = max(GEMM_CATS, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     ach = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
-    return {"bound": "tensor", "kernel": f"gemm_kernel ({dom}: tcgen05.mma.cta_group::2 256x256x16 CTA pairs, TMA-fed 6-stage ring, fused epilogue with TMA stores)",
+    return {"bound": "tensor", "kernel": f"gemm_kernel ({dom}: tcgen05.mma.cta_group::2 256x256x16 CTA pairs, TMA-fed 5-stage ring, fused epilogue with TMA stores)",
             "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
             "peak_kind": f"{pk['source']} sustained bf16 (burst {pk['tf_burst']})", "avg_launch_ms": d["ms"] / max(d["launches"], 1),
             "flops_per_launch": d["flops"] / max(d["launches"], 1), "traffic": ncu_traffic(dom), "ms_per_step_with_event_brackets": ms_prof / steps,

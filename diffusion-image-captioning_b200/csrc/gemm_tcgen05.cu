@@ -35,7 +35,7 @@ constexpr int TMEM_COLS = 512;
 // CG = 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256): each CTA
 // stages its own 128 rows of A and only HALF of the B tile (128 of the 256 N rows), so the shared-memory traffic per MMA
 // (TMA writes + tensor-core operand reads) drops by a third - the CG = 1 kernel is shared-memory-bandwidth bound at ~65 % of
-// the tensor pipe - and the freed shared memory deepens the ring from 4 to 6 stages.
+// the tensor pipe - and the freed shared memory deepens the ring (5 stages of 32 KB per CTA next to the 64 KB of TMA-store staging).
 template <int CG>
 struct Geo {
   static constexpr int BN_CTA = BN / CG;
