@@ -254,8 +254,13 @@ __device__ __forceinline__ void ap_store_out64(uint32_t taddr, __nv_bfloat16* ds
   }
 }
 
-template <bool BWD, int SLOT, bool PAIR>
-__global__ void __launch_bounds__(AP_THREADS, (BWD ? 2 : 4) / (PAIR ? 2 : 1))
+// CTAs per SM: backward 2 (smem, TMEM), forward 4 - or 3 (EVAL3): without dropout the softmax is short enough that three groups in flight
+// cover the chain, and 96 instead of 80 registers take most of the L = 18 kernel's spills away (measured, same box, R = 8192 x 12 heads:
+// p = 0: 177.5 us at 3 CTAs / 184.0 at 4; p = 0.1: 200.8 / 197.9 - so training keeps 4, the denoise loop takes 3).
+template <bool BWD, bool PAIR, bool EVAL3>
+constexpr int ap_ctas_per_sm() { return ((BWD ? 2 : (EVAL3 ? 3 : 4))) / (PAIR ? 2 : 1); }
+template <bool BWD, int SLOT, bool PAIR, bool EVAL3 = false>
+__global__ void __launch_bounds__(AP_THREADS, ap_ctas_per_sm<BWD, PAIR, EVAL3>())
 attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_qkv_lo,
                    const __grid_constant__ CUtensorMap tm_do_lo, const AttPArgs a) {
   extern __shared__ __align__(1024) uint8_t ap_smem[];
@@ -309,10 +314,12 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      for (int n = 0; n < my_tiles; ++n) {
-        const int row0 = (tile0 + n * tstride) * ROWS;   // first token row of the tile
-        mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+    // (the whole warp walks the loop, one elect.sync-elected lane issues: under `lane == 0` ptxas wraps every TMA / tcgen05 instruction in an
+    //  ELECT / PLOP3 / BRA.U.ANY waterfall - ~9 instructions per MMA on the issuer's dependent chain, see gemm_tcgen05.cu)
+    for (int n = 0; n < my_tiles; ++n) {
+      const int row0 = (tile0 + n * tstride) * ROWS;   // first token row of the tile
+      mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(in_full, NLOADS * AP_TILE);   // full 128-row boxes: rows past the tensor arrive as zeros
         tma_load_2d(smem + OFF_Q * AP_TILE, &tm_qkv, in_full, h * AP_DH, row0);
         tma_load_2d(smem + OFF_K * AP_TILE, &tm_qkv, in_full, a.D + h * AP_DH, row0);
@@ -325,10 +332,12 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           if (BWD) tma_load_2d(smem + LO + OFF_DO * AP_TILE, &tm_do_lo, in_full, h * AP_DH, row0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (same schedule as attention_umma.cu) =====================================
-    if (lane == 0) {
+    // Whole warp in the loop; each [MMAs + commit] group is issued by one elected lane (a commit sits with the MMAs it tracks).
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP: both operands K-major (contraction over the head dim)
       constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);    // O = P V, dQ = dS K: A K-major, B MN-major
       constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q: both MN-major
@@ -348,6 +357,7 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         mbar_wait(in_full, par);
         mbar_wait(t_empty, par ^ 1u);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S = Q K^T
           mm(tmem_base, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2),
@@ -359,8 +369,11 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(s_full);
+        }
+        __syncwarp();
         mbar_wait(p_full, par);
         tc_fence_after();
+        if (elect_one()) {
         if (!BWD) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // O = P V  (keys in blocks of 16: P chunk k / 4, 32 B per step; V rows 16 k)
@@ -380,8 +393,10 @@ attn_packed_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             mm(tmem_base + 128, make_smem_desc_sw128(sds + (k >> 2) * AP_TILE, 16, 1024) + (uint64_t)((k & 3) * 2),
                make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
         }
-        umma_commit(o_full);
+        umma_commit(o_full);     // (same elected lane as the MMAs above: tcgen05.commit tracks the issuing thread's operations)
         umma_commit(in_empty);   // every operand tile of this group has been consumed
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -596,24 +611,26 @@ __global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(co
   const int my_tiles = a.tiles > tile0 ? (a.tiles - tile0 + tstride - 1) / tstride : 0;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      for (int n = 0; n < my_tiles; ++n) {
-        const int sl = n & 1;
-        const uint32_t ph = (uint32_t)(n >> 1) & 1u;
-        uint8_t* base = smem + sl * SLOT_BYTES;
-        const int row0 = (tile0 + n * tstride) * ROWS;
-        mbar_wait(in_empty + sl, ph ^ 1u);
+    // ===================================== TMA producer (whole warp in the loop, one elected lane issues) =====================================
+    for (int n = 0; n < my_tiles; ++n) {
+      const int sl = n & 1;
+      const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+      uint8_t* base = smem + sl * SLOT_BYTES;
+      const int row0 = (tile0 + n * tstride) * ROWS;
+      mbar_wait(in_empty + sl, ph ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(in_full + sl, 4 * AP_TILE);
         tma_load_2d(base + OFF_Q * AP_TILE, &tm_qkv, in_full + sl, h * AP_DH, row0);
         tma_load_2d(base + OFF_K * AP_TILE, &tm_qkv, in_full + sl, a.D + h * AP_DH, row0);
         tma_load_2d(base + OFF_V * AP_TILE, &tm_qkv, in_full + sl, 2 * a.D + h * AP_DH, row0);
         tma_load_2d(base + OFF_DO * AP_TILE, &tm_do, in_full + sl, h * AP_DH, row0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer: [S, dP of n] then [dV, dK, dQ of n - 1] =====================================
-    if (lane == 0) {
+    // (whole warp in the loop; each [MMAs + commits] group goes out from one elect.sync-elected lane, no per-instruction waterfall)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);
       constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);
@@ -626,6 +643,7 @@ __global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(co
           mbar_wait(in_full + sl, ph);
           mbar_wait(t_empty + sl, ph ^ 1u);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // S = Q K^T
             umma_bf16(tb, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
@@ -634,6 +652,8 @@ __global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(co
             umma_bf16(tb + 128, make_smem_desc_sw128(sdo, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s,
                       k > 0 ? 1u : 0u);
           umma_commit(s_full + sl);
+          }
+          __syncwarp();
         }
         if (n >= 1) {
           const int m = n - 1, sl = m & 1;
@@ -642,6 +662,7 @@ __global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(co
           const uint32_t sq = b0 + OFF_Q * AP_TILE, sk = b0 + OFF_K * AP_TILE, sdo = b0 + OFF_DO * AP_TILE, sp = b0 + OFF_P * AP_TILE, sds = b0 + OFF_DS * AP_TILE;
           mbar_wait(p_full + sl, ph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // dV = P^T dO
             umma_bf16(tb, make_smem_desc_sw128(sp, AP_TILE, 1024) + (uint64_t)(k * 128), make_smem_desc_sw128(sdo, 8192, 1024) + (uint64_t)(k * 128), idesc_tv,
@@ -656,6 +677,8 @@ __global__ void __launch_bounds__(APP_THREADS, 1) attn_packed_bwd_pipe_kernel(co
                       make_smem_desc_sw128(sk, 8192, 1024) + (uint64_t)(k * 128), idesc_kv, k > 0 ? 1u : 0u);
           umma_commit(o_full + sl);
           umma_commit(in_empty + sl);
+          }
+          __syncwarp();
         }
       }
     }
@@ -817,7 +840,7 @@ int launch_packed_bwd_pipe(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, 
   return 0;
 }
 
-template <bool BWD, int SLOT, bool PAIR>
+template <bool BWD, int SLOT, bool PAIR, bool EVAL3 = false>
 int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const __nv_bfloat16* dctx, const __nv_bfloat16* dctx_lo, const uint32_t* keymask,
                   int R, int D, int H, __nv_bfloat16* out, __nv_bfloat16* out_lo, float* dbias, const DropoutCfg& drop, cudaStream_t st) {
   constexpr int NS = 127 / SLOT;
@@ -839,15 +862,15 @@ int launch_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, const _
   const size_t smem = (size_t)(BWD ? 7 : 3) * (PAIR ? 2 : 1) * AP_TILE + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_packed_kernel<BWD, SLOT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLIPDLM_CUDA_OK(cudaFuncSetAttribute(attn_packed_kernel<BWD, SLOT, PAIR, EVAL3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  // grid: a multiple of H (every CTA keeps one head), at most (2 | 4) CTAs per SM (half that in split precision), at most one CTA per (tile, head)
-  long long per_head = (((BWD ? 2LL : 4LL) / (PAIR ? 2 : 1)) * num_sms()) / H;
+  // grid: a multiple of H (every CTA keeps one head), at most ap_ctas_per_sm() CTAs per SM (half that in split precision), at most one CTA per (tile, head)
+  long long per_head = ((long long)ap_ctas_per_sm<BWD, PAIR, EVAL3>() * num_sms()) / H;
   if (per_head < 1) per_head = 1;
   if (per_head > a.tiles) per_head = a.tiles;
   const int grid = (int)(per_head * H);
-  CLIPDLM_CUDA_OK(launch_pdl(attn_packed_kernel<BWD, SLOT, PAIR>, dim3(grid), dim3(AP_THREADS), smem, st, tm_qkv, tm_do, tm_qkv_lo, tm_do_lo, a));
+  CLIPDLM_CUDA_OK(launch_pdl(attn_packed_kernel<BWD, SLOT, PAIR, EVAL3>, dim3(grid), dim3(AP_THREADS), smem, st, tm_qkv, tm_do, tm_qkv_lo, tm_do_lo, a));
   return 0;
 }
 
@@ -872,6 +895,10 @@ int launch_attn_packed(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, co
   if (BWD && g_packed_bwd_pipe && H <= num_sms()) {
     if (L == 16) return launch_packed_bwd_pipe<16>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
     return launch_packed_bwd_pipe<18>(qkv, dctx, keymask, R, D, H, out, dbias, drop, st);
+  }
+  if (!BWD && drop.thresh16 == 0) {   // eval / denoise forward: three CTAs per SM
+    if (L == 16) return launch_packed<false, 16, false, true>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
+    return launch_packed<false, 18, false, true>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
   }
   if (L == 16) return launch_packed<BWD, 16, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);
   return launch_packed<BWD, 18, false>(qkv, nullptr, dctx, nullptr, keymask, R, D, H, out, nullptr, dbias, drop, st);

@@ -189,21 +189,24 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      for (long long n = 0; n < my_groups; ++n) {
-        const long long grp = blockIdx.x + n * gridDim.x;
-        const int h = (int)(grp % a.H), r0 = (int)(grp / a.H) * NS;
-        mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+    // (the whole warp walks the loop, one elect.sync-elected lane issues: no ELECT / BRA.U.ANY waterfall per TMA / tcgen05 instruction)
+    for (long long n = 0; n < my_groups; ++n) {
+      const long long grp = blockIdx.x + n * gridDim.x;
+      const int h = (int)(grp % a.H), r0 = (int)(grp / a.H) * NS;
+      mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(in_full, NLOADS * AU_TILE);   // full boxes: rows >= L and sequences >= R arrive as zeros
         tma_load_3d(smem + OFF_Q * AU_TILE, &tm_qkv, in_full, h * AU_DH, 0, r0);
         tma_load_3d(smem + OFF_K * AU_TILE, &tm_qkv, in_full, a.D + h * AU_DH, 0, r0);
         tma_load_3d(smem + OFF_V * AU_TILE, &tm_qkv, in_full, 2 * a.D + h * AU_DH, 0, r0);
         if (BWD) tma_load_3d(smem + OFF_DO * AU_TILE, &tm_do, in_full, h * AU_DH, 0, r0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // Whole warp in the loop; each [MMAs + commits] group goes out from one elected lane (a commit sits with the MMAs it tracks).
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S, dP: both operands K-major (contraction over the head dim)
       constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);    // O = P V, dQ = dS K: A K-major, B MN-major
       constexpr uint32_t idesc_tv = make_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q: both MN-major
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
         mbar_wait(in_full, par);
         mbar_wait(t_empty, par ^ 1u);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S = Q K^T
           umma_bf16(tmem_base, make_smem_desc_sw128(sq, 16, 1024) + (uint64_t)(k * 2), make_smem_desc_sw128(sk, 16, 1024) + (uint64_t)(k * 2),
@@ -225,8 +229,11 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
                       make_smem_desc_sw128(sv, 16, 1024) + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(s_full);
+        }
+        __syncwarp();
         mbar_wait(p_full, par);
         tc_fence_after();
+        if (elect_one()) {
         if (!BWD) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // O = P V  (keys in blocks of 16: P chunk k / 4, 32 B per step; V rows 16 k)
@@ -248,6 +255,8 @@ __global__ void __launch_bounds__(AU_THREADS, BWD ? 2 : 4) attn_umma_kernel(cons
         }
         umma_commit(o_full);
         umma_commit(in_empty);   // every operand tile of this group has been consumed
+        }
+        __syncwarp();
       }
     }
   } else {

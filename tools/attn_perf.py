@@ -2,7 +2,7 @@
 """Micro-benchmark of the attention kernels at the train-chunk shape (R = 8192 sequences x L = 18, 12 heads): paths 0 (tcgen05, back-to-back
 packed sequences; backward also with the folded bias gradients), 3 (tcgen05, 32-row slots), 2 (mma.sync TMA ring), with and without dropout. Triage tool.
 CLIPDLM_ATTN_BWD_CONSUMERS=9..11 overrides the consumer-warp count of the TMA-ring backward (default 10).
-SEQ / DIM / ROWS env vars select other shapes (SEQ > 32: the one- / two-sequence-per-tile tcgen05 kernels, e.g. SEQ=66 DIM=1024)."""
+ATTN_PATHS=0,4 restricts the paths; SEQ / DIM / ROWS env vars select other shapes (SEQ > 32: the one- / two-sequence-per-tile tcgen05 kernels, e.g. SEQ=66 DIM=1024)."""
 import ctypes as C
 import os
 import sys
@@ -46,7 +46,8 @@ def timeit(fn, iters=20):
 fwd_bytes, bwd_bytes = R * Ls * D * 2 * 4, R * Ls * D * 2 * 7
 dbias = torch.zeros(3 * D, device=DEV)
 folded = (C.c_int32 * 1)()
-for path in ((0, 4, 3, 2) if Ls <= 32 else (0,)):
+PATHS = tuple(int(x) for x in os.environ["ATTN_PATHS"].split(",")) if os.environ.get("ATTN_PATHS") else None
+for path in (PATHS or ((0, 4, 3, 2) if Ls <= 32 else (0,))):
     lib.clipdlm_attn_force_simt(path)
     for p in (0.0, 0.1):
         f = timeit(lambda: L.check(lib.clipdlm_attn_fwd(C.byref(bq), km.data_ptr(), R, Ls, D, H, C.byref(bc), 1, 1, p, st)))
