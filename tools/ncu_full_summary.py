@@ -30,6 +30,8 @@ def main():
     w = csv.writer(sys.stdout)
     w.writerow(["capture", "id", "kernel", "grid", "block"] + [m[1] for m in METRICS] + [m[1] + "_unit" for m in METRICS if m[1] in ("time", "dram_read", "dram_write", "sm_clock")])
     for path in sorted(glob.glob(os.path.join(d, f"{tag}_full_*.csv"))):
+        if path.endswith("_source.csv"):   # the per-instruction source-page exports of tools/ncu_capture.sh have another layout
+            continue
         rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
         if len(rows) < 3:
             continue
