@@ -244,13 +244,16 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       // bias of this chunk's 32 columns. Default: straight from global memory - every lane reads the same 16 bytes (one L1 wavefront per
       // load, the tile's 1 KB stays L1-resident), so the per-tile fill of a shared bias array and its two epilogue-wide bar.syncs go away
       // (ncu source view: 8 % of the epilogue warps' samples on the lin1 forward GEMM sat at those barriers). Debug bit 13: the shared array.
+      // A plain ld.global, NOT ld.global.nc: the bias is a trainable parameter the optimizer kernel of the previous step rewrites, and under
+      // programmatic dependent launch this grid is resident before that kernel has finished - "read-only for the lifetime of the kernel" does
+      // not hold (the .nc version let the fused data-parallel step and the NCCL step drift apart by 7.6e-4 in three steps on two GPUs).
       const uint32_t sb = sbias_u32 + cc * 128;
       const float* gb = g.bias + col0 + cc * 32;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 b4;
         if (g.dbg & 8192u) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + j * 16));
-        else asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "l"(gb + j * 4));
+        else asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "l"(gb + j * 4) : "memory");
         upk2(add2(pk2(v[4 * j], v[4 * j + 1]), pk2(b4.x, b4.y)), v[4 * j], v[4 * j + 1]);
         upk2(add2(pk2(v[4 * j + 2], v[4 * j + 3]), pk2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
       }
