@@ -32,7 +32,7 @@ int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b
 int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, long long rows, int D,
                            const clipdlm_bf_t* dz, float* dw, float* db, unsigned long long seed, uint32_t site_out, float p_out,
                            const clipdlm_bf_t* dz_drop, uint32_t site_in, float p_in, const clipdlm_bf_t* gelu_u, float* dbias,
-                           cudaStream_t st, int gelu_stored = 0);
+                           cudaStream_t st);
 int colsum_dispatch(const clipdlm_bf_t* x, long long rows, int N, float* out, cudaStream_t st);
 int embed_loss_dispatch(const clipdlm_bf_t* x_out, const float* emb, const int* ids, const float* tgt, int tgt_rows, int R, int B, int Ltxt,
                         int L, int D, int kind, long long R_total, int batch_size, float weight, double* loss_acc, const clipdlm_bf_t* dx,

@@ -27,7 +27,7 @@ int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b
 int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, long long rows, int D,
                            const clipdlm_bf_t* dz, float* dw, float* db, unsigned long long seed, uint32_t site_out, float p_out,
                            const clipdlm_bf_t* dz_drop, uint32_t site_in, float p_in, const clipdlm_bf_t* gelu_u, float* dbias,
-                           cudaStream_t st, int gelu_stored = 0);
+                           cudaStream_t st);
 int colsum_dispatch(const clipdlm_bf_t* x, long long rows, int N, float* out, cudaStream_t st);
 int ce_row_terms_dispatch(const float* lse, const float* exp_shift, const int* targets, int tgt_period, float scale, int M, const void* w,
                           long long ldw, void* dx, long long ldx, int scatter_len, int scatter_stride, int D, float* row_scale, cudaStream_t st,
@@ -365,8 +365,6 @@ static int forward_impl(clipdlm_engine* e, const clipdlm_pass_t* p, cudaStream_t
   }
   clipdlm_gemm_t g = linear_fwd(e->h[NL], shadow(e, CLIPDLM_P_VT_W), param(e, CLIPDLM_P_VT_B), T, D, D, e->uv);
   g.out2_hi = e->gv.hi; g.out2_lo = e->gv.lo;
-  const bool head_deriv = gelu_deriv && e->uv.hi != nullptr;
-  if (head_deriv) g.epilogue = CLIPDLM_EPI_STORE_GELU_DERIV;   // uv receives gelu'(u): vocab_layer_norm's backward multiplies instead of evaluating it
   RUNG(g);
   RUNP(CLIPDLM_PROF_LN_FWD, 0, (double)T * 2 * D * (e->pair ? 4.0 : 2.0), layernorm_fwd_dispatch(&e->gv, param(e, CLIPDLM_P_VLN_W), param(e, CLIPDLM_P_VLN_B), c.ln_eps, T, D, &e->xo, p->x_out, 0, 0, 0.f, st));
   e->last = *p;
@@ -406,7 +404,7 @@ static int backward_from_g0(clipdlm_engine* e, cudaStream_t st) {
   (void)Ltxt;
   // 3. MLM transform head: x_out = LN_v(gelu(h W_t^T + b_t))
   RUNP(CLIPDLM_PROF_LN_BWD, 0, (double)T * 3 * D * (e->pair ? 4.0 : 2.0), layernorm_bwd_dispatch(&e->gv, &e->g0, param(e, CLIPDLM_P_VLN_W), c.ln_eps, T, D, &e->g1, grad(e, CLIPDLM_P_VLN_W),
-                             grad(e, CLIPDLM_P_VLN_B), 0, 0, 0.f, nullptr, 0, 0.f, &e->uv, grad(e, CLIPDLM_P_VT_B), st, e->last_gelu_deriv));
+                             grad(e, CLIPDLM_P_VLN_B), 0, 0, 0.f, nullptr, 0, 0.f, &e->uv, grad(e, CLIPDLM_P_VT_B), st));
   clipdlm_gemm_t g = linear_wgrad(e->g1, e->h[NL], T, D, D, grad(e, CLIPDLM_P_VT_W));
   RUNG(g);
   g = linear_dgrad(e->g1, shadow(e, CLIPDLM_P_VT_W), T, D, D, e->g0);

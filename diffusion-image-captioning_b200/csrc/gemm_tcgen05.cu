@@ -241,12 +241,10 @@ __device__ __forceinline__ void epi_store_fast(const GemmArgs& g, uint32_t taddr
       for (int j = 0; j < 16; ++j) upk2(mul2(pk2(v[2 * j], v[2 * j + 1]), rs2), v[2 * j], v[2 * j + 1]);
     }
     if (BIAS) {
-      // bias of this chunk's 32 columns. Default: straight from global memory - every lane reads the same 16 bytes (one L1 wavefront per
-      // load, the tile's 1 KB stays L1-resident), so the per-tile fill of a shared bias array and its two epilogue-wide bar.syncs go away
-      // (ncu source view: 8 % of the epilogue warps' samples on the lin1 forward GEMM sat at those barriers). Debug bit 13: the shared array.
-      // A plain ld.global, NOT ld.global.nc: the bias is a trainable parameter the optimizer kernel of the previous step rewrites, and under
-      // programmatic dependent launch this grid is resident before that kernel has finished - "read-only for the lifetime of the kernel" does
-      // not hold (the .nc version let the fused data-parallel step and the NCCL step drift apart by 7.6e-4 in three steps on two GPUs).
+      // bias of this chunk's 32 columns: from the per-tile shared array (default), or - experiment, host debug bit 13 - straight from global
+      // memory: every lane reads the same 16 bytes (one L1 wavefront per load), so the per-tile fill and its two epilogue-wide bar.syncs go
+      // away (ncu source view: 8 % of the epilogue warps' samples on the lin1 forward GEMM sat at those barriers; -1.5 to -3.5 % per launch).
+      // Never ld.global.nc: the bias is a trainable parameter, and the non-coherent path served stale values (gemm_dispatch).
       const uint32_t sb = sbias_u32 + cc * 128;
       const float* gb = g.bias + col0 + cc * 32;
 #pragma unroll
@@ -557,7 +555,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's readers done
         for (int i = threadIdx.x - 128; i < BN; i += 32 * EPI_WARPS) {
           const int n = n_blk * BN + i;
-          sbias[i] = n < g.N ? g.bias[n] : 0.f;
+          sbias[i] = n < g.N ? __ldcg(g.bias + n) : 0.f;   // L2 (coherence point of the optimizer's peer / multicast stores), not L1
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
@@ -1227,7 +1225,12 @@ int gemm_dispatch(const clipdlm_gemm_t* g, cudaStream_t st) {
   if (g->epilogue == CLIPDLM_EPI_LSE_EXP) ga.lse = g->exp_shift;
   if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) ga.lse = g->row_scale;
   ga.dbg = g_dbg_flags;
-  if (g->bias != nullptr && (reinterpret_cast<uintptr_t>(g->bias) & 15) != 0) ga.dbg |= 8192u;   // 16-byte bias loads need an aligned bias vector: else the shared array
+  // Bias of the specialised epilogues: the per-tile shared-memory array (kernel bit 13 set) unless debug bit 13 asks for direct global loads
+  // (and the bias vector is 16-byte aligned). The direct loads measured 1.5-3.5 % faster on the bias GEMMs, but tests/test_dp_fused_gpu.py
+  // (two GPUs, fused optimizer step against the NCCL step) diverged with them - with ld.global.nc on both exchange paths, with a plain
+  // ld.global still on the peer-store path - so they stay an opt-in experiment until that is understood.
+  if (g_dbg_flags & 8192u) ga.dbg &= ~8192u; else ga.dbg |= 8192u;
+  if (g->bias != nullptr && (reinterpret_cast<uintptr_t>(g->bias) & 15) != 0) ga.dbg |= 8192u;
   ga.fast_mode = -1;
   if (g->epilogue == CLIPDLM_EPI_STORE_ROWSCALE) {
     CLIPDLM_CHECK(g->row_scale && g->out_hi && g->res_hi && !g->bias && !g->u_hi && !g->out2_hi && !g->out_f32 && !g->out_lo && !g->res_lo &&

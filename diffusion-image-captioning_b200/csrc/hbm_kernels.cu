@@ -337,7 +337,6 @@ struct LnBwdArgs {
   BfPtr dz_drop;         // optional second output dz * mask_in / (1 - p_in)
   DropoutCfg drop_in;
   CBfPtr gelu_u;         // optional: dz *= gelu'(u)   (MLM transform head: z = gelu(u))
-  int gelu_stored;       // gelu_u already holds gelu'(u) (the forward ran STORE_GELU_DERIV): multiply, do not evaluate
   float* dbias;          // optional: += column sums of (dz_drop if set else dz)   -> bias grad of the producing Linear
 };
 
@@ -434,7 +433,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const LnBwdArgs a
         float u[8];
         load8(a.gelu_u, off, u);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] *= a.gelu_stored ? u[i] : dgelu_f(u[i]);
+        for (int i = 0; i < 8; ++i) d[i] *= dgelu_f(u[i]);
       }
       store8(a.dz, off, d);
       if (a.dz_drop.hi != nullptr) {
@@ -579,15 +578,10 @@ __global__ void __launch_bounds__(128, NV <= 3 ? 3 : 2) layernorm_bwd_fast_kerne
       if (GELU) {
         const uint4 ur = *reinterpret_cast<const uint4*>(a.gelu_u.hi + off);
         const uint32_t uw[4] = {ur.x, ur.y, ur.z, ur.w};
-        if (a.gelu_stored) {   // the forward stored gelu'(u): 1 multiply instead of a degree-6 polynomial + two EX2 per element (2.5 x on this launch)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) d[i] = mul2(d[i], bf2_to_f2(uw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 u = unpack_bf16x2(uw[i]);
-            d[i] = mul2(d[i], pk2(dgelu_f(u.x), dgelu_f(u.y)));
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float2 u = unpack_bf16x2(uw[i]);
+          d[i] = mul2(d[i], pk2(dgelu_f(u.x), dgelu_f(u.y)));
         }
       }
       *reinterpret_cast<uint4*>(a.dz.hi + off) = make_uint4(f2_to_bf2(d[0]), f2_to_bf2(d[1]), f2_to_bf2(d[2]), f2_to_bf2(d[3]));
@@ -1065,7 +1059,7 @@ int layernorm_fwd_dispatch(const clipdlm_bf_t* z, const float* w, const float* b
 int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const float* w, float eps, long long rows, int D,
                            const clipdlm_bf_t* dz, float* dw, float* db, unsigned long long seed, uint32_t site_out, float p_out,
                            const clipdlm_bf_t* dz_drop, uint32_t site_in, float p_in, const clipdlm_bf_t* gelu_u, float* dbias,
-                           cudaStream_t st, int gelu_stored) {
+                           cudaStream_t st) {
   CLIPDLM_CHECK(z && z->hi && dy && dy->hi && w && dz && dz->hi && rows > 0, "layernorm_bwd: bad arguments");
   LnBwdArgs a;
   a.z = cbf(z); a.dy = cbf(dy); a.w = w; a.eps = eps; a.rows = rows; a.D = D;
@@ -1074,7 +1068,6 @@ int layernorm_bwd_dispatch(const clipdlm_bf_t* z, const clipdlm_bf_t* dy, const 
   a.dz_drop = (dz_drop && p_in > 0.f) ? mbf(dz_drop) : mbf(nullptr);
   a.drop_in = make_drop(seed, site_in, p_in);
   a.gelu_u = cbf(gelu_u);
-  a.gelu_stored = gelu_stored;
   a.dbias = dbias;
   long long want = (rows + 3) / 4;
   int grid = (int)(want < 3LL * num_sms() ? want : 3LL * num_sms());  // 3 resident CTAs of 4 warps per SM (register-limited)

@@ -88,7 +88,7 @@ int clipdlm_gemm(const clipdlm_gemm_t* g, clipdlm_stream stream);
 /* Debug hook for bring-up: override the MN-major smem descriptor strides (bytes); 0,0 restores defaults. */
 void clipdlm_gemm_debug_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes);
 /* Debug hook for performance triage (tools/gemm_perf.py): bit 0 = drop the epilogue's global stores, bit 1 = drop its auxiliary
- * operand loads (residual / gelu' input), bit 2 = drain TMEM only (no epilogue math), bit 3 = force single-CTA tiles (cta_group::1), bit 4 = issue no MMAs, bit 5 = issue no TMA loads, bit 6 = use the generic STORE epilogue where a specialised one exists, bit 9 = launch GEMMs without programmatic dependent launch, bit 10 = row-wise global stores instead of TMA stores in the specialised epilogue, bit 12 = no band tile order in the lm_head passes, bit 13 = the specialised epilogues read the bias from a per-tile shared-memory array (two epilogue-wide barriers per tile) instead of global memory. 0 restores normal operation. */
+ * operand loads (residual / gelu' input), bit 2 = drain TMEM only (no epilogue math), bit 3 = force single-CTA tiles (cta_group::1), bit 4 = issue no MMAs, bit 5 = issue no TMA loads, bit 6 = use the generic STORE epilogue where a specialised one exists, bit 9 = launch GEMMs without programmatic dependent launch, bit 10 = row-wise global stores instead of TMA stores in the specialised epilogue, bit 12 = no band tile order in the lm_head passes, bit 13 = experiment: the specialised epilogues read the bias straight from global memory instead of the per-tile shared-memory array (two epilogue-wide barriers per tile). 0 restores normal operation. */
 void clipdlm_gemm_debug_flags(uint32_t flags);
 
 /* Reduce LSE partials: lse[m], argmax[m] (may be NULL), and adds sum_m(lse[m] - tgt_logit[m]) * scale to *loss_acc (double).
