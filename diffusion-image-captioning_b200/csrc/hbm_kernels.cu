@@ -39,6 +39,15 @@ __device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+// Coherent variant for TRAINABLE parameters read by kernels launched with programmatic dependent launch (the fast LayerNorm kernels): __ldg /
+// ld.global.nc is outside the acquire griddepcontrol.wait performs, and a parameter is rewritten by the optimizer between two launches of the
+// same kernel - the GEMM epilogues' bias served stale values that way. Plain ld.global, immune to const / __restrict__ inference.
+__device__ __forceinline__ void load8_f32_coherent(const float* p, float (&v)[8]) {
+  float4 a, b;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 __device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
@@ -270,8 +279,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_fwd_fast_kernel(const __nv_b
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     float wv[8], bv[8];
-    load8_f32(w + (v * 32 + lane) * 8, wv);
-    load8_f32(b + (v * 32 + lane) * 8, bv);
+    load8_f32_coherent(w + (v * 32 + lane) * 8, wv);
+    load8_f32_coherent(b + (v * 32 + lane) * 8, bv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { W[v][i] = pk2(wv[2 * i], wv[2 * i + 1]); B[v][i] = pk2(bv[2 * i], bv[2 * i + 1]); }
   }
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(128, NV <= 3 ? 3 : 2) layernorm_bwd_fast_kerne
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     float wv[8];
-    load8_f32(a.w + (v * 32 + lane) * 8, wv);
+    load8_f32_coherent(a.w + (v * 32 + lane) * 8, wv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) W[v][i] = pk2(wv[2 * i], wv[2 * i + 1]);
   }

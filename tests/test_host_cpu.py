@@ -36,6 +36,25 @@ def test_sass_is_blackwell_native():
     assert "UTMALDG" in sass
     assert "LDTM" in sass
     assert "sm_100a" in sass
+    # Regression guards read off the same dump (second session of round 2):
+    # (1) no non-coherent global load in a tcgen05 GEMM / attention kernel - their only scalar global loads besides streamed activations are
+    #     trainable parameters (biases), and LDG.E.CONSTANT (ld.global.nc) served stale biases under programmatic dependent launch chains;
+    # (2) the MMA issuers issue under elect.sync with the whole warp in the loop: a `lane == 0` loop wraps every UTCHMMA in an ELECT / R2UR /
+    #     BRA.U.ANY waterfall (one ELECT per MMA and more), the converged loops keep a handful per kernel.
+    fn, nc, elect, mma = None, {}, {}, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and ("11gemm_kernelI" in fn or "attn_packed" in fn or "attn_umma" in fn or ("layernorm_" in fn and "fast" in fn)):
+            # = the kernels launched with programmatic dependent launch (not small_gemm_kernel & co: plain launches)
+            if "LDG" in line and "CONSTANT" in line:
+                nc[fn] = nc.get(fn, 0) + 1
+            if " ELECT " in line:
+                elect[fn] = elect.get(fn, 0) + 1
+            if "UTCHMMA" in line:
+                mma[fn] = mma.get(fn, 0) + 1
+    assert not nc, f"non-coherent loads in {sorted(nc)[:3]}"
+    assert mma and all(elect.get(f, 0) <= 12 for f in mma), {f: (elect.get(f, 0), n) for f, n in mma.items() if elect.get(f, 0) > 12}
 
 
 def test_param_layout_matches_reference_counts():
