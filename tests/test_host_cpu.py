@@ -45,7 +45,7 @@ def test_sass_is_blackwell_native():
     for line in sass.splitlines():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
-        elif fn and ("11gemm_kernelI" in fn or "attn_packed" in fn or "attn_umma" in fn or ("layernorm_" in fn and "fast" in fn)):
+        elif fn and ("11gemm_kernelI" in fn or "attn_packed" in fn or "attn_umma" in fn or "attn_ring" in fn or ("layernorm_" in fn and "fast" in fn)):
             # = the kernels launched with programmatic dependent launch (not small_gemm_kernel & co: plain launches)
             if "LDG" in line and "CONSTANT" in line:
                 nc[fn] = nc.get(fn, 0) + 1
